@@ -1,0 +1,751 @@
+// pano_oracle.cpp — CPU ORACLE (test infrastructure, NOT product code).
+//
+// A plain C++17 restatement, without OpenCV, of the serial stitching path of the
+// reference (`src/serial/main.cpp`, cited per function below as "ref:").  It exists only
+// so that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs can check and time the CUDA engine against the reference's semantics.  Nothing in
+// the product path (the package's csrc/, the C ABI, the CLI) may link or call this file.
+//
+// One deliberate deviation from the reference: `std::mt19937 rng(rd())`
+// (ref: src/serial/main.cpp:264-265) becomes `std::mt19937 rng(seed)` with the seed passed
+// in, so runs are reproducible.  The shuffle itself is the real libstdc++ std::shuffle.
+//
+// The reference cannot be compiled here (every target needs OpenCV C++, which is absent),
+// so the OpenCV routines on the path are restated from their published algorithms
+// (OpenCV 4.x: cvtColor BGR2GRAY, findHomography 4-point path = normalised DLT + Jacobi
+// eigen, gemm small-matrix path, Mat /= scalar, cv::norm(Point2f), perspectiveTransform,
+// invert 3x3, warpPerspective INTER_LINEAR/BORDER_CONSTANT).  Parity pin: each restated
+// routine is checked bit-for-bit against the real routines of Python cv2 4.13.0 by
+// oracle/gen_golden.py and tests/test_oracle_vs_golden.py (fixtures in tests/golden/).
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off; no -march so no FMA is emitted,
+// matching the reference's x86-64 baseline build).
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <random>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+struct Match {  // the three cv::DMatch fields the path uses (ref: src/serial/main.cpp:237)
+  int32_t queryIdx;
+  int32_t trainIdx;
+  float distance;
+};
+
+// ---------------------------------------------------------------------------------------
+// cv::cvtColor(BGR2GRAY) for 8-bit input: 15-bit fixed point, coefficients B 3735, G 19235,
+// R 9798 (sum 32768), rounding constant 1<<14.   ref: src/serial/main.cpp:123-129
+// ---------------------------------------------------------------------------------------
+inline uint8_t gray_of(const uint8_t* p) {
+  return (uint8_t)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15);
+}
+
+// ref: src/serial/main.cpp:73-91  getGaussianKernel(5, 1.0)
+void gaussian_kernel(int ksize, double sigma, std::vector<double>& k) {
+  k.assign((size_t)ksize * ksize, 0.0);
+  double sum = 0.0;
+  int half = ksize / 2;
+  for (int i = 0; i < ksize; ++i) {
+    int x = i - half;
+    for (int j = 0; j < ksize; ++j) {
+      int y = j - half;
+      k[(size_t)i * ksize + j] = exp(-(x * x + y * y) / (2 * sigma * sigma));
+      sum += k[(size_t)i * ksize + j];
+    }
+  }
+  for (auto& e : k) e /= sum;
+}
+
+// ref: src/serial/main.cpp:96-116  convolveSequential — correlation, zero border of k px,
+// single accumulator, i (rows) outer, j (cols) inner, separate rounded multiply and add.
+void convolve(const double* in, int w, int h, const double* kern, int ksize, double* out) {
+  int k = ksize / 2;
+  std::fill(out, out + (size_t)w * h, 0.0);
+  for (int y = k; y < h - k; y++) {
+    for (int x = k; x < w - k; x++) {
+      double sum = 0.0;
+      for (int i = -k; i <= k; i++)
+        for (int j = -k; j <= k; j++)
+          sum += in[(size_t)(y + i) * w + (x + j)] * kern[(k + i) * ksize + (k + j)];
+      out[(size_t)y * w + x] = sum;
+    }
+  }
+}
+
+// ref: src/serial/main.cpp:119-155 — gray, Sobel, products, Gaussian, response.
+void harris_response(const uint8_t* bgr, int w, int h, size_t stride, double kparam,
+                     std::vector<double>& resp) {
+  size_t n = (size_t)w * h;
+  std::vector<double> gray(n), gx(n), gy(n), xx(n), yy(n), xy(n), t(n);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) gray[(size_t)y * w + x] = gray_of(bgr + y * stride + 3 * x);
+  const double sobx[9] = {-1, 0, 1, -2, 0, 2, -1, 0, 1};
+  const double soby[9] = {-1, -2, -1, 0, 0, 0, 1, 2, 1};
+  std::vector<double> g5;
+  gaussian_kernel(5, 1.0, g5);
+  convolve(gray.data(), w, h, sobx, 3, gx.data());
+  convolve(gray.data(), w, h, soby, 3, gy.data());
+  for (size_t i = 0; i < n; i++) {
+    xx[i] = gx[i] * gx[i];
+    yy[i] = gy[i] * gy[i];
+    xy[i] = gx[i] * gy[i];
+  }
+  convolve(xx.data(), w, h, g5.data(), 5, t.data()); xx.swap(t);
+  convolve(yy.data(), w, h, g5.data(), 5, t.data()); yy.swap(t);
+  convolve(xy.data(), w, h, g5.data(), 5, t.data()); xy.swap(t);
+  resp.assign(n, 0.0);
+  for (size_t i = 0; i < n; i++) {
+    double det = xx[i] * yy[i] - xy[i] * xy[i];
+    double trace = xx[i] + yy[i];
+    resp[i] = det - kparam * trace * trace;
+  }
+}
+
+// ref: src/serial/main.cpp:157-180 — threshold + strict NMS, row-major order.
+void nms(const double* resp, int w, int h, double thresh, int nbhd, std::vector<int32_t>& xy) {
+  int halfLen = nbhd / 2;
+  for (int y = halfLen; y < h - halfLen; y++) {
+    for (int x = halfLen; x < w - halfLen; x++) {
+      double r = resp[(size_t)y * w + x];
+      if (r <= thresh) continue;
+      double max_resp = std::numeric_limits<double>::lowest();
+      bool skip = false;
+      for (int i = -halfLen; i <= halfLen && !skip; i++) {
+        for (int j = -halfLen; j <= halfLen; j++) {
+          if (i == 0 && j == 0) continue;
+          max_resp = std::max(max_resp, resp[(size_t)(y + i) * w + (x + j)]);
+          if (max_resp > r) { skip = true; break; }
+        }
+      }
+      if (skip) continue;
+      if (r > max_resp) { xy.push_back(x); xy.push_back(y); }
+    }
+  }
+}
+
+// ref: src/serial/main.cpp:188-244 — brute-force SSD over patch x patch x 3 u8, first strict
+// minimum, in-border test on both sides, threshold on the best SSD.
+void match_keypoints(const int32_t* kq, int nq, const int32_t* kt, int nt,
+                     const uint8_t* imq, int wq, int hq, size_t sq,
+                     const uint8_t* imt, int wt, int ht, size_t st,
+                     int patch, double maxSSD, int offset, std::vector<Match>& out) {
+  int border = patch / 2;
+  // pre-gather in-border train patches (pure re-ordering of loads; same arithmetic)
+  std::vector<int> tj;
+  std::vector<uint8_t> tp;
+  int plen = patch * patch * 3;
+  for (int j = 0; j < nt; j++) {
+    int x = kt[2 * j], y = kt[2 * j + 1];
+    if (x < border || y < border || x + border >= wt || y + border >= ht) continue;
+    tj.push_back(j);
+    size_t o = tp.size();
+    tp.resize(o + plen);
+    uint8_t* d = &tp[o];
+    for (int dy = -border; dy <= border; dy++)
+      for (int dx = -border; dx <= border; dx++)
+        for (int c = 0; c < 3; c++) *d++ = imt[(size_t)(y + dy) * st + 3 * (x + dx) + c];
+  }
+  std::vector<Match> res((size_t)nq);
+  std::vector<uint8_t> has((size_t)nq, 0);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+  for (int i = 0; i < nq; i++) {
+    int x = kq[2 * i], y = kq[2 * i + 1];
+    if (x < border || y < border || x + border >= wq || y + border >= hq) continue;
+    std::vector<uint8_t> qp((size_t)plen);
+    {
+      uint8_t* d = qp.data();
+      for (int dy = -border; dy <= border; dy++)
+        for (int dx = -border; dx <= border; dx++)
+          for (int c = 0; c < 3; c++) *d++ = imq[(size_t)(y + dy) * sq + 3 * (x + dx) + c];
+    }
+    int best = -1;
+    uint64_t bestSSD = std::numeric_limits<uint64_t>::max();
+    for (size_t jj = 0; jj < tj.size(); jj++) {
+      const uint8_t* t = &tp[jj * plen];
+      uint32_t ssd = 0;
+      for (int e = 0; e < plen; e++) {
+        int d = (int)qp[e] - (int)t[e];
+        ssd += (uint32_t)(d * d);
+      }
+      if ((uint64_t)ssd < bestSSD) { bestSSD = ssd; best = tj[jj]; }
+    }
+    if ((double)bestSSD < maxSSD) {
+      res[i] = Match{i + offset, best, (float)bestSSD};
+      has[i] = 1;
+    }
+  }
+  for (int i = 0; i < nq; i++)
+    if (has[i]) out.push_back(res[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// cv::eigen for a symmetric n x n double matrix when OpenCV is built without Eigen/LAPACK
+// eigen solvers: cyclic-by-pivot Jacobi (OpenCV modules/core/src/lapack.cpp JacobiImpl_).
+// Eigenvalues sorted descending, eigenvectors as rows of V.
+// ---------------------------------------------------------------------------------------
+// OpenCV's own hypot (core/src/lapack.cpp), used by its Jacobi instead of libm's.
+inline double cv_hypot(double a, double b) {
+  a = std::abs(a);
+  b = std::abs(b);
+  if (a > b) {
+    b /= a;
+    return a * std::sqrt(1 + b * b);
+  }
+  if (b > 0) {
+    a /= b;
+    return b * std::sqrt(1 + a * a);
+  }
+  return 0;
+}
+
+void jacobi(double* A, int astep, double* W, double* V, int vstep, int n) {
+  const double eps = std::numeric_limits<double>::epsilon();
+  int i, j, k, m;
+  for (i = 0; i < n; i++) {
+    for (j = 0; j < n; j++) V[i * vstep + j] = 0;
+    V[i * vstep + i] = 1;
+  }
+  int iters, maxIters = n * n * 30;
+  std::vector<int> indRv(n), indCv(n);
+  int* indR = indRv.data();
+  int* indC = indCv.data();
+  double mv = 0;
+  for (k = 0; k < n; k++) {
+    W[k] = A[(astep + 1) * k];
+    if (k < n - 1) {
+      for (m = k + 1, mv = std::abs(A[astep * k + m]), i = k + 2; i < n; i++) {
+        double val = std::abs(A[astep * k + i]);
+        if (mv < val) mv = val, m = i;
+      }
+      indR[k] = m;
+    }
+    if (k > 0) {
+      for (m = 0, mv = std::abs(A[k]), i = 1; i < k; i++) {
+        double val = std::abs(A[astep * i + k]);
+        if (mv < val) mv = val, m = i;
+      }
+      indC[k] = m;
+    }
+  }
+  if (n > 1)
+    for (iters = 0; iters < maxIters; iters++) {
+      for (k = 0, mv = std::abs(A[indR[0]]), i = 1; i < n - 1; i++) {
+        double val = std::abs(A[astep * i + indR[i]]);
+        if (mv < val) mv = val, k = i;
+      }
+      int l = indR[k];
+      for (i = 1; i < n; i++) {
+        double val = std::abs(A[astep * indC[i] + i]);
+        if (mv < val) mv = val, k = indC[i], l = i;
+      }
+      double p = A[astep * k + l];
+      if (std::abs(p) <= eps) break;
+      double y = (W[l] - W[k]) * 0.5;
+      double t = std::abs(y) + cv_hypot(p, y);
+      double s = cv_hypot(p, t);
+      double c = t / s;
+      s = p / s;
+      t = (p / t) * p;
+      if (y < 0) s = -s, t = -t;
+      A[astep * k + l] = 0;
+      W[k] -= t;
+      W[l] += t;
+      double a0, b0;
+#define ROT(v0, v1) a0 = v0, b0 = v1, v0 = a0 * c - b0 * s, v1 = a0 * s + b0 * c
+      for (i = 0; i < k; i++) ROT(A[astep * i + k], A[astep * i + l]);
+      for (i = k + 1; i < l; i++) ROT(A[astep * k + i], A[astep * i + l]);
+      for (i = l + 1; i < n; i++) ROT(A[astep * k + i], A[astep * l + i]);
+      for (i = 0; i < n; i++) ROT(V[vstep * k + i], V[vstep * l + i]);
+#undef ROT
+      for (j = 0; j < 2; j++) {
+        int idx = j == 0 ? k : l;
+        if (idx < n - 1) {
+          for (m = idx + 1, mv = std::abs(A[astep * idx + m]), i = idx + 2; i < n; i++) {
+            double val = std::abs(A[astep * idx + i]);
+            if (mv < val) mv = val, m = i;
+          }
+          indR[idx] = m;
+        }
+        if (idx > 0) {
+          for (m = 0, mv = std::abs(A[idx]), i = 1; i < idx; i++) {
+            double val = std::abs(A[astep * i + idx]);
+            if (mv < val) mv = val, m = i;
+          }
+          indC[idx] = m;
+        }
+      }
+    }
+  for (k = 0; k < n - 1; k++) {
+    m = k;
+    for (i = k + 1; i < n; i++)
+      if (W[m] < W[i]) m = i;
+    if (k != m) {
+      std::swap(W[m], W[k]);
+      for (i = 0; i < n; i++) std::swap(V[vstep * m + i], V[vstep * k + i]);
+    }
+  }
+}
+
+// OpenCV gemm small-matrix path (3x3 * 3x3, alpha 1, no C): left-to-right, no FMA.
+inline void mul33(const double* a, const double* b, double* d) {
+  double r[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      r[i * 3 + j] = (a[i * 3 + 0] * b[0 + j] + a[i * 3 + 1] * b[3 + j]) + a[i * 3 + 2] * b[6 + j];
+  memcpy(d, r, sizeof r);
+}
+
+// cv::findHomography(src, dst) with method 0 and exactly 4 points == one call of
+// HomographyEstimatorCallback::runKernel (OpenCV calib3d/src/fundam.cpp): normalised DLT,
+// 9x9 LtL, smallest eigenvector via cv::eigen, de-normalise, scale by 1/h22.
+// Returns 0 (empty Mat) iff a mean-abs-deviation sum is < DBL_EPSILON.
+// ref call site: src/serial/main.cpp:279.  M = src (points1), m = dst (points2).
+int find_homography4(const float* M, const float* m, int count, double* Hout) {
+  double LtL[9][9], W[9], V[9][9];
+  double cMx = 0, cMy = 0, cmx = 0, cmy = 0, sMx = 0, sMy = 0, smx = 0, smy = 0;
+  for (int i = 0; i < count; i++) {
+    cmx += m[2 * i]; cmy += m[2 * i + 1];
+    cMx += M[2 * i]; cMy += M[2 * i + 1];
+  }
+  cmx /= count; cmy /= count; cMx /= count; cMy /= count;
+  for (int i = 0; i < count; i++) {
+    smx += fabs(m[2 * i] - cmx);
+    smy += fabs(m[2 * i + 1] - cmy);
+    sMx += fabs(M[2 * i] - cMx);
+    sMy += fabs(M[2 * i + 1] - cMy);
+  }
+  if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON ||
+      fabs(sMy) < DBL_EPSILON)
+    return 0;
+  smx = count / smx; smy = count / smy;
+  sMx = count / sMx; sMy = count / sMy;
+  double invHnorm[9] = {1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1};
+  double Hnorm2[9] = {sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1};
+  memset(LtL, 0, sizeof LtL);
+  for (int i = 0; i < count; i++) {
+    double x = (m[2 * i] - cmx) * smx, y = (m[2 * i + 1] - cmy) * smy;
+    double X = (M[2 * i] - cMx) * sMx, Y = (M[2 * i + 1] - cMy) * sMy;
+    double Lx[] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
+    double Ly[] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+    for (int j = 0; j < 9; j++)
+      for (int k = j; k < 9; k++) LtL[j][k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+  }
+  for (int i = 0; i < 9; i++)
+    for (int j = 0; j < i; j++) LtL[i][j] = LtL[j][i];  // completeSymm (upper -> lower)
+  jacobi(&LtL[0][0], 9, W, &V[0][0], 9, 9);
+  double Htemp[9], H0[9];
+  mul33(invHnorm, V[8], Htemp);
+  mul33(Htemp, Hnorm2, H0);
+  double sc = 1. / H0[8];
+  for (int i = 0; i < 9; i++) Hout[i] = H0[i] * sc;
+  return 1;
+}
+
+// Inlier predicate of ref: src/serial/main.cpp:285-293.
+//   pt2Transformed = H * (x, y, 1)      -> gemm small path, (h0*x + h1*y) + h2*1
+//   pt2Transformed /= w                  -> Mat::convertTo(-1, 1./w): multiply by reciprocal
+//   Point2f est(X, Y)                    -> double -> float casts
+//   cv::norm(est - pt2) < thr            -> float subtraction, sqrt((double)dx*dx + (double)dy*dy)
+// div_mode 0 = reciprocal multiply (OpenCV's Mat /= double), 1 = true division (diagnostic).
+inline bool is_inlier(const double* H, float x, float y, float qx, float qy, double thr,
+                      int div_mode) {
+  double X = (H[0] * x + H[1] * y) + H[2] * 1.0;
+  double Y = (H[3] * x + H[4] * y) + H[5] * 1.0;
+  double Wd = (H[6] * x + H[7] * y) + H[8] * 1.0;
+  float ex, ey;
+  if (div_mode == 0) {
+    double s = 1. / Wd;
+    ex = (float)(X * s);
+    ey = (float)(Y * s);
+  } else {
+    ex = (float)(X / Wd);
+    ey = (float)(Y / Wd);
+  }
+  float dx = ex - qx, dy = ey - qy;
+  return std::sqrt((double)dx * dx + (double)dy * dy) < thr;
+}
+
+// ref: src/serial/main.cpp:247-307 (SeqRansacHomographyCalculator::computeHomography),
+// seeded.  kp1 = query-side keypoints (right image), kp2 = train-side (left image).
+// Optional outputs: samples[iters*4] (match indices drawn, in draw order), counts[iters]
+// (inlier count, -1 where findHomography returned empty), inlier_mask[m] for the best H,
+// draws = number of 32-bit engine outputs consumed.
+int ransac(const int32_t* kp1, const int32_t* kp2, const Match* matches, int m, int iters,
+           int nsamples, double thr, uint32_t seed, int div_mode, double* Hbest, int* best_count,
+           int32_t* samples, int32_t* counts, uint8_t* inlier_mask, uint64_t* draws,
+           int* best_iter) {
+  struct CountingRng {  // forwards to mt19937, counts outputs (observer only)
+    typedef std::mt19937::result_type result_type;
+    std::mt19937 e;
+    uint64_t n = 0;
+    explicit CountingRng(uint32_t s) : e(s) {}
+    static constexpr result_type min() { return std::mt19937::min(); }
+    static constexpr result_type max() { return std::mt19937::max(); }
+    result_type operator()() { ++n; return e(); }
+  };
+  CountingRng rng(seed);
+  int bestInlierCount = 0;
+  bool have = false;
+  if (best_iter) *best_iter = -1;
+  std::vector<std::pair<Match, int32_t>> local((size_t)m);
+  for (int iter = 0; iter < iters; ++iter) {
+    if (m < nsamples) break;
+    for (int i = 0; i < m; i++) local[i] = {matches[i], i};
+    std::shuffle(local.begin(), local.end(), rng);
+    float src[8], dst[8];
+    for (int j = 0; j < nsamples && j < 4; j++) {
+      const Match& mm = local[j].first;
+      src[2 * j] = (float)kp1[2 * mm.queryIdx];
+      src[2 * j + 1] = (float)kp1[2 * mm.queryIdx + 1];
+      dst[2 * j] = (float)kp2[2 * mm.trainIdx];
+      dst[2 * j + 1] = (float)kp2[2 * mm.trainIdx + 1];
+      if (samples) samples[iter * 4 + j] = local[j].second;
+    }
+    double H[9];
+    if (!find_homography4(src, dst, 4, H)) {
+      if (counts) counts[iter] = -1;
+      continue;
+    }
+    int inlierCount = 0;
+    for (int i = 0; i < m; i++) {
+      const Match& mm = matches[i];
+      if (is_inlier(H, (float)kp1[2 * mm.queryIdx], (float)kp1[2 * mm.queryIdx + 1],
+                    (float)kp2[2 * mm.trainIdx], (float)kp2[2 * mm.trainIdx + 1], thr, div_mode))
+        inlierCount++;
+    }
+    if (counts) counts[iter] = inlierCount;
+    if (inlierCount > bestInlierCount) {
+      bestInlierCount = inlierCount;
+      memcpy(Hbest, H, sizeof H);
+      have = true;
+      if (best_iter) *best_iter = iter;
+    }
+  }
+  if (draws) *draws = rng.n;
+  if (best_count) *best_count = bestInlierCount;
+  if (have && inlier_mask) {
+    for (int i = 0; i < m; i++) {
+      const Match& mm = matches[i];
+      inlier_mask[i] = is_inlier(Hbest, (float)kp1[2 * mm.queryIdx], (float)kp1[2 * mm.queryIdx + 1],
+                                 (float)kp2[2 * mm.trainIdx], (float)kp2[2 * mm.trainIdx + 1], thr,
+                                 div_mode);
+    }
+  }
+  return have ? 1 : 0;
+}
+
+// cv::perspectiveTransform for Point2f input and a 3x3 double matrix
+// (OpenCV core/src/matmul.simd.hpp perspectiveTransform_32f).  ref: src/serial/main.cpp:342
+void perspective_transform(const float* src, int n, const double* m, float* dst) {
+  const double eps = FLT_EPSILON;
+  for (int i = 0; i < n; i++) {
+    float x = src[2 * i], y = src[2 * i + 1];
+    double w = x * m[6] + y * m[7] + m[8];
+    if (fabs(w) > eps) {
+      w = 1. / w;
+      dst[2 * i] = (float)((x * m[0] + y * m[1] + m[2]) * w);
+      dst[2 * i + 1] = (float)((x * m[3] + y * m[4] + m[5]) * w);
+    } else
+      dst[2 * i] = dst[2 * i + 1] = 0.f;
+  }
+}
+
+struct Canvas {
+  int cw, ch, offx, offy;  // canvas size; left image ROI origin = (int)(-minX), (int)(-minY)
+  double TH[9];            // translation * H
+};
+
+// ref: src/serial/main.cpp:335-369.  Returns 0 if the left ROI would not fit the canvas
+// (the reference would throw from cv::Mat::operator()(Rect)).
+int canvas_geometry(int wl, int hl, int wr, int hr, const double* H, Canvas* c) {
+  float rc[8] = {0.f, 0.f, (float)wr, 0.f, (float)wr, (float)hr, 0.f, (float)hr};
+  float wc[8];
+  perspective_transform(rc, 4, H, wc);
+  float lc[8] = {0.f, 0.f, (float)wl, 0.f, (float)wl, (float)hl, 0.f, (float)hl};
+  float minX = 0, minY = 0, maxX = (float)wl, maxY = (float)hl;
+  for (int i = 0; i < 4; i++) {
+    minX = std::min(minX, wc[2 * i]); minY = std::min(minY, wc[2 * i + 1]);
+    maxX = std::max(maxX, wc[2 * i]); maxY = std::max(maxY, wc[2 * i + 1]);
+  }
+  for (int i = 0; i < 4; i++) {
+    minX = std::min(minX, lc[2 * i]); minY = std::min(minY, lc[2 * i + 1]);
+    maxX = std::max(maxX, lc[2 * i]); maxY = std::max(maxY, lc[2 * i + 1]);
+  }
+  double T[9] = {1, 0, (double)(-minX), 0, 1, (double)(-minY), 0, 0, 1};
+  mul33(T, H, c->TH);
+  c->cw = (int)std::ceil(maxX - minX);
+  c->ch = (int)std::ceil(maxY - minY);
+  c->offx = (int)(-minX);
+  c->offy = (int)(-minY);
+  if (c->cw <= 0 || c->ch <= 0) return 0;
+  if (c->offx < 0 || c->offy < 0 || c->offx + wl > c->cw || c->offy + hl > c->ch) return 0;
+  return 1;
+}
+
+// cv::invert for 3x3 CV_64F (DECOMP_LU fast path, OpenCV core/src/lapack.cpp).
+int invert33(const double* s, double* d) {
+  double det = s[0] * (s[4] * s[8] - s[5] * s[7]) - s[1] * (s[3] * s[8] - s[5] * s[6]) +
+               s[2] * (s[3] * s[7] - s[4] * s[6]);
+  if (det == 0.) return 0;
+  det = 1. / det;
+  double t[9];
+  t[0] = (s[4] * s[8] - s[5] * s[7]) * det;
+  t[1] = (s[2] * s[7] - s[1] * s[8]) * det;
+  t[2] = (s[1] * s[5] - s[2] * s[4]) * det;
+  t[3] = (s[5] * s[6] - s[3] * s[8]) * det;
+  t[4] = (s[0] * s[8] - s[2] * s[6]) * det;
+  t[5] = (s[2] * s[3] - s[0] * s[5]) * det;
+  t[6] = (s[3] * s[7] - s[4] * s[6]) * det;
+  t[7] = (s[1] * s[6] - s[0] * s[7]) * det;
+  t[8] = (s[0] * s[4] - s[1] * s[3]) * det;
+  memcpy(d, t, sizeof t);
+  return 1;
+}
+
+inline int cv_round(double v) { return (int)lrint(v); }  // SSE2 cvtsd2si, ties-to-even
+inline short sat_short(int v) { return (short)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
+
+// cv::warpPerspective(src, dst, M, dsize) with INTER_LINEAR, BORDER_CONSTANT(0), 8UC3
+// (OpenCV imgproc/src/imgwarp.cpp WarpPerspectiveInvoker + remapBilinear fixed point):
+// M is inverted; the destination is processed in blocks (bw x bh); per block row the
+// coordinate numerators are X0 = M0*x + M1*(y+y1) + M2 at the block origin x, then
+// (X0 + M0*x1) * (32 / (W0 + M6*x1)) is rounded to an integer in 1/32-px units; bilinear
+// weights are the exact products (32-fx)(32-fy)*32 ... (15-bit), result (sum + 2^14) >> 15;
+// taps outside the source read 0.      ref call site: src/serial/main.cpp:371-372
+void warp_perspective(const uint8_t* src, int sw, int sh, size_t sstride, const double* M0,
+                      uint8_t* dst, int dw, int dh, size_t dstride) {
+  double M[9];
+  if (!invert33(M0, M)) { memset(M, 0, sizeof M); }
+  const int BLOCK_SZ = 32;
+  int bh0 = std::min(BLOCK_SZ / 2, dh);
+  int bw0 = std::min(BLOCK_SZ * BLOCK_SZ / bh0, dw);
+  bh0 = std::min(BLOCK_SZ * BLOCK_SZ / bw0, dh);
+  for (int y = 0; y < dh; y += bh0) {
+    for (int x = 0; x < dw; x += bw0) {
+      int bw = std::min(bw0, dw - x);
+      int bh = std::min(bh0, dh - y);
+      for (int y1 = 0; y1 < bh; y1++) {
+        double X0 = M[0] * x + M[1] * (y + y1) + M[2];
+        double Y0 = M[3] * x + M[4] * (y + y1) + M[5];
+        double W0 = M[6] * x + M[7] * (y + y1) + M[8];
+        uint8_t* drow = dst + (size_t)(y + y1) * dstride + 3 * (size_t)x;
+        for (int x1 = 0; x1 < bw; x1++) {
+          double W = W0 + M[6] * x1;
+          W = W ? 32. / W : 0;
+          double fX = std::max((double)INT_MIN, std::min((double)INT_MAX, (X0 + M[0] * x1) * W));
+          double fY = std::max((double)INT_MIN, std::min((double)INT_MAX, (Y0 + M[3] * x1) * W));
+          int X = cv_round(fX), Y = cv_round(fY);
+          int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+          int fx = X & 31, fy = Y & 31;
+          int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32;
+          int w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+          for (int c = 0; c < 3; c++) {
+            auto tap = [&](int yy, int xx) -> int {
+              return (xx >= 0 && xx < sw && yy >= 0 && yy < sh) ? src[(size_t)yy * sstride + 3 * xx + c] : 0;
+            };
+            int v = tap(sy, sx) * w00 + tap(sy, sx + 1) * w01 + tap(sy + 1, sx) * w10 +
+                    tap(sy + 1, sx + 1) * w11;
+            drow[3 * x1 + c] = (uint8_t)((v + (1 << 14)) >> 15);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ref: src/serial/main.cpp:371-386 — warp, left copy, "non-black overwrites" overlay.
+void compose(const uint8_t* left, int wl, int hl, size_t sl, const uint8_t* right, int wr, int hr,
+             size_t sr, const Canvas& c, uint8_t* canvas /* cw*ch*3 tightly packed */) {
+  size_t cs = (size_t)c.cw * 3;
+  std::vector<uint8_t> warped((size_t)c.ch * cs);
+  warp_perspective(right, wr, hr, sr, c.TH, warped.data(), c.cw, c.ch, cs);
+  memset(canvas, 0, (size_t)c.ch * cs);
+  for (int y = 0; y < hl; y++) memcpy(canvas + (size_t)(y + c.offy) * cs + 3 * (size_t)c.offx, left + y * sl, (size_t)wl * 3);
+  for (int y = 0; y < c.ch; y++)
+    for (int x = 0; x < c.cw; x++) {
+      const uint8_t* p = &warped[(size_t)y * cs + 3 * (size_t)x];
+      if (p[0] | p[1] | p[2]) memcpy(canvas + (size_t)y * cs + 3 * (size_t)x, p, 3);
+    }
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI for ctypes (tests / bench only)
+// =========================================================================================
+extern "C" {
+
+struct orc_dmatch { int32_t queryIdx, trainIdx; float distance; };
+
+void orc_gray(const uint8_t* bgr, int w, int h, size_t stride, uint8_t* gray) {
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) gray[(size_t)y * w + x] = gray_of(bgr + y * stride + 3 * x);
+}
+
+void orc_gaussian_kernel(int ksize, double sigma, double* out) {
+  std::vector<double> k;
+  gaussian_kernel(ksize, sigma, k);
+  memcpy(out, k.data(), k.size() * sizeof(double));
+}
+
+void orc_convolve(const double* in, int w, int h, const double* kern, int ksize, double* out) {
+  convolve(in, w, h, kern, ksize, out);
+}
+
+void orc_harris_response(const uint8_t* bgr, int w, int h, size_t stride, double k, double* resp) {
+  std::vector<double> r;
+  harris_response(bgr, w, h, stride, k, r);
+  memcpy(resp, r.data(), r.size() * sizeof(double));
+}
+
+// returns the number of keypoints; writes at most cap of them as (x, y) pairs
+int orc_detect(const uint8_t* bgr, int w, int h, size_t stride, double k, double thresh, int nbhd,
+               int32_t* xy, int cap) {
+  std::vector<double> r;
+  harris_response(bgr, w, h, stride, k, r);
+  std::vector<int32_t> v;
+  nms(r.data(), w, h, thresh, nbhd, v);
+  int n = (int)(v.size() / 2);
+  if (xy) memcpy(xy, v.data(), sizeof(int32_t) * 2 * (size_t)std::min(n, cap));
+  return n;
+}
+
+int orc_match(const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8_t* imq, int wq,
+              int hq, size_t sq, const uint8_t* imt, int wt, int ht, size_t st, int patch,
+              double maxSSD, int offset, orc_dmatch* out, int cap) {
+  std::vector<Match> v;
+  match_keypoints(kq, nq, kt, nt, imq, wq, hq, sq, imt, wt, ht, st, patch, maxSSD, offset, v);
+  int n = (int)v.size();
+  if (out) memcpy(out, v.data(), sizeof(Match) * (size_t)std::min(n, cap));
+  return n;
+}
+
+// cv::eigen(A symmetric n x n) -> W (descending), V (rows).  A is not modified.
+void orc_eigen_sym(const double* A, int n, double* W, double* V) {
+  std::vector<double> a(A, A + (size_t)n * n);
+  jacobi(a.data(), n, W, V, n, n);
+}
+
+int orc_find_homography4(const float* src, const float* dst, double* H) {
+  return find_homography4(src, dst, 4, H);
+}
+
+int orc_ransac(const int32_t* kp1, const int32_t* kp2, const orc_dmatch* matches, int m, int iters,
+               int nsamples, double thr, uint32_t seed, int div_mode, double* H, int* best_count,
+               int32_t* samples, int32_t* counts, uint8_t* inlier_mask, uint64_t* draws,
+               int* best_iter) {
+  return ransac(kp1, kp2, (const Match*)matches, m, iters, nsamples, thr, seed, div_mode, H,
+                best_count, samples, counts, inlier_mask, draws, best_iter);
+}
+
+// libstdc++ known-answer helpers: first n outputs of mt19937(seed); shuffle(iota(n)) with a
+// continuing engine (skip = outputs discarded first).
+void orc_mt19937(uint32_t seed, int n, uint32_t* out) {
+  std::mt19937 e(seed);
+  for (int i = 0; i < n; i++) out[i] = e();
+}
+void orc_shuffle_iota(uint32_t seed, uint64_t skip, int n, int reps, int32_t* out_first4) {
+  std::mt19937 e(seed);
+  e.discard(skip);
+  std::vector<int32_t> v((size_t)n);
+  for (int r = 0; r < reps; r++) {
+    for (int i = 0; i < n; i++) v[i] = i;
+    std::shuffle(v.begin(), v.end(), e);
+    for (int j = 0; j < 4; j++) out_first4[r * 4 + j] = j < n ? v[j] : -1;
+  }
+}
+
+void orc_perspective_transform(const float* pts, int n, const double* H, float* out) {
+  perspective_transform(pts, n, H, out);
+}
+
+int orc_invert33(const double* s, double* d) { return invert33(s, d); }
+
+// out: cw, ch, offx, offy; TH[9]
+int orc_canvas_geometry(int wl, int hl, int wr, int hr, const double* H, int* geom, double* TH) {
+  Canvas c;
+  int ok = canvas_geometry(wl, hl, wr, hr, H, &c);
+  geom[0] = c.cw; geom[1] = c.ch; geom[2] = c.offx; geom[3] = c.offy;
+  memcpy(TH, c.TH, sizeof c.TH);
+  return ok;
+}
+
+void orc_warp_perspective(const uint8_t* src, int sw, int sh, size_t sstride, const double* M,
+                          uint8_t* dst, int dw, int dh, size_t dstride) {
+  warp_perspective(src, sw, sh, sstride, M, dst, dw, dh, dstride);
+}
+
+int orc_compose(const uint8_t* left, int wl, int hl, size_t sl, const uint8_t* right, int wr, int hr,
+                size_t sr, const double* H, uint8_t* canvas, size_t cap, int* geom) {
+  Canvas c;
+  if (!canvas_geometry(wl, hl, wr, hr, H, &c)) return 0;
+  geom[0] = c.cw; geom[1] = c.ch; geom[2] = c.offx; geom[3] = c.offy;
+  if ((size_t)c.cw * c.ch * 3 > cap) return -1;
+  compose(left, wl, hl, sl, right, wr, hr, sr, c, canvas);
+  return 1;
+}
+
+// ref: src/serial/main.cpp:311-391 stitchTwoImages.  status: 1 ok, 0 no matches,
+// -2 RANSAC failed, -3 ROI does not fit, -1 canvas buffer too small.
+// times_ms[4] = detect(both), match, ransac, warp+overlay (wall clock).
+int orc_stitch_pair(const uint8_t* left, int wl, int hl, size_t sl, const uint8_t* right, int wr,
+                    int hr, size_t sr, uint32_t seed, uint8_t* canvas, size_t cap, int* geom,
+                    double* H, int* stats /* kl, kr, m, best_count */, double* times_ms) {
+  auto now = [] { return std::chrono::high_resolution_clock::now(); };
+  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  auto t0 = now();
+  std::vector<double> r;
+  std::vector<int32_t> kl, kr;
+  harris_response(left, wl, hl, sl, 0.04, r);
+  nms(r.data(), wl, hl, 1e6, 3, kl);
+  harris_response(right, wr, hr, sr, 0.04, r);
+  nms(r.data(), wr, hr, 1e6, 3, kr);
+  auto t1 = now();
+  std::vector<Match> mv;
+  match_keypoints(kr.data(), (int)kr.size() / 2, kl.data(), (int)kl.size() / 2, right, wr, hr, sr,
+                  left, wl, hl, sl, 5, 1e8, 0, mv);
+  auto t2 = now();
+  if (stats) { stats[0] = (int)kl.size() / 2; stats[1] = (int)kr.size() / 2; stats[2] = (int)mv.size(); stats[3] = 0; }
+  if (times_ms) { times_ms[0] = ms(t0, t1); times_ms[1] = ms(t1, t2); times_ms[2] = times_ms[3] = 0; }
+  if (mv.empty()) return 0;
+  int best = 0;
+  int ok = ransac(kr.data(), kl.data(), mv.data(), (int)mv.size(), 1000, 4, 3.0, seed, 0, H, &best,
+                  nullptr, nullptr, nullptr, nullptr, nullptr);
+  auto t3 = now();
+  if (stats) stats[3] = best;
+  if (times_ms) times_ms[2] = ms(t2, t3);
+  if (!ok) return -2;
+  Canvas c;
+  if (!canvas_geometry(wl, hl, wr, hr, H, &c)) return -3;
+  geom[0] = c.cw; geom[1] = c.ch; geom[2] = c.offx; geom[3] = c.offy;
+  if ((size_t)c.cw * c.ch * 3 > cap) return -1;
+  compose(left, wl, hl, sl, right, wr, hr, sr, c, canvas);
+  if (times_ms) times_ms[3] = ms(t3, now());
+  return 1;
+}
+
+int orc_num_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"
