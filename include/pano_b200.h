@@ -1,0 +1,187 @@
+/* pano_b200.h — C ABI of the B200-native stitching engine (libpano_b200.so).
+ *
+ * Drop-in boundary for the stitching hot path of
+ * Albus-Tan/UCB-CS267-Parallel-Panoramic-Image-Stitching.  Each entry point replaces one
+ * of the stage functions the reference's gpu_stitching executable links against; the
+ * reference interface it replaces is cited as "ref:" (paths relative to the reference
+ * repository).  Plain pointers and sizes only — no OpenCV, torch or CUDA types.
+ *
+ * Semantics are those of the reference's SERIAL path (src/serial/main.cpp), bit-exact for
+ * keypoints, matches, RANSAC samples / inlier counts / inlier sets, with one deliberate
+ * deviation: the RANSAC engine std::mt19937 is seeded from the context's seed instead of
+ * std::random_device (ref: src/serial/main.cpp:264-265), so results are reproducible.
+ *
+ * Conventions
+ *  - Images are 8-bit BGR, interleaved, row stride in bytes (what cv::imread returns).
+ *  - `mem` says where caller buffers live: PANO_MEM_HOST (pageable or pinned host memory;
+ *    the call copies in/out) or PANO_MEM_DEVICE (device pointers on the context's device;
+ *    no host copies of bulk data).
+ *  - Keypoints are int32 (x, y) pairs in the reference's row-major detection order
+ *    (cv::KeyPoint::pt of the reference is integral; size/angle are unused on the path).
+ *  - Matches mirror the three cv::DMatch fields the path uses.
+ *  - Every function returns a pano_status; none throws, none falls back to the CPU.
+ *    The reference's "empty result" cases map to distinct codes.
+ *  - A context is bound to one device and one stream and is not thread-safe (the reference
+ *    is single-threaded); use one context per device per thread.
+ */
+#ifndef PANO_B200_H
+#define PANO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pano_ctx pano_ctx;
+
+typedef enum {
+  PANO_OK = 0,
+  PANO_ERR_INVALID = 1,          /* bad argument */
+  PANO_ERR_CUDA = 2,             /* CUDA runtime error; see pano_last_error */
+  PANO_ERR_NO_MATCHES = 3,       /* ref: "Not enough matched corners" (src/serial/main.cpp:321-324) */
+  PANO_ERR_TOO_FEW_MATCHES = 4,  /* matches < numSamples: RANSAC loop breaks at once (:268-269) */
+  PANO_ERR_NO_HOMOGRAPHY = 5,    /* no iteration produced an inlier: empty Mat (:329-332) */
+  PANO_ERR_ROI = 6,              /* left ROI outside canvas: the reference throws at :376 */
+  PANO_ERR_CAPACITY = 7,         /* caller buffer too small; required size is reported */
+  PANO_ERR_UNSUPPORTED = 8,      /* option outside what the engine implements */
+  PANO_ERR_NO_DEVICE = 9         /* no CUDA device / not an sm_100 device */
+} pano_status;
+
+enum { PANO_MEM_HOST = 0, PANO_MEM_DEVICE = 1 };
+
+/* ref: src/serial/main.cpp:28-34 HarrisCornerOptions (same defaults). */
+typedef struct {
+  double k;                 /* 0.04 */
+  double nms_thresh;        /* 1e6  */
+  int nms_neighborhood;     /* 3 (odd) */
+  int patch_size;           /* 5 (odd; 1, 3 or 5 supported) */
+  double max_ssd_thresh;    /* 1e8  */
+} pano_harris_opts;
+
+/* ref: src/serial/main.cpp:36-40 RansacOptions / src/gpu/ransac.cuh:10-14 Options. */
+typedef struct {
+  int num_iterations;       /* 1000 */
+  int num_samples;          /* 4 (only 4 is supported: cv::findHomography's 4-point path) */
+  double distance_threshold;/* 3.0 */
+} pano_ransac_opts;
+
+/* ref: cv::DMatch(queryIdx, trainIdx, distance) as built at src/serial/main.cpp:237. */
+typedef struct {
+  int32_t query_idx;
+  int32_t train_idx;
+  float distance;
+} pano_dmatch;
+
+typedef struct {
+  int canvas_w, canvas_h;   /* ref: canvasSize, src/serial/main.cpp:369 */
+  int left_x, left_y;       /* ref: cv::Rect(-minX, -minY, ...), :376 */
+  double TH[9];             /* translation * H, :366-372 */
+} pano_canvas_info;
+
+typedef struct {
+  int status;               /* pano_status of this pair */
+  int n_kp_left, n_kp_right;
+  int n_matches;
+  int best_inliers;
+  int best_iteration;
+  double H[9];              /* right -> left homography (row-major), ref: :328 */
+  pano_canvas_info canvas;
+  float ms_detect, ms_match, ms_ransac, ms_warp, ms_total;  /* device time, CUDA events */
+} pano_pair_result;
+
+void pano_default_harris_opts(pano_harris_opts* o);
+void pano_default_ransac_opts(pano_ransac_opts* o);
+
+/* Context: device ordinal, RANSAC seed.  Fails (never falls back) without an sm_100 GPU. */
+int pano_create(int device, uint32_t seed, pano_ctx** out);
+void pano_destroy(pano_ctx* ctx);
+int pano_set_seed(pano_ctx* ctx, uint32_t seed);
+const char* pano_last_error(const pano_ctx* ctx);
+const char* pano_version(void);
+/* number of engine kernels launched by this context so far (bench.py's gpu_launches) */
+uint64_t pano_kernel_launches(const pano_ctx* ctx);
+/* 0 = tensor-core matcher (default), 1 = SIMT cross-check kernel (debug / tests) */
+int pano_set_matcher(pano_ctx* ctx, int which);
+
+/* ---- stage entry points -------------------------------------------------------------- */
+
+/* ref: gpuHarrisCornerDetectorDetect(image, k, nmsThresh, nmsNeighborhood)
+ *      (src/gpu/harris_detector.cuh:5-9) with the semantics of seqHarrisCornerDetectorDetect
+ *      (src/serial/main.cpp:119-185).  Writes min(*count, cap) keypoints; *count is the
+ *      full number (PANO_ERR_CAPACITY if cap was too small). */
+int pano_detect(pano_ctx* ctx, const uint8_t* bgr, int w, int h, size_t stride, int mem,
+                const pano_harris_opts* opts, int32_t* xy_out, int cap, int* count);
+
+/* Harris response plane (FP64, w*h, row-major), for inspection and parity tests.
+ * ref: src/serial/main.cpp:123-155. */
+int pano_harris_response(pano_ctx* ctx, const uint8_t* bgr, int w, int h, size_t stride, int mem,
+                         double k, double* resp_out);
+
+/* ref: convolveCUDA(input64f, output64f, kernel) (src/gpu/convolution.cuh:5) with the
+ *      semantics of convolveSequential (src/serial/main.cpp:96-116). */
+int pano_convolve_f64(pano_ctx* ctx, const double* in, int w, int h, const double* kernel,
+                      int ksize, int mem, double* out);
+
+/* ref: gpuHarrisMatchKeyPoints(kpQuery, kpTrain, imgQuery, imgTrain, patchSize, maxSSD,
+ *      offset) (src/gpu/harris_matcher.cuh:5-9) with the semantics of
+ *      seqHarrisMatchKeyPoints (src/serial/main.cpp:188-244). */
+int pano_match(pano_ctx* ctx, const int32_t* kp_query, int n_query, const int32_t* kp_train,
+               int n_train, const uint8_t* img_query, int wq, int hq, size_t stride_q,
+               const uint8_t* img_train, int wt, int ht, size_t stride_t, int mem,
+               const pano_harris_opts* opts, int offset, pano_dmatch* out, int cap, int* count);
+
+/* ref: GpuRansacHomographyCalculator::computeHomography(kp1, kp2, matches)
+ *      (src/gpu/ransac.cuh:8-36) with the semantics of
+ *      SeqRansacHomographyCalculator::computeHomography (src/serial/main.cpp:247-307).
+ *      Optional outputs (may be NULL): samples_out[num_iterations*4] match indices drawn per
+ *      iteration, counts_out[num_iterations] inlier counts (-1 where findHomography was
+ *      empty), inlier_mask_out[n_matches] for the returned H.  Host pointers always. */
+int pano_ransac(pano_ctx* ctx, const int32_t* kp1, int n1, const int32_t* kp2, int n2,
+                const pano_dmatch* matches, int n_matches, int mem, const pano_ransac_opts* opts,
+                double H_out[9], int* best_inliers, int* best_iteration, int32_t* samples_out,
+                int32_t* counts_out, uint8_t* inlier_mask_out);
+
+/* Canvas geometry for a homography.  ref: src/serial/main.cpp:335-369, :376. */
+int pano_canvas_geometry(int wl, int hl, int wr, int hr, const double H[9], pano_canvas_info* out);
+
+/* ref: cv::warpPerspective + left copy + overlay, src/serial/main.cpp:371-386.
+ *      canvas_out: canvas_h rows of canvas_stride bytes (>= 3*canvas_w). */
+int pano_warp_overlay(pano_ctx* ctx, const uint8_t* left, int wl, int hl, size_t stride_l,
+                      const uint8_t* right, int wr, int hr, size_t stride_r, int mem,
+                      const double H[9], uint8_t* canvas_out, size_t canvas_stride,
+                      size_t canvas_cap_bytes, pano_canvas_info* info);
+
+/* cv::warpPerspective alone (INTER_LINEAR, BORDER_CONSTANT 0), for parity tests. */
+int pano_warp_perspective(pano_ctx* ctx, const uint8_t* src, int w, int h, size_t stride, int mem,
+                          const double M[9], uint8_t* dst, int dw, int dh, size_t dstride);
+
+/* ---- fused pipeline ------------------------------------------------------------------ */
+
+/* ref: stitchTwoImages(left, right, harrisOpts, ransacOpts) (src/serial/main.cpp:311-391;
+ *      src/gpu/main.cpp:322-426).  Everything stays on the device between stages.  The
+ *      canvas is kept in the context; fetch it with pano_get_canvas or feed it to the next
+ *      fold step.  res->status carries the reference's failure cases. */
+int pano_stitch_pair(pano_ctx* ctx, const uint8_t* left, int wl, int hl, size_t stride_l,
+                     const uint8_t* right, int wr, int hr, size_t stride_r, int mem,
+                     const pano_harris_opts* hopts, const pano_ransac_opts* ropts,
+                     pano_pair_result* res);
+
+/* Copies the context's current canvas (result of the last successful pair / fold step). */
+int pano_get_canvas(pano_ctx* ctx, uint8_t* out, size_t out_stride, size_t cap_bytes, int mem,
+                    int* w, int* h);
+/* Device pointer/stride of the context's current canvas (valid until the next stitch call). */
+int pano_canvas_device(pano_ctx* ctx, const uint8_t** ptr, size_t* stride, int* w, int* h);
+
+/* ref: stitchAllImages(images, ...) (src/serial/main.cpp:395-414): left fold over n images;
+ *      a failed step keeps the previous panorama.  results[n-1] receives one record per step
+ *      (may be NULL).  Returns PANO_OK if a panorama exists at the end. */
+int pano_stitch_fold(pano_ctx* ctx, const uint8_t* const* images, const int* ws, const int* hs,
+                     const size_t* strides, int n, int mem, const pano_harris_opts* hopts,
+                     const pano_ransac_opts* ropts, pano_pair_result* results);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANO_B200_H */

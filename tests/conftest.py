@@ -1,0 +1,69 @@
+import ctypes
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "ucb-cs267-parallel-panoramic-image-stitching_b200"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def load_pkg():
+    return importlib.import_module(PKG)
+
+
+def load_synth():
+    return importlib.import_module(PKG + ".synth")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle.oracle import Oracle
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    d = os.path.join(ROOT, "tests", "hostsim")
+    so = os.path.join(d, "libhostsim.so")
+    src = os.path.join(d, "hostsim.cpp")
+    hdrs = [os.path.join(ROOT, PKG, "csrc", f) for f in ("pano_core.cuh", "replay_plan.hpp")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
+    return ctypes.CDLL(so)
+
+
+@pytest.fixture(scope="session")
+def pins():
+    return np.load(os.path.join(GOLDEN, "opencv_pins.npz"))
+
+
+@pytest.fixture(scope="session")
+def engine():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    pkg = load_pkg()
+    e = pkg.Engine(device=0, seed=12345)   # raises if the .so is missing: no fallback
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="session")
+def small_pair():
+    return load_synth().make_pair(960, 540, seed=267)
+
+
+@pytest.fixture(scope="session")
+def mid_pair():
+    return load_synth().make_pair(1920, 1080, seed=31)

@@ -1,0 +1,103 @@
+// hostsim.cpp — CPU emulation of the engine's kernels' LOGIC, for the no-GPU test tier.
+//
+// TEST INFRASTRUCTURE ONLY.  It compiles the very headers the CUDA kernels use
+// (csrc/pano_core.cuh, csrc/replay_plan.hpp) with g++ and re-runs the kernels' control flow
+// (grid of candidate walks + chain for the shuffle replay, per-hypothesis DLT, per-pixel warp)
+// in plain loops, so that the order-exact arithmetic and the speculation scheme can be checked
+// against the oracle without a GPU.  It is not linked into, or reachable from, the product.
+#include <cstdint>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../../ucb-cs267-parallel-panoramic-image-stitching_b200/csrc/pano_core.cuh"
+#include "../../ucb-cs267-parallel-panoramic-image-stitching_b200/csrc/replay_plan.hpp"
+
+using namespace pano;
+
+extern "C" {
+
+int hs_find_homography4(const float* src, const float* dst, double* H) {
+  double LtL[81], V[81];
+  return find_homography4(src, dst, H, LtL, V);
+}
+
+int hs_is_inlier(const double* H, float x, float y, float qx, float qy, double thr) {
+  return is_inlier(H, x, y, qx, qy, thr) ? 1 : 0;
+}
+
+// out: cw, ch, offx, offy, bw0, ok ; TH[9]; Minv[9]
+void hs_canvas_geometry(int wl, int hl, int wr, int hr, const double* H, int* geom, double* TH, double* Minv) {
+  CanvasGeom g;
+  canvas_geometry(wl, hl, wr, hr, H, &g);
+  geom[0] = g.cw; geom[1] = g.ch; geom[2] = g.offx; geom[3] = g.offy; geom[4] = g.bw0; geom[5] = g.ok;
+  memcpy(TH, g.TH, sizeof g.TH);
+  memcpy(Minv, g.Minv, sizeof g.Minv);
+}
+
+// emulates warp_overlay_kernel<false>: cv::warpPerspective(src, M, (dw, dh))
+void hs_warp_perspective(const uint8_t* src, int w, int h, size_t stride, const double* M, uint8_t* dst, int dw,
+                         int dh, size_t dstride) {
+  double Minv[9];
+  invert33(M, Minv);
+  int bh0 = dh < 16 ? dh : 16;
+  int bw0 = 1024 / bh0;
+  if (bw0 > dw) bw0 = dw;
+  for (int y = 0; y < dh; y++)
+    for (int x = 0; x < dw; x++) {
+      int X, Y;
+      warp_coord(Minv, x, y, bw0, &X, &Y);
+      uint32_t v = warp_pixel(src, stride, w, h, X, Y);
+      uint8_t* o = dst + (size_t)y * dstride + 3 * (size_t)x;
+      o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16);
+    }
+}
+
+// emulates replay_walk_kernel + replay_chain_kernel chunk by chunk.
+// returns 0 ok, 1 window miss, 2 stream too short.  stats: G, n_cand, max_w, chunks
+int hs_replay(uint32_t seed, uint32_t n, int iters, int window_scale, int32_t* samples, uint64_t* end_offset,
+              double* stats) {
+  ReplayPlan P = plan_replay(n, iters, window_scale);
+  const uint32_t steps = shuffle_steps(n);
+  const bool pairs = shuffle_uses_pairs(n);
+  uint64_t guard = steps + 4096;
+  std::vector<uint32_t> X(P.stream_need + guard, 0xffffffffu);
+  {
+    std::mt19937 e(seed);
+    for (uint64_t i = 0; i < P.stream_need; i++) X[i] = e();
+  }
+  if (stats) { stats[0] = P.G; stats[1] = P.n_cand; stats[2] = P.max_w; stats[3] = (iters + P.G - 1) / P.G; stats[4] = P.mu; stats[5] = P.sigma; }
+  std::vector<uint32_t> cand_end(P.n_cand);
+  std::vector<int> cand_samp((size_t)P.n_cand * 4);
+  uint64_t base = 0;
+  for (int c0 = 0; c0 < iters; c0 += P.G) {
+    int Gc = std::min(P.G, iters - c0);
+    for (int g = 0; g < Gc; g++) {
+      const WinEntry& we = P.win[g];
+      for (uint32_t j = 0; j < we.width; j++) {
+        uint64_t start = base + (uint64_t)g * steps + we.lo + j;
+        if (start + 2ull * steps + 64ull >= P.stream_need) return 2;
+        int a[4];
+        uint32_t rel0 = (uint32_t)(start - base);
+        uint32_t end = pairs ? walk_shuffle<true>(X.data() + base, rel0, n, steps, P.thr.data(), a)
+                             : walk_shuffle<false>(X.data() + base, rel0, n, steps, P.thr.data(), a);
+        cand_end[we.first + j] = end;
+        memcpy(&cand_samp[(size_t)(we.first + j) * 4], a, sizeof a);
+      }
+    }
+    uint32_t rel = 0;
+    for (int g = 0; g < Gc; g++) {
+      const WinEntry& we = P.win[g];
+      long long j = (long long)rel - ((long long)g * steps + we.lo);
+      if (j < 0 || j >= (long long)we.width) return 1;
+      uint32_t pick = we.first + (uint32_t)j;
+      memcpy(&samples[(size_t)(c0 + g) * 4], &cand_samp[(size_t)pick * 4], 4 * sizeof(int));
+      rel = cand_end[pick];
+    }
+    base += rel;
+  }
+  if (end_offset) *end_offset = base;
+  return 0;
+}
+
+}  // extern "C"

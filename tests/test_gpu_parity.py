@@ -1,0 +1,258 @@
+"""GPU tier (-m gpu): the CUDA engine, called through the C ABI, against the CPU oracle on the
+same inputs.  Bars (BASELINE.json north_star): keypoints, match lists, RANSAC samples / counts /
+inlier sets bit-exact; homographies within 1e-4 relative (asserted bit-exact here, which is
+stronger); warped pixels within +-1 LSB (asserted exact)."""
+import numpy as np
+import pytest
+
+from conftest import load_pkg, load_synth
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+# ---------------- K1 / K2: detector --------------------------------------------------------
+def test_harris_response_bit_exact(engine, oracle, small_pair):
+    left, right, _ = small_pair
+    for img in (left, right):
+        r_gpu = engine.harrisResponse(img)
+        r_cpu = oracle.harris_response(img)
+        assert np.array_equal(bits(r_gpu), bits(r_cpu))
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (33, 35), (97, 61), (130, 5), (5, 130), (6, 6), (255, 257)])
+def test_detect_ragged_sizes(engine, oracle, w, h):
+    rng = np.random.default_rng(w * 1000 + h)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    # blocky content so that corners exist
+    img[h // 4: h // 2, w // 4: w // 2] = (250, 20, 30)
+    assert np.array_equal(bits(engine.harrisResponse(img)), bits(oracle.harris_response(img)))
+    assert np.array_equal(engine.gpuHarrisCornerDetectorDetect(img), oracle.detect(img))
+
+
+def test_detect_keypoints_identical_and_ordered(engine, oracle, small_pair, mid_pair):
+    for pair in (small_pair, mid_pair):
+        for img in pair[:2]:
+            k_gpu = engine.gpuHarrisCornerDetectorDetect(img)
+            k_cpu = oracle.detect(img)
+            assert len(k_cpu) > 100
+            assert np.array_equal(k_gpu, k_cpu)
+
+
+def test_detect_flat_image_has_no_keypoints(engine, oracle):
+    img = np.full((70, 90, 3), 128, np.uint8)
+    assert len(engine.gpuHarrisCornerDetectorDetect(img)) == 0 == len(oracle.detect(img))
+
+
+def test_detect_ties_are_rejected(engine, oracle):
+    """strict NMS (ref: src/serial/main.cpp:164-176): periodic texture creates exact ties"""
+    img = np.zeros((96, 96, 3), np.uint8)
+    img[::8, :, :] = 255
+    img[:, ::8, :] = 255
+    assert np.array_equal(engine.gpuHarrisCornerDetectorDetect(img), oracle.detect(img))
+
+
+def test_detect_other_options(engine, oracle, small_pair):
+    left = small_pair[0]
+    for k, th, nb in ((0.06, 5e5, 3), (0.04, 1e7, 5), (0.04, 1e5, 7)):
+        assert np.array_equal(engine.gpuHarrisCornerDetectorDetect(left, k, th, nb), oracle.detect(left, k, th, nb))
+
+
+def test_convolve_matches_oracle(engine, oracle):
+    rng = np.random.default_rng(1)
+    a = rng.uniform(-1000, 1000, (45, 67))
+    for ks in (3, 5, 7):
+        kern = rng.uniform(-1, 1, (ks, ks))
+        assert np.array_equal(bits(engine.convolveCUDA(a, kern)), bits(oracle.convolve(a, kern)))
+
+
+# ---------------- K3 / K4: matcher -----------------------------------------------------------
+@pytest.mark.parametrize("which", [1, 0])
+def test_matches_identical(engine, oracle, small_pair, mid_pair, which):
+    engine.set_matcher(which)
+    try:
+        for left, right, _ in (small_pair, mid_pair):
+            kl, kr = oracle.detect(left), oracle.detect(right)
+            m_cpu = oracle.match(kr, kl, right, left)
+            m_gpu = engine.gpuHarrisMatchKeyPoints(kr, kl, right, left)
+            assert len(m_cpu) > 50
+            assert np.array_equal(m_gpu, m_cpu)
+    finally:
+        engine.set_matcher(0)
+
+
+@pytest.mark.parametrize("which", [1, 0])
+def test_match_edge_cases(engine, oracle, small_pair, which):
+    engine.set_matcher(which)
+    try:
+        left, right, _ = small_pair
+        kl, kr = oracle.detect(left), oracle.detect(right)
+        # keypoints on the border are skipped on both sides; duplicates create exact SSD ties
+        kq = np.concatenate([[[0, 0], [1, 5], [right.shape[1] - 1, 9], [5, right.shape[0] - 2]], kr[:300]]).astype(np.int32)
+        kt = np.concatenate([kl[:200], kl[:200], [[1, 1], [left.shape[1] - 2, 7]]]).astype(np.int32)
+        for off in (0, 17):
+            a = engine.gpuHarrisMatchKeyPoints(kq, kt, right, left, offset=off)
+            b = oracle.match(kq, kt, right, left, offset=off)
+            assert np.array_equal(a, b)
+        # a threshold that really filters
+        a = engine.gpuHarrisMatchKeyPoints(kr, kl, right, left, maxSSDThresh=3000.0)
+        b = oracle.match(kr, kl, right, left, max_ssd=3000.0)
+        assert 0 < len(b) < len(kr) and np.array_equal(a, b)
+        # other patch size
+        a = engine.gpuHarrisMatchKeyPoints(kr, kl, right, left, patchSize=3)
+        b = oracle.match(kr, kl, right, left, patch=3)
+        assert np.array_equal(a, b)
+        # empty sides
+        empty = np.zeros((0, 2), np.int32)
+        assert len(engine.gpuHarrisMatchKeyPoints(empty, kl, right, left)) == 0
+        assert len(engine.gpuHarrisMatchKeyPoints(kr, empty, right, left)) == 0
+        # no in-border train keypoint at all
+        assert len(engine.gpuHarrisMatchKeyPoints(kr, np.array([[0, 0], [1, 1]], np.int32), right, left)) == 0
+    finally:
+        engine.set_matcher(0)
+
+
+# ---------------- K5 - K7: RANSAC ------------------------------------------------------------
+def _ransac_inputs(oracle, pair):
+    left, right, _ = pair
+    kl, kr = oracle.detect(left), oracle.detect(right)
+    return kl, kr, oracle.match(kr, kl, right, left)
+
+
+@pytest.mark.parametrize("seed", [12345, 1, 267])
+def test_ransac_bit_exact(engine, oracle, small_pair, seed):
+    kl, kr, m = _ransac_inputs(oracle, small_pair)
+    engine.set_seed(seed)
+    g = engine.computeHomography(kr, kl, m, details=True)
+    c = oracle.ransac(kr, kl, m, seed=seed)
+    engine.set_seed(12345)
+    assert g["ok"] and c["ok"]
+    assert np.array_equal(g["samples"], c["samples"])          # replayed std::shuffle
+    assert np.array_equal(g["counts"], c["counts"])            # per-iteration inlier counts
+    assert (g["best_count"], g["best_iter"]) == (c["best_count"], c["best_iter"])
+    assert np.array_equal(g["inlier_mask"], c["inlier_mask"])  # inlier set
+    assert np.array_equal(bits(g["H"]), bits(c["H"]))          # homography (bar: 1e-4 relative)
+
+
+def test_ransac_mid_size_and_subsets(engine, oracle, mid_pair):
+    kl, kr, m = _ransac_inputs(oracle, mid_pair)
+    pkg = load_pkg()
+    for sub in (len(m), 1001, 4, 5, 6, 7, 8, 64):   # even / odd / tiny match counts
+        mm = m[:sub]
+        g = engine.computeHomography(kr, kl, mm, details=True)
+        c = oracle.ransac(kr, kl, mm, seed=12345)
+        assert g["ok"] == c["ok"]
+        assert np.array_equal(g["samples"], c["samples"])
+        assert np.array_equal(g["counts"], c["counts"])
+        if c["ok"]:
+            assert np.array_equal(bits(g["H"]), bits(c["H"]))
+            assert np.array_equal(g["inlier_mask"], c["inlier_mask"])
+    # fewer matches than samples: the reference's loop breaks at once -> empty H
+    assert engine.computeHomography(kr, kl, m[:3]) is None
+    # fewer iterations
+    o = pkg.RansacOptions(numIterations_=37)
+    g = engine.computeHomography(kr, kl, m, o, details=True)
+    c = oracle.ransac(kr, kl, m, iters=37, seed=12345)
+    assert np.array_equal(g["samples"], c["samples"][:37]) and np.array_equal(g["counts"], c["counts"][:37])
+
+
+def test_ransac_degenerate_samples(engine, oracle):
+    """all matches share an x (findHomography returns empty every time) -> no homography"""
+    kp1 = np.array([[5, i * 3] for i in range(40)], np.int32)
+    kp2 = np.array([[9 + i, i * 3 + 1] for i in range(40)], np.int32)
+    m = np.zeros(40, load_pkg().MATCH_DTYPE)
+    m["queryIdx"] = np.arange(40); m["trainIdx"] = np.arange(40)
+    g = engine.computeHomography(kp1, kp2, m, details=True)
+    c = oracle.ransac(kp1, kp2, m, seed=12345)
+    assert not g["ok"] and not c["ok"]
+    assert np.array_equal(g["counts"], c["counts"]) and (c["counts"] == -1).all()
+
+
+# ---------------- K8: warp + overlay ---------------------------------------------------------
+def test_warp_perspective_matches_cv2_fixtures(engine, pins):
+    for i in range(4):
+        ref = pins["warp_out%d" % i]
+        out = engine.warpPerspective(pins["warp_src"], pins["warp_M%d" % i], (ref.shape[1], ref.shape[0]))
+        assert np.array_equal(out, ref)
+
+
+def test_warp_overlay_identical(engine, oracle, small_pair):
+    left, right, Ht = small_pair
+    rng = np.random.default_rng(4)
+    Hs = [Ht, np.array([[1.0, 0, 480.0], [0, 1, 0], [0, 0, 1]]), np.array([[1.0, 0, -100.5], [0, 1, -20.25], [0, 0, 1]]),
+          Ht @ np.array([[1.01, 0.01, 3], [-0.01, 0.99, -40], [1e-6, 2e-6, 1]])]
+    for H in Hs:
+        a = engine.warpOverlay(left, right, H)
+        b = oracle.compose(left, right, H)
+        assert (a is None) == (b is None)
+        if b is not None:
+            assert a.shape == b.shape
+            assert np.abs(a.astype(int) - b.astype(int)).max() <= 1   # the bar
+            assert np.array_equal(a, b)                               # what we actually get
+
+
+# ---------------- fused pair / fold ------------------------------------------------------------
+def test_stitch_pair_end_to_end(engine, oracle, small_pair, mid_pair):
+    for left, right, Ht in (small_pair, mid_pair):
+        canvas, r = engine.stitchTwoImages(left, right)
+        o = oracle.stitch_pair(left, right, seed=12345)
+        assert r["status"] == 0 and o["status"] == 1
+        assert (r["kl"], r["kr"], r["m"], r["best"]) == (o["stats"]["kl"], o["stats"]["kr"], o["stats"]["m"], o["stats"]["best"])
+        assert np.array_equal(bits(r["H"]), bits(o["H"]))
+        assert np.abs(r["H"] / r["H"][2, 2] - Ht).max() / np.abs(Ht).max() < 5e-3     # recovers the truth
+        assert r["canvas"] == o["geom"]
+        assert np.array_equal(canvas, o["canvas"])
+
+
+def test_stitch_pair_device_resident_inputs(engine, oracle, small_pair):
+    import torch
+    left, right, _ = small_pair
+    L, R = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+    canvas, r = engine.stitchTwoImages(L, R)
+    o = oracle.stitch_pair(left, right, seed=12345)
+    assert r["status"] == 0
+    assert np.array_equal(canvas.cpu().numpy(), o["canvas"])
+
+
+def test_stitch_failure_statuses(engine, oracle):
+    pkg = load_pkg()
+    flat = np.full((64, 80, 3), 90, np.uint8)
+    canvas, r = engine.stitchTwoImages(flat, flat)
+    assert canvas is None and r["status"] == pkg.PANO_ERR_NO_MATCHES
+    assert oracle.stitch_pair(flat, flat)["status"] == 0
+
+
+def test_stitch_fold_three_images(engine, oracle):
+    views = load_synth().make_strip(n=3, w=640, h=400, seed=5)
+    pano, log = engine.stitchAllImages(views)
+    opano, olog = oracle.stitch_fold(views, seed=12345)
+    assert [l["status"] == 0 for l in log] == [l["status"] == 1 for l in olog]
+    assert pano.shape == opano.shape and np.array_equal(pano, opano)
+
+
+# ---------------- full-size properties (BASELINE config 3: 3840x2160 pair) ----------------------
+def test_full_size_pair_properties(engine, oracle):
+    left, right, Ht = load_synth().make_pair(3840, 2160, seed=267)
+    canvas, r = engine.stitchTwoImages(left, right)
+    assert r["status"] == 0
+    H = r["H"] / r["H"][2, 2]
+    assert np.abs(H - Ht).max() / np.abs(Ht).max() < 2e-3
+    assert 8000 < r["kl"] < 25000 and r["m"] > 4000 and r["best"] > 0.3 * r["m"]
+    # idempotence / determinism: same inputs, same seed -> identical outputs
+    canvas2, r2 = engine.stitchTwoImages(left, right)
+    assert np.array_equal(canvas, canvas2) and np.array_equal(bits(r["H"]), bits(r2["H"]))
+    # the left image appears verbatim wherever the warped right image is black
+    cw, ch, ox, oy = r["canvas"]
+    region = canvas[oy:oy + left.shape[0], ox:ox + 200]   # far left: right image does not reach
+    assert np.array_equal(region, left[:, :200])
+    # stage parity at full size against the oracle (keypoints, matches, RANSAC)
+    kl, kr = oracle.detect(left), oracle.detect(right)
+    assert np.array_equal(engine.gpuHarrisCornerDetectorDetect(left), kl)
+    m = oracle.match(kr, kl, right, left)
+    assert np.array_equal(engine.gpuHarrisMatchKeyPoints(kr, kl, right, left), m)
+    c = oracle.ransac(kr, kl, m, seed=12345)
+    assert np.array_equal(bits(r["H"]), bits(c["H"])) and r["best"] == c["best_count"]
+    assert np.array_equal(canvas, oracle.compose(left, right, c["H"]))

@@ -1,0 +1,82 @@
+"""CPU tier: the kernels' shared order-exact arithmetic (csrc/pano_core.cuh) and the shuffle
+replay's windowed-speculation scheme (csrc/replay_plan.hpp), compiled for the host and run as
+plain loops (tests/hostsim), against the oracle / real libstdc++."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+def p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def test_find_homography4_host_compile_matches_oracle(hostsim, oracle, pins):
+    for src, dst, H, ok in zip(pins["fh_src"], pins["fh_dst"], pins["fh_H"], pins["fh_ok"]):
+        out = np.zeros((3, 3))
+        r = hostsim.hs_find_homography4(p(np.ascontiguousarray(src), C.c_float), p(np.ascontiguousarray(dst), C.c_float),
+                                        p(out, C.c_double))
+        assert bool(r) == bool(ok)
+        if ok:
+            assert np.array_equal(out.view(np.uint64), H.view(np.uint64))
+
+
+def test_warp_model_matches_cv2_fixtures(hostsim, pins):
+    src = np.ascontiguousarray(pins["warp_src"])
+    for i in range(4):
+        ref = pins["warp_out%d" % i]
+        M = np.ascontiguousarray(pins["warp_M%d" % i])
+        out = np.zeros_like(ref)
+        hostsim.hs_warp_perspective(p(src, C.c_uint8), src.shape[1], src.shape[0], C.c_size_t(src.strides[0]),
+                                    p(M, C.c_double), p(out, C.c_uint8), ref.shape[1], ref.shape[0],
+                                    C.c_size_t(out.strides[0]))
+        assert np.array_equal(out, ref)
+
+
+def test_canvas_geometry_matches_oracle(hostsim, oracle):
+    rng = np.random.default_rng(3)
+    for t in range(200):
+        H = np.array([[1 + rng.normal() * 0.01, rng.normal() * 0.01, rng.uniform(-500, 2500)],
+                      [rng.normal() * 0.01, 1 + rng.normal() * 0.01, rng.uniform(-200, 200)],
+                      [rng.normal() * 1e-6, rng.normal() * 1e-6, 1.0]])
+        geom = np.zeros(6, np.int32); TH = np.zeros((3, 3)); Mi = np.zeros((3, 3))
+        hostsim.hs_canvas_geometry(1000, 700, 900, 650, p(H, C.c_double), p(geom, C.c_int32), p(TH, C.c_double),
+                                   p(Mi, C.c_double))
+        ok, g, TH2 = oracle.canvas_geometry(1000, 700, 900, 650, H)
+        assert bool(geom[5]) == ok
+        assert tuple(int(v) for v in geom[:4]) == g
+        assert np.array_equal(TH.view(np.uint64), TH2.view(np.uint64))
+
+
+@pytest.mark.parametrize("n,iters", [(4, 64), (5, 64), (6, 64), (7, 64), (8, 64), (9, 33), (10, 100), (33, 100),
+                                     (256, 300), (257, 300), (1000, 1000), (2500, 1000), (4097, 600),
+                                     (65535, 6), (65536, 6), (70000, 12)])
+def test_replay_matches_std_shuffle(hostsim, oracle, n, iters):
+    """first 4 elements of every iteration's shuffled copy == real std::shuffle with one
+    continuing mt19937 (both regimes: paired draws for n <= 65535, single draws above)."""
+    ref = oracle.shuffle_iota(12345, n, reps=iters)
+    samples = np.zeros((iters, 4), np.int32)
+    end = C.c_uint64(0)
+    st = hostsim.hs_replay(C.c_uint32(12345), C.c_uint32(n), iters, 1, p(samples, C.c_int32), C.byref(end), None)
+    assert st == 0
+    assert np.array_equal(samples, ref)
+
+
+def test_replay_other_seeds(hostsim, oracle):
+    for seed in (0, 1, 267, 0xFFFFFFFF):
+        ref = oracle.shuffle_iota(seed, 3001, reps=200)
+        samples = np.zeros((200, 4), np.int32)
+        st = hostsim.hs_replay(C.c_uint32(seed), C.c_uint32(3001), 200, 1, p(samples, C.c_int32), None, None)
+        assert st == 0 and np.array_equal(samples, ref)
+
+
+def test_replay_total_draws_match_oracle_ransac(hostsim, oracle, small_pair):
+    left, right, _ = small_pair
+    kl, kr = oracle.detect(left), oracle.detect(right)
+    m = oracle.match(kr, kl, right, left)
+    r = oracle.ransac(kr, kl, m, seed=12345)
+    samples = np.zeros((1000, 4), np.int32)
+    end = C.c_uint64(0)
+    st = hostsim.hs_replay(C.c_uint32(12345), C.c_uint32(len(m)), 1000, 1, p(samples, C.c_int32), C.byref(end), None)
+    assert st == 0 and end.value == r["draws"]
+    assert np.array_equal(samples, r["samples"])

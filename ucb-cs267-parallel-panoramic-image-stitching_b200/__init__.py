@@ -1,0 +1,350 @@
+"""pano_b200 — host-side mirror of the reference's GPU stage interface over the C ABI.
+
+The product is ``libpano_b200.so`` (hand-written sm_100a CUDA kernels behind the C ABI in
+``include/pano_b200.h``).  This module is the thin Python binding used by tests and bench.py;
+it mirrors the names and argument meaning of the reference's stage entry points:
+
+    gpuHarrisCornerDetectorDetect   ref: src/gpu/harris_detector.cuh:5-9
+    gpuHarrisMatchKeyPoints         ref: src/gpu/harris_matcher.cuh:5-9
+    GpuRansacHomographyCalculator   ref: src/gpu/ransac.cuh:8-36
+    convolveCUDA                    ref: src/gpu/convolution.cuh:5
+    stitchTwoImages / stitchAllImages   ref: src/gpu/main.cpp:322-449
+
+with the SERIAL path's semantics (ref: src/serial/main.cpp).  There is no CPU fallback: if the
+library is missing or no sm_100 GPU is present, construction raises.
+
+Images are ``numpy`` uint8 arrays (H, W, 3) BGR on the host, or CUDA ``torch`` uint8 tensors of
+the same shape (then nothing bulk crosses PCIe).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpano_b200.so")
+
+PANO_OK = 0
+PANO_ERR_INVALID, PANO_ERR_CUDA, PANO_ERR_NO_MATCHES, PANO_ERR_TOO_FEW_MATCHES = 1, 2, 3, 4
+PANO_ERR_NO_HOMOGRAPHY, PANO_ERR_ROI, PANO_ERR_CAPACITY, PANO_ERR_UNSUPPORTED, PANO_ERR_NO_DEVICE = 5, 6, 7, 8, 9
+STATUS_NAMES = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NO_MATCHES", 4: "TOO_FEW_MATCHES", 5: "NO_HOMOGRAPHY",
+                6: "ROI", 7: "CAPACITY", 8: "UNSUPPORTED", 9: "NO_DEVICE"}
+MEM_HOST, MEM_DEVICE = 0, 1
+
+MATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("distance", "<f4")])
+
+# every symbol include/pano_b200.h declares
+EXPORTED_SYMBOLS = [
+    "pano_default_harris_opts", "pano_default_ransac_opts", "pano_create", "pano_destroy", "pano_set_seed",
+    "pano_last_error", "pano_version", "pano_kernel_launches", "pano_set_matcher", "pano_detect",
+    "pano_harris_response", "pano_convolve_f64", "pano_match", "pano_ransac", "pano_canvas_geometry",
+    "pano_warp_overlay", "pano_warp_perspective", "pano_stitch_pair", "pano_get_canvas", "pano_canvas_device",
+    "pano_stitch_fold",
+]
+
+
+class HarrisCornerOptions(C.Structure):
+    """ref: src/serial/main.cpp:28-34"""
+    _fields_ = [("k_", C.c_double), ("nmsThresh_", C.c_double), ("nmsNeighborhood_", C.c_int),
+                ("patchSize_", C.c_int), ("maxSSDThresh_", C.c_double)]
+
+    def __init__(self, k_=0.04, nmsThresh_=1e6, nmsNeighborhood_=3, patchSize_=5, maxSSDThresh_=1e8):
+        super().__init__(k_, nmsThresh_, nmsNeighborhood_, patchSize_, maxSSDThresh_)
+
+
+class RansacOptions(C.Structure):
+    """ref: src/serial/main.cpp:36-40, src/gpu/ransac.cuh:10-14"""
+    _fields_ = [("numIterations_", C.c_int), ("numSamples_", C.c_int), ("distanceThreshold_", C.c_double)]
+
+    def __init__(self, numIterations_=1000, numSamples_=4, distanceThreshold_=3.0):
+        super().__init__(numIterations_, numSamples_, distanceThreshold_)
+
+
+class CanvasInfo(C.Structure):
+    _fields_ = [("canvas_w", C.c_int), ("canvas_h", C.c_int), ("left_x", C.c_int), ("left_y", C.c_int),
+                ("TH", C.c_double * 9)]
+
+
+class PairResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("n_kp_left", C.c_int), ("n_kp_right", C.c_int), ("n_matches", C.c_int),
+                ("best_inliers", C.c_int), ("best_iteration", C.c_int), ("H", C.c_double * 9),
+                ("canvas", CanvasInfo), ("ms_detect", C.c_float), ("ms_match", C.c_float),
+                ("ms_ransac", C.c_float), ("ms_warp", C.c_float), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return dict(status=self.status, status_name=STATUS_NAMES.get(self.status, str(self.status)),
+                    kl=self.n_kp_left, kr=self.n_kp_right, m=self.n_matches, best=self.best_inliers,
+                    best_iter=self.best_iteration, H=np.array(self.H[:], np.float64).reshape(3, 3),
+                    canvas=(self.canvas.canvas_w, self.canvas.canvas_h, self.canvas.left_x, self.canvas.left_y),
+                    ms=dict(detect=self.ms_detect, match=self.ms_match, ransac=self.ms_ransac,
+                            warp=self.ms_warp, total=self.ms_total))
+
+
+class PanoError(RuntimeError):
+    def __init__(self, status, msg=""):
+        super().__init__("pano_b200: %s (%d) %s" % (STATUS_NAMES.get(status, "?"), status, msg))
+        self.status = status
+
+
+def build(verbose=False):
+    """Compile libpano_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", _HERE, "-j8"], stdout=out)
+    return LIB_PATH
+
+
+def load_library():
+    """Loads the C-ABI library.  Raises if it has not been built: there is no fallback."""
+    if not os.path.exists(LIB_PATH):
+        raise PanoError(PANO_ERR_NO_DEVICE, "libpano_b200.so is not built (run __graft_entry__.build())")
+    lib = C.CDLL(LIB_PATH)
+    lib.pano_last_error.restype = C.c_char_p
+    lib.pano_version.restype = C.c_char_p
+    lib.pano_kernel_launches.restype = C.c_uint64
+    return lib
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+class _Img:
+    """pointer / geometry of an image argument (numpy host array or CUDA torch tensor)"""
+
+    def __init__(self, img):
+        if _is_torch_cuda(img):
+            assert img.dim() == 3 and img.shape[2] == 3 and str(img.dtype) == "torch.uint8"
+            assert img.stride(2) == 1 and img.stride(1) == 3
+            self.keep = img
+            self.ptr = C.c_void_p(img.data_ptr())
+            self.h, self.w = int(img.shape[0]), int(img.shape[1])
+            self.stride = int(img.stride(0))
+            self.mem = MEM_DEVICE
+        else:
+            a = np.asarray(img)
+            assert a.ndim == 3 and a.shape[2] == 3 and a.dtype == np.uint8
+            if a.strides[2] != 1 or a.strides[1] != 3:
+                a = np.ascontiguousarray(a)
+            self.keep = a
+            self.ptr = C.c_void_p(a.ctypes.data)
+            self.h, self.w = a.shape[0], a.shape[1]
+            self.stride = a.strides[0]
+            self.mem = MEM_HOST
+
+
+class Engine:
+    """One context = one device + one stream (ref: single-threaded caller)."""
+
+    def __init__(self, device=0, seed=12345):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        st = self.lib.pano_create(int(device), C.c_uint32(seed), C.byref(self.ctx))
+        if st != PANO_OK:
+            self.ctx = None
+            raise PanoError(st, "pano_create failed (an sm_100 GPU is required; there is no CPU path)")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.pano_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st, allow=()):
+        if st != PANO_OK and st not in allow:
+            raise PanoError(st, (self.lib.pano_last_error(self.ctx) or b"").decode())
+        return st
+
+    def set_seed(self, seed):
+        self._check(self.lib.pano_set_seed(self.ctx, C.c_uint32(seed)))
+
+    def set_matcher(self, which):
+        """0 = tensor-core matcher (product), 1 = SIMT cross-check kernel"""
+        self._check(self.lib.pano_set_matcher(self.ctx, int(which)))
+
+    def kernel_launches(self):
+        return int(self.lib.pano_kernel_launches(self.ctx))
+
+    # ---- stage entry points (reference names) ----------------------------------------
+    def gpuHarrisCornerDetectorDetect(self, image, k=0.04, nmsThresh=1e6, nmsNeighborhood=3):
+        im = _Img(image)
+        assert im.mem == MEM_HOST, "stage API with device images: use detect_device"
+        opts = HarrisCornerOptions(k, nmsThresh, nmsNeighborhood)
+        count = C.c_int(0)
+        self._check(self.lib.pano_detect(self.ctx, im.ptr, im.w, im.h, C.c_size_t(im.stride), im.mem, C.byref(opts),
+                                         None, 0, C.byref(count)))
+        xy = np.empty((max(count.value, 1), 2), np.int32)
+        self._check(self.lib.pano_detect(self.ctx, im.ptr, im.w, im.h, C.c_size_t(im.stride), im.mem, C.byref(opts),
+                                         xy.ctypes.data_as(C.c_void_p), count.value, C.byref(count)))
+        return xy[:count.value]
+
+    def harrisResponse(self, image, k=0.04):
+        im = _Img(image)
+        assert im.mem == MEM_HOST
+        out = np.empty((im.h, im.w), np.float64)
+        self._check(self.lib.pano_harris_response(self.ctx, im.ptr, im.w, im.h, C.c_size_t(im.stride), im.mem,
+                                                  C.c_double(k), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def convolveCUDA(self, input64f, kernel):
+        a = np.ascontiguousarray(input64f, np.float64)
+        kern = np.ascontiguousarray(kernel, np.float64)
+        out = np.empty_like(a)
+        self._check(self.lib.pano_convolve_f64(self.ctx, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0],
+                                               kern.ctypes.data_as(C.c_void_p), kern.shape[0], MEM_HOST,
+                                               out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def gpuHarrisMatchKeyPoints(self, keypointsL, keypointsR, image1, image2, patchSize=5, maxSSDThresh=1e8,
+                                offset=0):
+        """(query keypoints, train keypoints, query image, train image) as in the reference."""
+        kq = np.ascontiguousarray(keypointsL, np.int32).reshape(-1, 2)
+        kt = np.ascontiguousarray(keypointsR, np.int32).reshape(-1, 2)
+        iq, it = _Img(image1), _Img(image2)
+        assert iq.mem == MEM_HOST and it.mem == MEM_HOST
+        opts = HarrisCornerOptions(patchSize_=patchSize, maxSSDThresh_=maxSSDThresh)
+        out = np.empty(max(len(kq), 1), MATCH_DTYPE)
+        count = C.c_int(0)
+        self._check(self.lib.pano_match(self.ctx, kq.ctypes.data_as(C.c_void_p), len(kq),
+                                        kt.ctypes.data_as(C.c_void_p), len(kt), iq.ptr, iq.w, iq.h,
+                                        C.c_size_t(iq.stride), it.ptr, it.w, it.h, C.c_size_t(it.stride), MEM_HOST,
+                                        C.byref(opts), int(offset), out.ctypes.data_as(C.c_void_p), len(out),
+                                        C.byref(count)))
+        return out[:count.value]
+
+    def computeHomography(self, keypoints1, keypoints2, matches, options=None, details=False):
+        """GpuRansacHomographyCalculator::computeHomography.  Returns H (3x3) or None (the
+        reference's empty Mat); with details=True a dict with samples/counts/inlier mask."""
+        o = options or RansacOptions()
+        k1 = np.ascontiguousarray(keypoints1, np.int32).reshape(-1, 2)
+        k2 = np.ascontiguousarray(keypoints2, np.int32).reshape(-1, 2)
+        m = np.ascontiguousarray(matches, MATCH_DTYPE)
+        H = np.zeros((3, 3), np.float64)
+        best, best_iter = C.c_int(0), C.c_int(-1)
+        it = max(o.numIterations_, 1)
+        samples = np.full((it, 4), -1, np.int32)
+        counts = np.full(it, -2, np.int32)
+        mask = np.zeros(max(len(m), 1), np.uint8)
+        st = self.lib.pano_ransac(self.ctx, k1.ctypes.data_as(C.c_void_p), len(k1), k2.ctypes.data_as(C.c_void_p),
+                                  len(k2), m.ctypes.data_as(C.c_void_p), len(m), MEM_HOST, C.byref(o),
+                                  H.ctypes.data_as(C.c_void_p), C.byref(best), C.byref(best_iter),
+                                  samples.ctypes.data_as(C.c_void_p) if details else None,
+                                  counts.ctypes.data_as(C.c_void_p) if details else None,
+                                  mask.ctypes.data_as(C.c_void_p) if details else None)
+        self._check(st, allow=(PANO_ERR_TOO_FEW_MATCHES, PANO_ERR_NO_HOMOGRAPHY))
+        Hret = H if st == PANO_OK else None
+        if not details:
+            return Hret
+        return dict(ok=st == PANO_OK, status=st, H=Hret, best_count=best.value, best_iter=best_iter.value,
+                    samples=samples, counts=counts, inlier_mask=mask[:len(m)].astype(bool))
+
+    def canvasGeometry(self, wl, hl, wr, hr, H):
+        H = np.ascontiguousarray(H, np.float64)
+        info = CanvasInfo()
+        st = self.lib.pano_canvas_geometry(wl, hl, wr, hr, H.ctypes.data_as(C.c_void_p), C.byref(info))
+        return st == PANO_OK, (info.canvas_w, info.canvas_h, info.left_x, info.left_y), \
+            np.array(info.TH[:], np.float64).reshape(3, 3)
+
+    def warpPerspective(self, src, M, dsize):
+        im = _Img(src)
+        assert im.mem == MEM_HOST
+        M = np.ascontiguousarray(M, np.float64)
+        dw, dh = dsize
+        dst = np.empty((dh, dw, 3), np.uint8)
+        self._check(self.lib.pano_warp_perspective(self.ctx, im.ptr, im.w, im.h, C.c_size_t(im.stride), MEM_HOST,
+                                                   M.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p),
+                                                   dw, dh, C.c_size_t(dst.strides[0])))
+        return dst
+
+    def warpOverlay(self, left, right, H):
+        """warp + left copy + overlay of stitchTwoImages for a given H; None if the ROI fails."""
+        L, R = _Img(left), _Img(right)
+        assert L.mem == MEM_HOST and R.mem == MEM_HOST
+        H = np.ascontiguousarray(H, np.float64)
+        ok, (cw, ch, _, _), _ = self.canvasGeometry(L.w, L.h, R.w, R.h, H)
+        if not ok:
+            return None
+        canvas = np.empty((ch, cw, 3), np.uint8)
+        info = CanvasInfo()
+        self._check(self.lib.pano_warp_overlay(self.ctx, L.ptr, L.w, L.h, C.c_size_t(L.stride), R.ptr, R.w, R.h,
+                                               C.c_size_t(R.stride), MEM_HOST, H.ctypes.data_as(C.c_void_p),
+                                               canvas.ctypes.data_as(C.c_void_p), C.c_size_t(canvas.strides[0]),
+                                               C.c_size_t(canvas.nbytes), C.byref(info)))
+        return canvas
+
+    # ---- fused pipeline ----------------------------------------------------------------
+    def stitchTwoImages(self, leftImage, rightImage, harrisOpts=None, ransacOpts=None, fetch=True):
+        """ref: stitchTwoImages.  Returns (canvas or None, result dict).  With CUDA tensors as
+        inputs and fetch=False nothing but the small result record crosses PCIe."""
+        ho, ro = harrisOpts or HarrisCornerOptions(), ransacOpts or RansacOptions()
+        L, R = _Img(leftImage), _Img(rightImage)
+        assert L.mem == R.mem
+        res = PairResult()
+        st = self.lib.pano_stitch_pair(self.ctx, L.ptr, L.w, L.h, C.c_size_t(L.stride), R.ptr, R.w, R.h,
+                                       C.c_size_t(R.stride), L.mem, C.byref(ho), C.byref(ro), C.byref(res))
+        self._check(st, allow=(PANO_ERR_NO_MATCHES, PANO_ERR_TOO_FEW_MATCHES, PANO_ERR_NO_HOMOGRAPHY, PANO_ERR_ROI))
+        d = res.as_dict()
+        canvas = None
+        if st == PANO_OK and fetch:
+            canvas = self.getCanvas(device=(L.mem == MEM_DEVICE))
+        return canvas, d
+
+    def getCanvas(self, device=False, out=None):
+        w, h = C.c_int(0), C.c_int(0)
+        self._check(self.lib.pano_get_canvas(self.ctx, None, 0, 0, MEM_HOST, C.byref(w), C.byref(h)))
+        if device:
+            import torch
+            t = out if out is not None else torch.empty((h.value, w.value, 3), dtype=torch.uint8,
+                                                        device="cuda:%d" % self.device)
+            self._check(self.lib.pano_get_canvas(self.ctx, C.c_void_p(t.data_ptr()), C.c_size_t(t.stride(0)),
+                                                 C.c_size_t(t.numel()), MEM_DEVICE, C.byref(w), C.byref(h)))
+            return t
+        a = out if out is not None else np.empty((h.value, w.value, 3), np.uint8)
+        self._check(self.lib.pano_get_canvas(self.ctx, a.ctypes.data_as(C.c_void_p), C.c_size_t(a.strides[0]),
+                                             C.c_size_t(a.nbytes), MEM_HOST, C.byref(w), C.byref(h)))
+        return a
+
+    def stitchAllImages(self, images, harrisOpts=None, ransacOpts=None, fetch=True):
+        """ref: stitchAllImages (left fold).  Returns (panorama, [per-step result dicts])."""
+        ho, ro = harrisOpts or HarrisCornerOptions(), ransacOpts or RansacOptions()
+        ims = [_Img(i) for i in images]
+        n = len(ims)
+        assert n >= 1 and all(i.mem == ims[0].mem for i in ims)
+        ptrs = (C.c_void_p * n)(*[i.ptr for i in ims])
+        ws = (C.c_int * n)(*[i.w for i in ims])
+        hs = (C.c_int * n)(*[i.h for i in ims])
+        ss = (C.c_size_t * n)(*[i.stride for i in ims])
+        results = (PairResult * max(n - 1, 1))()
+        self._check(self.lib.pano_stitch_fold(self.ctx, ptrs, ws, hs, ss, n, ims[0].mem, C.byref(ho), C.byref(ro),
+                                              results))
+        pano = self.getCanvas(device=(ims[0].mem == MEM_DEVICE)) if fetch else None
+        return pano, [results[i].as_dict() for i in range(n - 1)]
+
+
+# reference-style free functions bound to a default engine ------------------------------
+_default = None
+
+
+def default_engine():
+    global _default
+    if _default is None:
+        _default = Engine()
+    return _default
+
+
+class GpuRansacHomographyCalculator:
+    """ref: src/gpu/ransac.cuh:8-36"""
+    Options = RansacOptions
+
+    def __init__(self, options=None, engine=None):
+        self.options_ = options or RansacOptions()
+        self.engine = engine or default_engine()
+
+    def computeHomography(self, keypoints1, keypoints2, matches):
+        return self.engine.computeHomography(keypoints1, keypoints2, matches, self.options_)

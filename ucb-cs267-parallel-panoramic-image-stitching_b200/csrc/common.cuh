@@ -1,0 +1,163 @@
+// common.cuh — internal declarations shared by the engine's translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pano_b200.h"
+#include "pano_core.cuh"
+
+namespace pano {
+
+struct CudaError {
+  cudaError_t e;
+  const char* what;
+  const char* file;
+  int line;
+};
+
+#define PANO_CUDA(expr)                                                  \
+  do {                                                                   \
+    cudaError_t e__ = (expr);                                            \
+    if (e__ != cudaSuccess) throw ::pano::CudaError{e__, #expr, __FILE__, __LINE__}; \
+  } while (0)
+
+// every engine kernel launch goes through this: counts it and surfaces launch errors
+extern uint64_t g_kernel_launches;
+#define PANO_LAUNCH_CHECK()            \
+  do {                                 \
+    ++::pano::g_kernel_launches;       \
+    PANO_CUDA(cudaGetLastError());     \
+  } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) PANO_CUDA(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    PANO_CUDA(cudaMalloc(&p, want));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) PANO_CUDA(cudaFreeHost(p));
+    p = nullptr;
+    cap = 0;
+    PANO_CUDA(cudaMallocHost(&p, bytes + bytes / 4 + 256));
+    cap = bytes + bytes / 4 + 256;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// A BGR8 image resident on the device.
+struct DevImage {
+  const uint8_t* p = nullptr;
+  int w = 0, h = 0;
+  size_t stride = 0;
+};
+
+// Keypoints of one image, resident on the device, in the reference's row-major order.
+struct DevKeypoints {
+  DevBuf xy;       // int32 (x, y) pairs
+  int count = 0;
+};
+
+// Descriptors of the in-border keypoints of one image (patch bytes, zero padded rows).
+struct DevDescriptors {
+  DevBuf desc;     // [count_pad][PANO_DESC_STRIDE] u8
+  DevBuf norm;     // u32 sum of squares per row
+  DevBuf orig;     // int32 index into the full keypoint list
+  int count = 0;   // in-border keypoints
+};
+
+constexpr int PANO_DESC_STRIDE = 128;  // bytes per descriptor row (75 used for a 5x5x3 patch)
+
+// ---- kernels' host launchers (one per .cu) ---------------------------------------------
+struct HarrisScratch {
+  DevBuf resp, mask, rowcnt, rowoff, total;
+};
+// Runs gray->Sobel->Gaussian->response (+optional copy-out), NMS mask, ordered compaction.
+// Leaves the keypoints in kp (device) and returns their number.
+int harris_detect_device(cudaStream_t st, const DevImage& img, const pano_harris_opts& o,
+                         HarrisScratch& s, DevKeypoints& kp, PinnedBuf& pin);
+void harris_response_device(cudaStream_t st, const DevImage& img, double k, double* resp_dev);
+void convolve_f64_device(cudaStream_t st, const double* in, int w, int h, const double* kern_dev,
+                         int ksize, double* out);
+
+// exclusive scan of n uint32 (single block); writes total to *total_dev if non-null
+void exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, int n, uint32_t* total_dev);
+
+// stable compaction of indices i in [0,n) with flags[i] != 0; out_idx gets the indices,
+// *count_dev the count.  tmp must hold 2*ceil(n/256)+2 uint32.
+void compact_flagged(cudaStream_t st, const uint8_t* flags, int n, int32_t* out_idx,
+                     uint32_t* count_dev, DevBuf& tmp);
+
+struct MatchScratch {
+  DevBuf flags, tmp, best, cnt, mflags, midx, mtmp;
+};
+int build_descriptors_device(cudaStream_t st, const DevImage& img, const int32_t* xy, int n, int patch,
+                             MatchScratch& s, DevDescriptors& d, PinnedBuf& pin);
+// best[i] = (ssd << 32 | j) over all train descriptors, lowest j on ties
+void match_simt_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
+                       unsigned long long* best);
+void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
+                     unsigned long long* best);
+bool match_tc_available();
+// turns best[] into pano_match records (ascending query order), applying maxSSD; returns count
+int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
+                        const unsigned long long* best, double max_ssd, int offset, int patch,
+                        MatchScratch& s, pano_dmatch* out_dev, PinnedBuf& pin);
+
+struct RansacScratch {
+  DevBuf pts, thr, cand_off, cand_samp, base, samples, Hs, valid, counts, result, mask, plan;
+};
+struct RansacResult {
+  int status;  // PANO_OK / PANO_ERR_*
+  double H[9];
+  int best_count, best_iter;
+};
+struct MtStream {
+  DevBuf x;           // uint32 outputs of std::mt19937(seed)
+  uint64_t len = 0;   // outputs generated so far
+  uint64_t guard = 0; // never-rejecting guard words after the stream
+  uint32_t seed = 0;
+  bool valid = false;
+  DevBuf state;       // 624-word engine state to continue from
+};
+void mt_ensure(cudaStream_t st, MtStream& mt, uint32_t seed, uint64_t need, uint64_t guard);
+RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_t* kp2_dev,
+                           const pano_dmatch* matches_dev, int m, const pano_ransac_opts& o,
+                           uint32_t seed, MtStream& mt, RansacScratch& s, PinnedBuf& pin,
+                           int32_t* samples_out_host, int32_t* counts_out_host,
+                           uint8_t* mask_out_host, int window_scale);
+
+void warp_overlay_device(cudaStream_t st, const DevImage& left, const DevImage& right,
+                         const CanvasGeom& g, uint8_t* canvas, size_t canvas_stride);
+void warp_only_device(cudaStream_t st, const DevImage& src, const double* Minv, int bw0, uint8_t* dst,
+                      int dw, int dh, size_t dstride);
+
+}  // namespace pano

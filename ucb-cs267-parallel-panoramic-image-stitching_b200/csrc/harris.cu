@@ -1,0 +1,332 @@
+// harris.cu — K1 Harris response (gray -> Sobel -> products -> 5x5 Gaussian -> response),
+// K2 strict NMS into a bit mask, ordered (row-major) compaction into a keypoint list.
+//
+// Semantics: ref src/serial/main.cpp:119-185 (seqHarrisCornerDetectorDetect) and :96-116
+// (convolveSequential).  The response is bit-identical to the reference's FP64 pipeline:
+//  - gray is OpenCV's 15-bit fixed point BGR2GRAY;
+//  - Sobel sums and the three products are small integers, exact in FP64 in any order;
+//  - the 5x5 Gaussian is accumulated in the reference's order (rows outer, columns inner,
+//    one accumulator from 0.0) with separately rounded multiply and add (__dmul_rn /
+//    __dadd_rn, never FMA);
+//  - borders: Sobel output is 0 on the outer ring, Gaussian output 0 on the outer 2 px, and
+//    the Gaussian reads the zero Sobel ring.
+// Roofline: FP64-pipe bound (157 non-fusable FP64 ops per pixel against 3 B/px of input).
+#include "common.cuh"
+
+namespace pano {
+
+namespace {
+
+constexpr int TX = 32;        // tile width  (one warp spans a tile row)
+constexpr int TY = 32;        // tile height
+constexpr int RPT = 4;        // output rows per thread (vertical strip)
+constexpr int BY = TY / RPT;  // 8 thread rows -> 256 threads
+constexpr int PW = TX + 4, PH = TY + 4;  // product planes incl. Gaussian halo
+constexpr int GW = TX + 6, GH = TY + 6;  // gray incl. Sobel halo
+
+struct GaussTaps {
+  double g[25];
+};
+
+__global__ void __launch_bounds__(TX* BY)
+harris_response_kernel(const uint8_t* __restrict__ img, int w, int h, size_t stride, double kparam,
+                       GaussTaps taps, double* __restrict__ resp) {
+  __shared__ uint8_t sgray[GH][GW + 2];
+  __shared__ double sxx[PH][PW];
+  __shared__ double syy[PH][PW];
+  __shared__ double sxy[PH][PW];
+
+  const int tid = threadIdx.y * TX + threadIdx.x;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+
+  // phase 1: gray tile with a 3-px halo (values outside the image are never used)
+  for (int i = tid; i < GH * GW; i += TX * BY) {
+    int gy = i / GW, gx = i - gy * GW;
+    int X = x0 - 3 + gx, Y = y0 - 3 + gy;
+    int v = 0;
+    if (X >= 0 && X < w && Y >= 0 && Y < h) {
+      const uint8_t* p = img + (size_t)Y * stride + 3 * (size_t)X;
+      v = gray_u8(p[0], p[1], p[2]);
+    }
+    sgray[gy][gx] = (uint8_t)v;
+  }
+  __syncthreads();
+
+  // phase 2: Sobel (integer, exact) and the three products on the tile + 2-px halo
+  for (int i = tid; i < PH * PW; i += TX * BY) {
+    int py = i / PW, px = i - py * PW;
+    int X = x0 - 2 + px, Y = y0 - 2 + py;
+    int gx = 0, gy = 0;
+    if (X >= 1 && X <= w - 2 && Y >= 1 && Y <= h - 2) {
+      int r = py + 1, c = px + 1;
+      int a00 = sgray[r - 1][c - 1], a01 = sgray[r - 1][c], a02 = sgray[r - 1][c + 1];
+      int a10 = sgray[r][c - 1], a12 = sgray[r][c + 1];
+      int a20 = sgray[r + 1][c - 1], a21 = sgray[r + 1][c], a22 = sgray[r + 1][c + 1];
+      gx = (a02 - a00) + 2 * (a12 - a10) + (a22 - a20);
+      gy = (a20 - a00) + 2 * (a21 - a01) + (a22 - a02);
+    }
+    sxx[py][px] = (double)(gx * gx);
+    syy[py][px] = (double)(gy * gy);
+    sxy[py][px] = (double)(gx * gy);
+  }
+  __syncthreads();
+
+  // phase 3: 5x5 Gaussian of the three planes for a vertical strip of RPT pixels.  Input
+  // rows are visited in increasing order so every output accumulates its 25 terms in the
+  // reference's (row, column) order.
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  double axx[RPT], ayy[RPT], axy[RPT];
+#pragma unroll
+  for (int o = 0; o < RPT; o++) axx[o] = ayy[o] = axy[o] = 0.0;
+#pragma unroll
+  for (int r = 0; r < RPT + 4; r++) {
+    double vxx[5], vyy[5], vxy[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      vxx[j] = sxx[ty * RPT + r][tx + j];
+      vyy[j] = syy[ty * RPT + r][tx + j];
+      vxy[j] = sxy[ty * RPT + r][tx + j];
+    }
+#pragma unroll
+    for (int o = 0; o < RPT; o++) {
+      int i = r - o;  // kernel row for output o
+      if (i >= 0 && i < 5) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          double g = taps.g[i * 5 + j];
+          axx[o] = __dadd_rn(axx[o], __dmul_rn(vxx[j], g));
+          ayy[o] = __dadd_rn(ayy[o], __dmul_rn(vyy[j], g));
+          axy[o] = __dadd_rn(axy[o], __dmul_rn(vxy[j], g));
+        }
+      }
+    }
+  }
+  const int X = x0 + tx;
+#pragma unroll
+  for (int o = 0; o < RPT; o++) {
+    int Y = y0 + ty * RPT + o;
+    if (X < w && Y < h) {
+      double r = 0.0;
+      if (X >= 2 && X <= w - 3 && Y >= 2 && Y <= h - 3) r = harris_resp(axx[o], ayy[o], axy[o], kparam);
+      resp[(size_t)Y * w + X] = r;
+    }
+  }
+}
+
+// K2a: threshold + strict NMS over a (2*half+1)^2 neighbourhood -> bit mask + per-row counts.
+// ref: src/serial/main.cpp:157-180 (keep iff resp > thresh and resp > every neighbour).
+__global__ void nms_mask_kernel(const double* __restrict__ resp, int w, int h, double thresh, int half,
+                                uint32_t* __restrict__ mask, int mask_stride,
+                                uint32_t* __restrict__ rowcnt) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (y >= h) return;
+  bool keep = false;
+  if (x >= half && x < w - half && y >= half && y < h - half) {
+    double r = resp[(size_t)y * w + x];
+    if (r > thresh) {
+      keep = true;
+      for (int i = -half; i <= half && keep; i++)
+        for (int j = -half; j <= half; j++) {
+          if (i == 0 && j == 0) continue;
+          if (!(r > resp[(size_t)(y + i) * w + (x + j)])) { keep = false; break; }
+        }
+    }
+  }
+  unsigned b = __ballot_sync(0xffffffffu, keep);
+  if (threadIdx.x == 0) {
+    mask[(size_t)y * mask_stride + blockIdx.x] = b;
+    if (b) atomicAdd(&rowcnt[y], __popc(b));
+  }
+}
+
+// K2b: ordered scatter, one warp per image row.
+__global__ void scatter_keypoints_kernel(const uint32_t* __restrict__ mask, int mask_stride, int h,
+                                         const uint32_t* __restrict__ rowoff, int32_t* __restrict__ xy) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= h) return;
+  uint32_t base = rowoff[row];
+  for (int w0 = 0; w0 < mask_stride; w0 += 32) {
+    uint32_t word = (w0 + lane < mask_stride) ? mask[(size_t)row * mask_stride + w0 + lane] : 0u;
+    uint32_t c = __popc(word), incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    uint32_t pos = base + incl - c;
+    while (word) {
+      int b = __ffs(word) - 1;
+      word &= word - 1;
+      xy[2 * (size_t)pos] = (w0 + lane) * 32 + b;
+      xy[2 * (size_t)pos + 1] = row;
+      pos++;
+    }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// single-block exclusive scan with a running carry over chunks of blockDim.x
+__global__ void scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n,
+                            uint32_t* __restrict__ total) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t woff[32];
+  __shared__ uint32_t chunk_total;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t carry = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < n ? in[i] : 0u, incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t s = lane < nw ? wsum[lane] : 0u, si = s;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, si, d);
+        if (lane >= d) si += t;
+      }
+      woff[lane] = si - s;
+      if (lane == 31) chunk_total = si;
+    }
+    __syncthreads();
+    if (i < n) out[i] = carry + woff[wid] + incl - v;
+    carry += chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
+// generic FP64 correlation with a zero border (ref: convolveSequential / convolveCUDA)
+__global__ void convolve_f64_kernel(const double* __restrict__ in, int w, int h,
+                                    const double* __restrict__ kern, int ksize, double* __restrict__ out) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  int k = ksize / 2;
+  double sum = 0.0;
+  if (x >= k && x < w - k && y >= k && y < h - k) {
+    for (int i = -k; i <= k; i++)
+      for (int j = -k; j <= k; j++)
+        sum = __dadd_rn(sum, __dmul_rn(in[(size_t)(y + i) * w + (x + j)], kern[(k + i) * ksize + (k + j)]));
+  }
+  out[(size_t)y * w + x] = sum;
+}
+
+// block counts of flagged items (256 per block)
+__global__ void flag_count_kernel(const uint8_t* __restrict__ flags, int n, uint32_t* __restrict__ bc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int f = (i < n && flags[i]) ? 1 : 0;
+  int c = __syncthreads_count(f);
+  if (threadIdx.x == 0) bc[blockIdx.x] = c;
+}
+
+__global__ void flag_scatter_kernel(const uint8_t* __restrict__ flags, int n, const uint32_t* __restrict__ boff,
+                                    int32_t* __restrict__ out) {
+  __shared__ uint32_t wcnt[8];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  bool f = (i < n && flags[i]);
+  unsigned b = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) wcnt[wid] = __popc(b);
+  __syncthreads();
+  uint32_t off = boff[blockIdx.x];
+  for (int k = 0; k < wid; k++) off += wcnt[k];
+  if (f) out[off + __popc(b & ((1u << lane) - 1))] = i;
+}
+
+// getGaussianKernel(5, 1.0) exactly as the reference computes it on the host
+// (ref: src/serial/main.cpp:73-91; libm exp, row-major running sum, divide by the sum).
+GaussTaps make_taps() {
+  GaussTaps t;
+  const int ks = 5, half = 2;
+  const double sigma = 1.0;
+  double sum = 0.0;
+  for (int i = 0; i < ks; ++i) {
+    int x = i - half;
+    for (int j = 0; j < ks; ++j) {
+      int y = j - half;
+      t.g[i * ks + j] = exp(-(x * x + y * y) / (2 * sigma * sigma));
+      sum += t.g[i * ks + j];
+    }
+  }
+  for (int i = 0; i < 25; i++) t.g[i] /= sum;
+  return t;
+}
+
+}  // namespace
+
+void exclusive_scan_u32(cudaStream_t st, const uint32_t* in, uint32_t* out, int n, uint32_t* total_dev) {
+  scan_kernel<<<1, 1024, 0, st>>>(in, out, n, total_dev);
+  PANO_LAUNCH_CHECK();
+}
+
+void compact_flagged(cudaStream_t st, const uint8_t* flags, int n, int32_t* out_idx, uint32_t* count_dev,
+                     DevBuf& tmp) {
+  int nb = (n + 255) / 256;
+  if (nb < 1) nb = 1;
+  tmp.reserve(sizeof(uint32_t) * (2 * (size_t)nb + 2));
+  uint32_t* bc = tmp.as<uint32_t>();
+  uint32_t* bo = bc + nb;
+  flag_count_kernel<<<nb, 256, 0, st>>>(flags, n, bc);
+  PANO_LAUNCH_CHECK();
+  exclusive_scan_u32(st, bc, bo, nb, count_dev);
+  flag_scatter_kernel<<<nb, 256, 0, st>>>(flags, n, bo, out_idx);
+  PANO_LAUNCH_CHECK();
+}
+
+void harris_response_device(cudaStream_t st, const DevImage& img, double k, double* resp_dev) {
+  static const GaussTaps taps = make_taps();
+  dim3 grid((img.w + TX - 1) / TX, (img.h + TY - 1) / TY), block(TX, BY);
+  harris_response_kernel<<<grid, block, 0, st>>>(img.p, img.w, img.h, img.stride, k, taps, resp_dev);
+  PANO_LAUNCH_CHECK();
+}
+
+void convolve_f64_device(cudaStream_t st, const double* in, int w, int h, const double* kern_dev, int ksize,
+                         double* out) {
+  dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+  convolve_f64_kernel<<<grid, block, 0, st>>>(in, w, h, kern_dev, ksize, out);
+  PANO_LAUNCH_CHECK();
+}
+
+int harris_detect_device(cudaStream_t st, const DevImage& img, const pano_harris_opts& o, HarrisScratch& s,
+                         DevKeypoints& kp, PinnedBuf& pin) {
+  const int w = img.w, h = img.h;
+  const int mask_stride = (w + 31) / 32;
+  s.resp.reserve(sizeof(double) * (size_t)w * h);
+  s.mask.reserve(sizeof(uint32_t) * (size_t)mask_stride * h);
+  s.rowcnt.reserve(sizeof(uint32_t) * (size_t)h);
+  s.rowoff.reserve(sizeof(uint32_t) * (size_t)h);
+  s.total.reserve(sizeof(uint32_t));
+  pin.reserve(64);
+
+  harris_response_device(st, img, o.k, s.resp.as<double>());
+  PANO_CUDA(cudaMemsetAsync(s.rowcnt.p, 0, sizeof(uint32_t) * (size_t)h, st));
+  {
+    dim3 block(32, 8), grid(mask_stride, (h + 7) / 8);
+    nms_mask_kernel<<<grid, block, 0, st>>>(s.resp.as<double>(), w, h, o.nms_thresh, o.nms_neighborhood / 2,
+                                            s.mask.as<uint32_t>(), mask_stride, s.rowcnt.as<uint32_t>());
+    PANO_LAUNCH_CHECK();
+  }
+  exclusive_scan_u32(st, s.rowcnt.as<uint32_t>(), s.rowoff.as<uint32_t>(), h, s.total.as<uint32_t>());
+  PANO_CUDA(cudaMemcpyAsync(pin.p, s.total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  PANO_CUDA(cudaStreamSynchronize(st));
+  int n = (int)*pin.as<uint32_t>();
+  kp.count = n;
+  kp.xy.reserve(sizeof(int32_t) * 2 * (size_t)(n > 0 ? n : 1));
+  if (n > 0) {
+    int wpb = 8;
+    scatter_keypoints_kernel<<<(h + wpb - 1) / wpb, wpb * 32, 0, st>>>(s.mask.as<uint32_t>(), mask_stride, h,
+                                                                     s.rowoff.as<uint32_t>(), kp.xy.as<int32_t>());
+    PANO_LAUNCH_CHECK();
+  }
+  return n;
+}
+
+}  // namespace pano

@@ -1,0 +1,537 @@
+// pano_api.cu — the C ABI (include/pano_b200.h): context, stage entry points, and the fused
+// device-resident pair / fold pipelines.  Host-side orchestration mirrors
+// ref src/serial/main.cpp:311-414 (stitchTwoImages / stitchAllImages) and the stage
+// interfaces of ref src/gpu/*.cuh.  No CPU fallback anywhere: without an sm_100 device
+// pano_create fails and nothing else can be called.
+#include "common.cuh"
+
+#include <algorithm>
+#include <exception>
+#include <new>
+
+namespace pano {
+uint64_t g_kernel_launches = 0;
+}
+
+using namespace pano;
+
+struct pano_ctx {
+  int device = 0;
+  uint32_t seed = 0;
+  int matcher = 0;  // 0 tensor-core, 1 SIMT
+  cudaStream_t st = nullptr;
+  std::string err;
+  PinnedBuf pin;
+  DevBuf up[2];  // staging for host images
+  DevBuf kpup[2], mup;
+  HarrisScratch hs;
+  DevKeypoints kpL, kpR;
+  MatchScratch ms;
+  DevDescriptors dQ, dT;
+  DevBuf best, matches;
+  RansacScratch rs;
+  MtStream mt;
+  DevBuf tmp[3];
+  DevBuf canvas[2];
+  int cur = 0;
+  int cw = 0, ch = 0;
+  size_t cstride = 0;
+  bool has_canvas = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int fail(pano_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define API_TRY(c)                                  \
+  if (!(c)) return PANO_ERR_INVALID;                \
+  try {                                             \
+    PANO_CUDA(cudaSetDevice((c)->device));
+
+#define API_CATCH(c)                                                                        \
+  }                                                                                         \
+  catch (const CudaError& e) {                                                              \
+    char buf[512];                                                                          \
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e.e,                  \
+             cudaGetErrorString(e.e), e.file, e.line, e.what);                              \
+    (c)->err = buf;                                                                         \
+    cudaGetLastError();                                                                     \
+    return PANO_ERR_CUDA;                                                                   \
+  }                                                                                         \
+  catch (const std::exception& e) {                                                         \
+    (c)->err = e.what();                                                                    \
+    return PANO_ERR_CUDA;                                                                   \
+  }
+
+// Returns a device view of an image; host images are copied into staging slot `slot`.
+DevImage to_device(pano_ctx* c, const uint8_t* p, int w, int h, size_t stride, int mem, int slot) {
+  DevImage d;
+  d.w = w;
+  d.h = h;
+  if (mem == PANO_MEM_DEVICE) {
+    d.p = p;
+    d.stride = stride;
+    return d;
+  }
+  size_t pitch = align_up((size_t)w * 3, 256);
+  c->up[slot].reserve(pitch * h);
+  PANO_CUDA(cudaMemcpy2DAsync(c->up[slot].p, pitch, p, stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, c->st));
+  d.p = c->up[slot].as<uint8_t>();
+  d.stride = pitch;
+  return d;
+}
+
+const void* upload(pano_ctx* c, DevBuf& buf, const void* p, size_t bytes, int mem) {
+  if (mem == PANO_MEM_DEVICE || bytes == 0) return p;
+  buf.reserve(bytes);
+  PANO_CUDA(cudaMemcpyAsync(buf.p, p, bytes, cudaMemcpyHostToDevice, c->st));
+  return buf.p;
+}
+
+bool valid_image(const uint8_t* p, int w, int h, size_t stride) {
+  return p && w > 0 && h > 0 && stride >= (size_t)w * 3;
+}
+
+int check_harris(const pano_harris_opts& o) {
+  if (o.nms_neighborhood < 1 || o.nms_neighborhood % 2 == 0 || o.nms_neighborhood > 15) return PANO_ERR_UNSUPPORTED;
+  if (o.patch_size != 1 && o.patch_size != 3 && o.patch_size != 5) return PANO_ERR_UNSUPPORTED;
+  return PANO_OK;
+}
+
+void run_matcher(pano_ctx* c, const DevDescriptors& q, const DevDescriptors& t) {
+  c->best.reserve(sizeof(unsigned long long) * (size_t)std::max(q.count, 1));
+  if (c->matcher == 0 && match_tc_available())
+    match_tc_device(c->st, q, t, c->best.as<unsigned long long>());
+  else
+    match_simt_device(c->st, q, t, c->best.as<unsigned long long>());
+}
+
+// match stage on device-resident inputs; leaves matches in c->matches; returns count
+int match_on_device(pano_ctx* c, const int32_t* kq, int nq, const int32_t* kt, int nt, const DevImage& iq,
+                    const DevImage& it, const pano_harris_opts& o, int offset) {
+  int nqi = build_descriptors_device(c->st, iq, kq, nq, o.patch_size, c->ms, c->dQ, c->pin);
+  int nti = build_descriptors_device(c->st, it, kt, nt, o.patch_size, c->ms, c->dT, c->pin);
+  if (nqi == 0 || nti == 0) return 0;
+  run_matcher(c, c->dQ, c->dT);
+  c->matches.reserve(sizeof(pano_dmatch) * (size_t)nqi);
+  return emit_matches_device(c->st, c->dQ, c->dT, c->best.as<unsigned long long>(), o.max_ssd_thresh, offset,
+                             o.patch_size, c->ms, c->matches.as<pano_dmatch>(), c->pin);
+}
+
+RansacResult ransac_retry(pano_ctx* c, const int32_t* kp1, const int32_t* kp2, const pano_dmatch* m, int n,
+                          const pano_ransac_opts& o, int32_t* samples, int32_t* counts, uint8_t* mask) {
+  RansacResult r;
+  int scale = 1;
+  for (;;) {
+    r = ransac_device(c->st, kp1, kp2, m, n, o, c->seed, c->mt, c->rs, c->pin, samples, counts, mask, scale);
+    if (r.status >= 0 || scale >= 16) break;
+    scale *= 2;  // a speculation window was missed: re-run wider (exactness is never traded)
+  }
+  if (r.status < 0) {
+    c->err = "shuffle replay could not be resolved";
+    r.status = PANO_ERR_CUDA;
+  }
+  return r;
+}
+
+void fill_canvas_info(const CanvasGeom& g, pano_canvas_info* info) {
+  info->canvas_w = g.cw;
+  info->canvas_h = g.ch;
+  info->left_x = g.offx;
+  info->left_y = g.offy;
+  memcpy(info->TH, g.TH, sizeof g.TH);
+}
+
+// ref: src/serial/main.cpp:311-391.  left/right are device views.  On success the new
+// canvas is in c->canvas[c->cur].
+int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const pano_harris_opts& ho,
+                       const pano_ransac_opts& ro, pano_pair_result* res) {
+  memset(res, 0, sizeof *res);
+  res->best_iteration = -1;
+  cudaStream_t st = c->st;
+  PANO_CUDA(cudaEventRecord(c->ev[0], st));
+  // 1. corner detection (ref :316-317)
+  res->n_kp_left = harris_detect_device(st, L, ho, c->hs, c->kpL, c->pin);
+  res->n_kp_right = harris_detect_device(st, R, ho, c->hs, c->kpR, c->pin);
+  PANO_CUDA(cudaEventRecord(c->ev[1], st));
+  // 2. matching: right = query, left = train (ref :320)
+  int m = match_on_device(c, c->kpR.xy.as<int32_t>(), c->kpR.count, c->kpL.xy.as<int32_t>(), c->kpL.count, R, L,
+                          ho, 0);
+  res->n_matches = m;
+  PANO_CUDA(cudaEventRecord(c->ev[2], st));
+  auto finish = [&](int status) {
+    PANO_CUDA(cudaEventRecord(c->ev[4], st));
+    PANO_CUDA(cudaEventSynchronize(c->ev[4]));
+    cudaEventElapsedTime(&res->ms_detect, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&res->ms_match, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&res->ms_total, c->ev[0], c->ev[4]);
+    res->status = status;
+    return status;
+  };
+  if (m == 0) return finish(PANO_ERR_NO_MATCHES);
+  // 3. RANSAC (ref :327-332)
+  RansacResult rr = ransac_retry(c, c->kpR.xy.as<int32_t>(), c->kpL.xy.as<int32_t>(), c->matches.as<pano_dmatch>(),
+                                 m, ro, nullptr, nullptr, nullptr);
+  PANO_CUDA(cudaEventRecord(c->ev[3], st));
+  if (rr.status != PANO_OK) {
+    int s = finish(rr.status);
+    cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
+    return s;
+  }
+  memcpy(res->H, rr.H, sizeof rr.H);
+  res->best_inliers = rr.best_count;
+  res->best_iteration = rr.best_iter;
+  // 4. canvas geometry (ref :335-369), warp + overlay (ref :371-386)
+  CanvasGeom g;
+  canvas_geometry(L.w, L.h, R.w, R.h, rr.H, &g);
+  fill_canvas_info(g, &res->canvas);
+  if (!g.ok) {
+    int s = finish(PANO_ERR_ROI);
+    cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
+    return s;
+  }
+  int nxt = 1 - c->cur;
+  size_t pitch = align_up((size_t)g.cw * 3, 256);
+  c->canvas[nxt].reserve(pitch * (size_t)g.ch);
+  warp_overlay_device(st, L, R, g, c->canvas[nxt].as<uint8_t>(), pitch);
+  finish(PANO_OK);
+  cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
+  cudaEventElapsedTime(&res->ms_warp, c->ev[3], c->ev[4]);
+  c->cur = nxt;
+  c->cw = g.cw;
+  c->ch = g.ch;
+  c->cstride = pitch;
+  c->has_canvas = true;
+  return PANO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void pano_default_harris_opts(pano_harris_opts* o) {
+  o->k = 0.04;
+  o->nms_thresh = 1e6;
+  o->nms_neighborhood = 3;
+  o->patch_size = 5;
+  o->max_ssd_thresh = 1e8;
+}
+
+void pano_default_ransac_opts(pano_ransac_opts* o) {
+  o->num_iterations = 1000;
+  o->num_samples = 4;
+  o->distance_threshold = 3.0;
+}
+
+const char* pano_version(void) { return "pano_b200 0.1 (sm_100a)"; }
+
+int pano_create(int device, uint32_t seed, pano_ctx** out) {
+  if (!out) return PANO_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return PANO_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    cudaGetLastError();
+    return PANO_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+  }
+  pano_ctx* c = new (std::nothrow) pano_ctx();
+  if (!c) return PANO_ERR_INVALID;
+  c->device = device;
+  c->seed = seed;
+  try {
+    PANO_CUDA(cudaSetDevice(device));
+    PANO_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    for (auto& e : c->ev) PANO_CUDA(cudaEventCreate(&e));
+    c->pin.reserve(4096);
+  } catch (const CudaError&) {
+    cudaGetLastError();
+    delete c;
+    return PANO_ERR_CUDA;
+  }
+  *out = c;
+  return PANO_OK;
+}
+
+void pano_destroy(pano_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->st) cudaStreamSynchronize(c->st);
+  DevBuf* bufs[] = {&c->up[0], &c->up[1], &c->kpup[0], &c->kpup[1], &c->mup, &c->hs.resp, &c->hs.mask, &c->hs.rowcnt,
+                    &c->hs.rowoff, &c->hs.total, &c->kpL.xy, &c->kpR.xy, &c->ms.flags, &c->ms.tmp, &c->ms.best,
+                    &c->ms.cnt, &c->ms.mflags, &c->ms.midx, &c->ms.mtmp, &c->dQ.desc, &c->dQ.norm, &c->dQ.orig,
+                    &c->dT.desc, &c->dT.norm, &c->dT.orig, &c->best, &c->matches, &c->rs.pts, &c->rs.thr,
+                    &c->rs.cand_off, &c->rs.cand_samp, &c->rs.base, &c->rs.samples, &c->rs.Hs, &c->rs.valid,
+                    &c->rs.counts, &c->rs.result, &c->rs.mask, &c->rs.plan, &c->mt.x, &c->mt.state, &c->tmp[0],
+                    &c->tmp[1], &c->tmp[2], &c->canvas[0], &c->canvas[1]};
+  for (DevBuf* b : bufs) b->release();
+  c->pin.release();
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+
+int pano_set_seed(pano_ctx* c, uint32_t seed) {
+  if (!c) return PANO_ERR_INVALID;
+  c->seed = seed;
+  return PANO_OK;
+}
+
+int pano_set_matcher(pano_ctx* c, int which) {
+  if (!c || (which != 0 && which != 1)) return PANO_ERR_INVALID;
+  c->matcher = which;
+  return PANO_OK;
+}
+
+const char* pano_last_error(const pano_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+uint64_t pano_kernel_launches(const pano_ctx*) { return g_kernel_launches; }
+
+int pano_detect(pano_ctx* c, const uint8_t* bgr, int w, int h, size_t stride, int mem, const pano_harris_opts* opts,
+                int32_t* xy_out, int cap, int* count) {
+  API_TRY(c)
+  if (!valid_image(bgr, w, h, stride) || !opts || !count) return fail(c, PANO_ERR_INVALID, "pano_detect: bad argument");
+  if (int e = check_harris(*opts)) return fail(c, e, "pano_detect: unsupported option");
+  DevImage img = to_device(c, bgr, w, h, stride, mem, 0);
+  int n = harris_detect_device(c->st, img, *opts, c->hs, c->kpL, c->pin);
+  *count = n;
+  int ncopy = std::min(n, cap);
+  if (xy_out && ncopy > 0) {
+    PANO_CUDA(cudaMemcpyAsync(xy_out, c->kpL.xy.p, sizeof(int32_t) * 2 * (size_t)ncopy,
+                              mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
+  }
+  PANO_CUDA(cudaStreamSynchronize(c->st));
+  return (xy_out && n > cap) ? PANO_ERR_CAPACITY : PANO_OK;
+  API_CATCH(c)
+}
+
+int pano_harris_response(pano_ctx* c, const uint8_t* bgr, int w, int h, size_t stride, int mem, double k,
+                         double* resp_out) {
+  API_TRY(c)
+  if (!valid_image(bgr, w, h, stride) || !resp_out) return fail(c, PANO_ERR_INVALID, "pano_harris_response: bad argument");
+  DevImage img = to_device(c, bgr, w, h, stride, mem, 0);
+  size_t bytes = sizeof(double) * (size_t)w * h;
+  double* dst = resp_out;
+  if (mem == PANO_MEM_HOST) {
+    c->hs.resp.reserve(bytes);
+    dst = c->hs.resp.as<double>();
+  }
+  harris_response_device(c->st, img, k, dst);
+  if (mem == PANO_MEM_HOST) PANO_CUDA(cudaMemcpyAsync(resp_out, dst, bytes, cudaMemcpyDeviceToHost, c->st));
+  PANO_CUDA(cudaStreamSynchronize(c->st));
+  return PANO_OK;
+  API_CATCH(c)
+}
+
+int pano_convolve_f64(pano_ctx* c, const double* in, int w, int h, const double* kernel, int ksize, int mem,
+                      double* out) {
+  API_TRY(c)
+  if (!in || !out || !kernel || w <= 0 || h <= 0 || ksize < 1 || ksize % 2 == 0)
+    return fail(c, PANO_ERR_INVALID, "pano_convolve_f64: bad argument");
+  size_t bytes = sizeof(double) * (size_t)w * h;
+  const double* din = (const double*)upload(c, c->tmp[0], in, bytes, mem);
+  const double* dk = (const double*)upload(c, c->tmp[1], kernel, sizeof(double) * ksize * ksize, mem);
+  double* dout = out;
+  if (mem == PANO_MEM_HOST) {
+    c->tmp[2].reserve(bytes);
+    dout = c->tmp[2].as<double>();
+  }
+  convolve_f64_device(c->st, din, w, h, dk, ksize, dout);
+  if (mem == PANO_MEM_HOST) PANO_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, c->st));
+  PANO_CUDA(cudaStreamSynchronize(c->st));
+  return PANO_OK;
+  API_CATCH(c)
+}
+
+int pano_match(pano_ctx* c, const int32_t* kp_query, int n_query, const int32_t* kp_train, int n_train,
+               const uint8_t* img_query, int wq, int hq, size_t stride_q, const uint8_t* img_train, int wt, int ht,
+               size_t stride_t, int mem, const pano_harris_opts* opts, int offset, pano_dmatch* out, int cap,
+               int* count) {
+  API_TRY(c)
+  if (!valid_image(img_query, wq, hq, stride_q) || !valid_image(img_train, wt, ht, stride_t) || !opts || !count ||
+      n_query < 0 || n_train < 0 || (n_query > 0 && !kp_query) || (n_train > 0 && !kp_train))
+    return fail(c, PANO_ERR_INVALID, "pano_match: bad argument");
+  if (int e = check_harris(*opts)) return fail(c, e, "pano_match: unsupported option");
+  DevImage iq = to_device(c, img_query, wq, hq, stride_q, mem, 0);
+  DevImage it = to_device(c, img_train, wt, ht, stride_t, mem, 1);
+  const int32_t* kq = (const int32_t*)upload(c, c->kpup[0], kp_query, sizeof(int32_t) * 2 * (size_t)n_query, mem);
+  const int32_t* kt = (const int32_t*)upload(c, c->kpup[1], kp_train, sizeof(int32_t) * 2 * (size_t)n_train, mem);
+  int m = match_on_device(c, kq, n_query, kt, n_train, iq, it, *opts, offset);
+  *count = m;
+  int ncopy = std::min(m, cap);
+  if (out && ncopy > 0)
+    PANO_CUDA(cudaMemcpyAsync(out, c->matches.p, sizeof(pano_dmatch) * (size_t)ncopy,
+                              mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
+  PANO_CUDA(cudaStreamSynchronize(c->st));
+  return (out && m > cap) ? PANO_ERR_CAPACITY : PANO_OK;
+  API_CATCH(c)
+}
+
+int pano_ransac(pano_ctx* c, const int32_t* kp1, int n1, const int32_t* kp2, int n2, const pano_dmatch* matches,
+                int n_matches, int mem, const pano_ransac_opts* opts, double H_out[9], int* best_inliers,
+                int* best_iteration, int32_t* samples_out, int32_t* counts_out, uint8_t* inlier_mask_out) {
+  API_TRY(c)
+  if (!opts || !H_out || n1 < 0 || n2 < 0 || n_matches < 0 || (n_matches > 0 && (!kp1 || !kp2 || !matches)))
+    return fail(c, PANO_ERR_INVALID, "pano_ransac: bad argument");
+  if (opts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "pano_ransac: only num_samples == 4 is supported");
+  if (best_inliers) *best_inliers = 0;
+  if (best_iteration) *best_iteration = -1;
+  if (n_matches < opts->num_samples || opts->num_iterations <= 0) return PANO_ERR_TOO_FEW_MATCHES;
+  const int32_t* d1 = (const int32_t*)upload(c, c->kpup[0], kp1, sizeof(int32_t) * 2 * (size_t)n1, mem);
+  const int32_t* d2 = (const int32_t*)upload(c, c->kpup[1], kp2, sizeof(int32_t) * 2 * (size_t)n2, mem);
+  const pano_dmatch* dm = (const pano_dmatch*)upload(c, c->mup, matches, sizeof(pano_dmatch) * (size_t)n_matches, mem);
+  RansacResult r = ransac_retry(c, d1, d2, dm, n_matches, *opts, samples_out, counts_out, inlier_mask_out);
+  if (best_inliers) *best_inliers = r.best_count;
+  if (best_iteration) *best_iteration = r.best_iter;
+  if (r.status == PANO_OK) memcpy(H_out, r.H, sizeof r.H);
+  return r.status;
+  API_CATCH(c)
+}
+
+int pano_canvas_geometry(int wl, int hl, int wr, int hr, const double H[9], pano_canvas_info* out) {
+  if (!H || !out || wl <= 0 || hl <= 0 || wr <= 0 || hr <= 0) return PANO_ERR_INVALID;
+  CanvasGeom g;
+  canvas_geometry(wl, hl, wr, hr, H, &g);
+  fill_canvas_info(g, out);
+  return g.ok ? PANO_OK : PANO_ERR_ROI;
+}
+
+int pano_warp_overlay(pano_ctx* c, const uint8_t* left, int wl, int hl, size_t stride_l, const uint8_t* right, int wr,
+                      int hr, size_t stride_r, int mem, const double H[9], uint8_t* canvas_out, size_t canvas_stride,
+                      size_t canvas_cap_bytes, pano_canvas_info* info) {
+  API_TRY(c)
+  if (!valid_image(left, wl, hl, stride_l) || !valid_image(right, wr, hr, stride_r) || !H || !canvas_out)
+    return fail(c, PANO_ERR_INVALID, "pano_warp_overlay: bad argument");
+  CanvasGeom g;
+  canvas_geometry(wl, hl, wr, hr, H, &g);
+  if (info) fill_canvas_info(g, info);
+  if (!g.ok) return PANO_ERR_ROI;
+  if (canvas_stride < (size_t)g.cw * 3 || canvas_cap_bytes < canvas_stride * (size_t)(g.ch - 1) + (size_t)g.cw * 3)
+    return PANO_ERR_CAPACITY;
+  DevImage L = to_device(c, left, wl, hl, stride_l, mem, 0);
+  DevImage R = to_device(c, right, wr, hr, stride_r, mem, 1);
+  if (mem == PANO_MEM_DEVICE) {
+    warp_overlay_device(c->st, L, R, g, canvas_out, canvas_stride);
+  } else {
+    size_t pitch = align_up((size_t)g.cw * 3, 256);
+    c->tmp[0].reserve(pitch * (size_t)g.ch);
+    warp_overlay_device(c->st, L, R, g, c->tmp[0].as<uint8_t>(), pitch);
+    PANO_CUDA(cudaMemcpy2DAsync(canvas_out, canvas_stride, c->tmp[0].p, pitch, (size_t)g.cw * 3, g.ch,
+                                cudaMemcpyDeviceToHost, c->st));
+  }
+  PANO_CUDA(cudaStreamSynchronize(c->st));
+  return PANO_OK;
+  API_CATCH(c)
+}
+
+int pano_warp_perspective(pano_ctx* c, const uint8_t* src, int w, int h, size_t stride, int mem, const double M[9],
+                          uint8_t* dst, int dw, int dh, size_t dstride) {
+  API_TRY(c)
+  if (!valid_image(src, w, h, stride) || !M || !dst || dw <= 0 || dh <= 0 || dstride < (size_t)dw * 3)
+    return fail(c, PANO_ERR_INVALID, "pano_warp_perspective: bad argument");
+  double Minv[9];
+  invert33(M, Minv);
+  int bh0 = std::min(16, dh);
+  int bw0 = std::min(1024 / bh0, dw);
+  DevImage S = to_device(c, src, w, h, stride, mem, 0);
+  if (mem == PANO_MEM_DEVICE) {
+    warp_only_device(c->st, S, Minv, bw0, dst, dw, dh, dstride);
+  } else {
+    size_t pitch = align_up((size_t)dw * 3, 256);
+    c->tmp[0].reserve(pitch * (size_t)dh);
+    warp_only_device(c->st, S, Minv, bw0, c->tmp[0].as<uint8_t>(), dw, dh, pitch);
+    PANO_CUDA(cudaMemcpy2DAsync(dst, dstride, c->tmp[0].p, pitch, (size_t)dw * 3, dh, cudaMemcpyDeviceToHost, c->st));
+  }
+  PANO_CUDA(cudaStreamSynchronize(c->st));
+  return PANO_OK;
+  API_CATCH(c)
+}
+
+int pano_stitch_pair(pano_ctx* c, const uint8_t* left, int wl, int hl, size_t stride_l, const uint8_t* right, int wr,
+                     int hr, size_t stride_r, int mem, const pano_harris_opts* hopts, const pano_ransac_opts* ropts,
+                     pano_pair_result* res) {
+  API_TRY(c)
+  if (!valid_image(left, wl, hl, stride_l) || !valid_image(right, wr, hr, stride_r) || !hopts || !ropts || !res)
+    return fail(c, PANO_ERR_INVALID, "pano_stitch_pair: bad argument");
+  if (int e = check_harris(*hopts)) return fail(c, e, "pano_stitch_pair: unsupported option");
+  if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
+  DevImage L = to_device(c, left, wl, hl, stride_l, mem, 0);
+  DevImage R = to_device(c, right, wr, hr, stride_r, mem, 1);
+  return stitch_pair_device(c, L, R, *hopts, *ropts, res);
+  API_CATCH(c)
+}
+
+int pano_canvas_device(pano_ctx* c, const uint8_t** ptr, size_t* stride, int* w, int* h) {
+  if (!c || !c->has_canvas) return PANO_ERR_INVALID;
+  if (ptr) *ptr = c->canvas[c->cur].as<uint8_t>();
+  if (stride) *stride = c->cstride;
+  if (w) *w = c->cw;
+  if (h) *h = c->ch;
+  return PANO_OK;
+}
+
+int pano_get_canvas(pano_ctx* c, uint8_t* out, size_t out_stride, size_t cap_bytes, int mem, int* w, int* h) {
+  API_TRY(c)
+  if (!c->has_canvas) return fail(c, PANO_ERR_INVALID, "pano_get_canvas: no canvas");
+  if (w) *w = c->cw;
+  if (h) *h = c->ch;
+  if (!out) return PANO_OK;
+  if (out_stride < (size_t)c->cw * 3 || cap_bytes < out_stride * (size_t)(c->ch - 1) + (size_t)c->cw * 3)
+    return PANO_ERR_CAPACITY;
+  PANO_CUDA(cudaMemcpy2DAsync(out, out_stride, c->canvas[c->cur].p, c->cstride, (size_t)c->cw * 3, c->ch,
+                              mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
+  PANO_CUDA(cudaStreamSynchronize(c->st));
+  return PANO_OK;
+  API_CATCH(c)
+}
+
+int pano_stitch_fold(pano_ctx* c, const uint8_t* const* images, const int* ws, const int* hs, const size_t* strides,
+                     int n, int mem, const pano_harris_opts* hopts, const pano_ransac_opts* ropts,
+                     pano_pair_result* results) {
+  API_TRY(c)
+  if (!images || !ws || !hs || !strides || n < 1 || !hopts || !ropts)
+    return fail(c, PANO_ERR_INVALID, "pano_stitch_fold: bad argument");
+  for (int i = 0; i < n; i++)
+    if (!valid_image(images[i], ws[i], hs[i], strides[i])) return fail(c, PANO_ERR_INVALID, "pano_stitch_fold: bad image");
+  if (int e = check_harris(*hopts)) return fail(c, e, "pano_stitch_fold: unsupported option");
+  if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
+  // panorama = images[0] (ref :400): place it in the current canvas slot
+  {
+    size_t pitch = align_up((size_t)ws[0] * 3, 256);
+    c->canvas[c->cur].reserve(pitch * (size_t)hs[0]);
+    PANO_CUDA(cudaMemcpy2DAsync(c->canvas[c->cur].p, pitch, images[0], strides[0], (size_t)ws[0] * 3, hs[0],
+                                mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
+    c->cw = ws[0];
+    c->ch = hs[0];
+    c->cstride = pitch;
+    c->has_canvas = true;
+  }
+  for (int i = 1; i < n; i++) {
+    DevImage L;
+    L.p = c->canvas[c->cur].as<uint8_t>();
+    L.w = c->cw;
+    L.h = c->ch;
+    L.stride = c->cstride;
+    DevImage R = to_device(c, images[i], ws[i], hs[i], strides[i], mem, 1);
+    pano_pair_result r;
+    int s = stitch_pair_device(c, L, R, *hopts, *ropts, &r);
+    if (results) results[i - 1] = r;
+    if (s == PANO_ERR_CUDA) return s;
+    // any other failure: the reference logs and keeps the previous panorama (ref :404-407)
+  }
+  PANO_CUDA(cudaStreamSynchronize(c->st));
+  return PANO_OK;
+  API_CATCH(c)
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+"""Synthetic textured image pairs with a known homography (numpy only, deterministic).
+
+Used by tests and bench.py for the configs of BASELINE.json that have no image files
+("synthetic 3840x2160 textured pair with known homography", strips, batches).  A "world" image
+is smooth multi-octave colour noise plus many random filled rectangles (their corners are what
+the Harris detector fires on); the left view is a crop, the right view is the world resampled
+through a known homography (shift + small rotation + small perspective) plus +-2 LSB noise.
+"""
+import numpy as np
+
+
+def _upsample_bilinear(g, h, w):
+    gh, gw = g.shape[:2]
+    ys = np.linspace(0, gh - 1.001, h).astype(np.float32)
+    xs = np.linspace(0, gw - 1.001, w).astype(np.float32)
+    y0 = ys.astype(np.int32); fy = (ys - y0)[:, None, None]
+    x0 = xs.astype(np.int32); fx = (xs - x0)[None, :, None]
+    r0 = g[y0]; r1 = g[y0 + 1]
+    rows = r0 * (1 - fy) + r1 * fy            # (h, gw, 3)
+    return rows[:, x0] * (1 - fx) + rows[:, x0 + 1] * fx
+
+
+def make_world(h, w, seed, n_rect=None, rect_px=(10, 70)):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    img = np.full((h, w, 3), 96.0, np.float32)
+    for s, amp in ((128, 40.0), (48, 24.0), (16, 10.0)):
+        g = rng.uniform(-1, 1, (h // s + 3, w // s + 3, 3)).astype(np.float32)
+        img += amp * _upsample_bilinear(g, h, w)
+    if n_rect is None:
+        n_rect = int(h * w / 2600)
+    lo, hi = rect_px
+    xs = rng.integers(0, w, n_rect); ys = rng.integers(0, h, n_rect)
+    ws = rng.integers(lo, hi, n_rect); hs = rng.integers(lo, hi, n_rect)
+    cols = rng.uniform(0, 255, (n_rect, 3)).astype(np.float32)
+    for i in range(n_rect):
+        img[ys[i]:ys[i] + hs[i], xs[i]:xs[i] + ws[i]] = cols[i]
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def _sample_bilinear(world, X, Y):
+    H, W = world.shape[:2]
+    X = np.clip(X, 0, W - 1.001); Y = np.clip(Y, 0, H - 1.001)
+    x0 = X.astype(np.int32); y0 = Y.astype(np.int32)
+    fx = (X - x0)[..., None].astype(np.float32); fy = (Y - y0)[..., None].astype(np.float32)
+    w00 = world[y0, x0].astype(np.float32); w01 = world[y0, x0 + 1].astype(np.float32)
+    w10 = world[y0 + 1, x0].astype(np.float32); w11 = world[y0 + 1, x0 + 1].astype(np.float32)
+    return (w00 * (1 - fx) + w01 * fx) * (1 - fy) + (w10 * (1 - fx) + w11 * fx) * fy
+
+
+def make_pair(w=3840, h=2160, seed=267, overlap=0.5, rot_deg=0.3, persp=1e-6, noise=2, n_rect=None):
+    """Returns (left, right, H_true) with H_true mapping right-image to left-image coordinates."""
+    margin = max(16, h // 18)
+    shift = int(round(w * (1.0 - overlap)))
+    world = make_world(h + 2 * margin, w + shift + 2 * margin, seed, n_rect=n_rect)
+    left = np.ascontiguousarray(world[margin:margin + h, margin:margin + w])
+    # right pixel (x, y) looks at world point A @ (x, y, 1)
+    th = np.deg2rad(rot_deg)
+    cx, cy = w / 2.0, h / 2.0
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    C0 = np.array([[1, 0, -cx], [0, 1, -cy], [0, 0, 1.0]])
+    C1 = np.array([[1, 0, cx], [0, 1, cy], [0, 0, 1.0]])
+    P = np.array([[1, 0, 0], [0, 1, 0], [persp, -persp, 1.0]])
+    T = np.array([[1, 0, margin + shift], [0, 1, margin], [0, 0, 1.0]])
+    A = T @ C1 @ R @ P @ C0
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    den = A[2, 0] * xx + A[2, 1] * yy + A[2, 2]
+    X = (A[0, 0] * xx + A[0, 1] * yy + A[0, 2]) / den
+    Y = (A[1, 0] * xx + A[1, 1] * yy + A[1, 2]) / den
+    right = _sample_bilinear(world, X, Y)
+    rng = np.random.Generator(np.random.PCG64(seed + 1000003))
+    if noise:
+        right = right + rng.integers(-noise, noise + 1, right.shape)
+    right = np.clip(np.rint(right), 0, 255).astype(np.uint8)
+    H_true = np.array([[1, 0, -margin], [0, 1, -margin], [0, 0, 1.0]]) @ A
+    return left, np.ascontiguousarray(right), H_true / H_true[2, 2]
+
+
+def make_strip(n=8, w=2000, h=1500, seed=267, stride_frac=0.75, rot_deg=0.2, noise=2):
+    """n overlapping views cut left-to-right from one world (config: 8-image strip panorama)."""
+    stride = int(w * stride_frac)
+    margin = max(16, h // 15)
+    world = make_world(h + 2 * margin, stride * (n - 1) + w + 2 * margin, seed)
+    views = []
+    rng = np.random.Generator(np.random.PCG64(seed + 7))
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    for i in range(n):
+        if i == 0:
+            v = world[margin:margin + h, margin:margin + w].astype(np.float32)
+        else:
+            th = np.deg2rad(rot_deg * (1 if i % 2 else -1))
+            c, s = np.cos(th), np.sin(th)
+            X = c * (xx - w / 2) - s * (yy - h / 2) + w / 2 + margin + i * stride
+            Y = s * (xx - w / 2) + c * (yy - h / 2) + h / 2 + margin
+            v = _sample_bilinear(world, X, Y)
+            v = v + rng.integers(-noise, noise + 1, v.shape)
+        views.append(np.ascontiguousarray(np.clip(np.rint(v), 0, 255).astype(np.uint8)))
+    return views
