@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 stitching engine (BASELINE.json metric:
+"stitched MP/s and ms per 4K pair (detect+match+RANSAC+warp)").
+
+    python bench.py --gpus N --steps K --warmup W            # engine arm (1 process per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
+
+A step = one pass of the full hot path (detect both images, match, seeded RANSAC, warp +
+overlay) over one batch of P distinct synthetic 3840x2160 pairs per GPU (config 3 of
+BASELINE.json; P pairs = P*50 MB of input, larger than the 126 MB L2, rotating every step).
+`value`  : whole-job stitched MP/s (input megapixels of all ranks / max-over-ranks device time),
+           inputs already resident in HBM, canvases left in HBM.
+`e2e`    : the same metric through the C-ABI call with HOST (pinned) buffers: H2D of both images
+           and D2H of every canvas inside the timed region.
+`roofline`: the dominant kernel of the step, timed live with CUDA events on the engine's stream.
+`cpu_baseline`: the CPU oracle (restatement of the reference's serial path; the reference
+           itself needs OpenCV C++ and cannot be built here) on a bounded sample, rank 0 only.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "ucb-cs267-parallel-panoramic-image-stitching_b200"
+METRIC = "stitched_MP_per_s_4K_pair_detect_match_ransac_warp"
+UNIT = "MP/s"
+SEED = 12345
+
+
+def cached_pair(w, h, seed):
+    synth = importlib.import_module(PKG + ".synth")
+    d = os.environ.get("PANO_SYNTH_CACHE", "/tmp/pano_synth_cache")
+    os.makedirs(d, exist_ok=True)
+    f = os.path.join(d, "pair_%dx%d_%d.npz" % (w, h, seed))
+    if os.path.exists(f):
+        try:
+            z = np.load(f)
+            return z["left"], z["right"]
+        except Exception:
+            pass
+    left, right, H = synth.make_pair(w, h, seed=seed)
+    tmp = f + ".%d.tmp.npz" % os.getpid()
+    np.savez(tmp, left=left, right=right, H=H)
+    os.replace(tmp, f)
+    return left, right
+
+
+def peaks():
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(f):
+        p = json.load(open(f))
+        return p.get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU algorithm (oracle port; the reference needs OpenCV C++)
+# ----------------------------------------------------------------------------------------------
+def run_reference(a):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle
+    O = Oracle("omp")
+    cores = O.num_threads()
+    w, h = a.w, a.h
+    pairs = [cached_pair(w, h, 1000 + i) for i in range(max(1, min(a.pairs, 2)))]
+    times = []
+    for s in range(a.warmup + a.steps):
+        l, r = pairs[s % len(pairs)]
+        t0 = time.perf_counter()
+        res = O.stitch_pair(l, r, seed=SEED)
+        dt = time.perf_counter() - t0
+        assert res["status"] == 1
+        if s >= a.warmup:
+            times.append(dt)
+    mp = 2 * w * h / 1e6
+    tot = sum(times)
+    val = mp * len(times) / tot
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1000 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
+            "config": {"workload": "synthetic %dx%d textured pair, known homography (BASELINE config 3)" % (w, h),
+                       "pairs_per_step": 1, "seed": SEED},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d step(s) of 1 pair, oracle -O2 with OpenMP on %d threads "
+                                       "(reference needs OpenCV C++: not buildable here)" % (len(times), cores)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# engine arm
+# ----------------------------------------------------------------------------------------------
+def time_kernel(eng, torch, fn, reps=5):
+    """device time of fn() (which enqueues on the engine's stream and syncs) via CUDA events on
+    that stream"""
+    st = torch.cuda.ExternalStream(eng.stream_ptr())
+    best = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        fn()
+        e1.record(st)
+        e1.synchronize()
+        best.append(e0.elapsed_time(e1))
+    return statistics.median(best)
+
+
+def run_engine(a):
+    import torch
+    import ctypes as C
+    rank, world, local = dist_env()
+    pkg = importlib.import_module(PKG)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    eng = pkg.Engine(device=local, seed=SEED)
+    w, h, P = a.w, a.h, a.pairs
+    host = [cached_pair(w, h, 1000 + rank * P + i) for i in range(P)]
+    Ld = [torch.from_numpy(l).cuda() for l, _ in host]
+    Rd = [torch.from_numpy(r).cuda() for _, r in host]
+    Lh = [torch.from_numpy(l).pin_memory() for l, _ in host]
+    Rh = [torch.from_numpy(r).pin_memory() for _, r in host]
+    cap = 3 * (2 * w + 64) * (h + 256)
+    Ch = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(P)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        res, ms = eng.stitchBatch(Ld, Rd)
+        return res, ms
+
+    def step_e2e():
+        res, ms = eng.stitchBatch([t.numpy() for t in Lh], [t.numpy() for t in Rh],
+                                  canvases_out=[c.numpy() for c in Ch])
+        return res, ms
+
+    # ---- resident-input throughput --------------------------------------------------------
+    for _ in range(a.warmup):
+        res, _ = step_resident()
+    assert all(r["status"] == 0 for r in res), [r["status_name"] for r in res]
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    n0 = eng.kernel_launches()
+    ms_dev, t0 = 0.0, time.perf_counter()
+    stage = {"detect": 0.0, "match": 0.0, "ransac": 0.0, "warp": 0.0}
+    for _ in range(a.steps):
+        res, ms = step_resident()
+        ms_dev += ms
+        for r in res:
+            for k in stage:
+                stage[k] += r["ms"][k]
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = eng.kernel_launches() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end-to-end (host buffers) ----------------------------------------------------------
+    for _ in range(min(a.warmup, 2)):
+        step_e2e()
+    barrier()
+    ms_e2e = 0.0
+    for _ in range(a.steps):
+        res_e, ms = step_e2e()
+        ms_e2e += ms
+    barrier()
+    d2h = sum(3 * r["canvas"][0] * r["canvas"][1] for r in res_e)
+    h2d = P * 2 * 3 * w * h
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e, wall * 1000.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e, wall_ms = [float(x) for x in t]
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    else:
+        wall_ms = wall * 1000.0
+    mp_step = world * P * 2 * w * h / 1e6
+    value = mp_step * a.steps / (ms_dev / 1000.0)
+    e2e_val = mp_step * a.steps / (ms_e2e / 1000.0)
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel ------------------------------------------------
+        hbm, how = peaks()
+        npx = w * h
+        r0 = res[0]
+        stage_ms = {k: v / (a.steps * P) for k, v in stage.items()}
+        resp = torch.empty((h, w), dtype=torch.float64, device="cuda")
+        Limg = Ld[0]
+
+        def k_harris():
+            eng._check(eng.lib.pano_harris_response(eng.ctx, C.c_void_p(Limg.data_ptr()), w, h,
+                                                    C.c_size_t(Limg.stride(0)), 1, C.c_double(0.04),
+                                                    C.c_void_p(resp.data_ptr())))
+        t_harris = time_kernel(eng, torch, k_harris)
+        cw, ch = r0["canvas"][0], r0["canvas"][1]
+        pitch = (3 * cw + 255) // 256 * 256   # same pitched layout the fused path uses
+        canvas = torch.empty((ch, pitch), dtype=torch.uint8, device="cuda")
+        Hm = np.ascontiguousarray(r0["H"])
+        info = pkg.CanvasInfo()
+
+        def k_warp():
+            eng._check(eng.lib.pano_warp_overlay(eng.ctx, C.c_void_p(Ld[0].data_ptr()), w, h, C.c_size_t(Ld[0].stride(0)),
+                                                 C.c_void_p(Rd[0].data_ptr()), w, h, C.c_size_t(Rd[0].stride(0)), 1,
+                                                 Hm.ctypes.data_as(C.c_void_p), C.c_void_p(canvas.data_ptr()),
+                                                 C.c_size_t(canvas.stride(0)), C.c_size_t(canvas.numel()),
+                                                 C.byref(info)))
+        t_warp = time_kernel(eng, torch, k_warp)
+        kernels = {
+            "harris_response_kernel": {"ms": t_harris, "alg_bytes": 3 * npx, "launches_per_pair": 2,
+                                       "note": "FP64-pipe bound by construction (157 non-fusable FP64 ops/px); "
+                                               "algorithmic traffic is 3 B/px"},
+            "warp_overlay_kernel": {"ms": t_warp, "alg_bytes": 3 * (2 * npx + cw * ch), "launches_per_pair": 1,
+                                    "note": "HBM bound: both sources read once, canvas written once"},
+        }
+        share = {k: v["ms"] * v["launches_per_pair"] for k, v in kernels.items()}
+        dom = max(stage_ms, key=stage_ms.get)
+        # the roofline object describes the dominant HBM-type kernel of the step; the stage
+        # table next to it shows where the rest of the time goes (RANSAC replay is latency /
+        # issue bound, not bandwidth bound — see DESIGN.md)
+        top = max(share, key=share.get)
+        ach = kernels[top]["alg_bytes"] / (kernels[top]["ms"] / 1000.0) / 1e9
+        roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                    "traffic": None, "peak_source": how + " copy bandwidth (MEASURED_PEAKS.json)",
+                    "kernel_ms": kernels[top]["ms"], "note": kernels[top]["note"],
+                    "other_kernels": {k: {"ms": v["ms"], "achieved_GBs": v["alg_bytes"] / (v["ms"] / 1e3) / 1e9,
+                                          "frac": v["alg_bytes"] / (v["ms"] / 1e3) / 1e9 / hbm} for k, v in kernels.items()},
+                    "stage_ms_per_pair": stage_ms, "dominant_stage": dom}
+        # ---- CPU baseline: serial oracle on one core, bounded sample ---------------------------
+        cpu = None
+        if not a.no_cpu:
+            from oracle.oracle import Oracle
+            O = Oracle()
+            l, r = host[0]
+            t0 = time.perf_counter()
+            o = O.stitch_pair(l, r, seed=SEED)
+            dt = time.perf_counter() - t0
+            ok = (o["status"] == 1 and np.array_equal(o["H"].view(np.uint64), res[0]["H"].view(np.uint64)))
+            cpu = {"value": 2 * npx / 1e6 / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "1 pair of the same workload, serial oracle (-O2), %.2f s; "
+                             "H bit-identical to the engine's: %s" % (dt, ok),
+                   "stage_ms": o["times_ms"]}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_dev / a.steps, "ms_per_pair": ms_dev / (a.steps * P), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
+                "config": {"workload": "synthetic %dx%d textured pair, known homography (BASELINE config 3), "
+                                       "%d distinct pairs per GPU per step" % (w, h, P),
+                           "pairs_per_step_per_gpu": P, "seed": SEED, "l2_policy": "inputs %d MB per GPU > 126 MB L2, "
+                           "rotating every step" % (P * 2 * 3 * npx // 2**20), "keypoints": [r0["kl"], r0["kr"]],
+                           "matches": r0["m"], "inliers": r0["best"], "parallelism": "pairs sharded over %d GPU(s), "
+                           "no data-path collective" % world},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_pair": ms_e2e / (a.steps * P)},
+                "wall_ms_per_step": wall_ms / a.steps, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line, default=float), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--pairs", type=int, default=4, help="distinct 4K pairs per GPU per step")
+    ap.add_argument("--size", default="3840x2160")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    a.w, a.h = [int(v) for v in a.size.split("x")]
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_engine(a)
+
+
+if __name__ == "__main__":
+    main()

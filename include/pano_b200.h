@@ -181,6 +181,22 @@ int pano_stitch_fold(pano_ctx* ctx, const uint8_t* const* images, const int* ws,
                      const size_t* strides, int n, int mem, const pano_harris_opts* hopts,
                      const pano_ransac_opts* ropts, pano_pair_result* results);
 
+/* Throughput mode: n independent pairs (BASELINE config "batch of 4K pairs"), each exactly
+ * pano_stitch_pair.  lefts/rights/canvases_out are arrays of n pointers in `mem`; all pairs
+ * share the given image geometry.  canvases_out may be NULL (canvases are then produced and
+ * discarded on the device); otherwise canvas i is written tightly packed (stride 3*canvas_w)
+ * if it fits canvas_cap_bytes, else results[i].status = PANO_ERR_CAPACITY.
+ * *ms_batch = device time of the whole batch (CUDA events on the context's stream). */
+int pano_stitch_batch(pano_ctx* ctx, int n, const uint8_t* const* lefts, const uint8_t* const* rights,
+                      int wl, int hl, size_t stride_l, int wr, int hr, size_t stride_r, int mem,
+                      const pano_harris_opts* hopts, const pano_ransac_opts* ropts,
+                      pano_pair_result* results, uint8_t* const* canvases_out, size_t canvas_cap_bytes,
+                      float* ms_batch);
+
+/* The context's CUDA stream (a cudaStream_t), so callers can bracket calls with their own
+ * events or order their own work against the engine's. */
+void* pano_stream(pano_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,9 @@ void gaussian_kernel(int ksize, double sigma, std::vector<double>& k) {
 void convolve(const double* in, int w, int h, const double* kern, int ksize, double* out) {
   int k = ksize / 2;
   std::fill(out, out + (size_t)w * h, 0.0);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
   for (int y = k; y < h - k; y++) {
     for (int x = k; x < w - k; x++) {
       double sum = 0.0;
@@ -423,6 +426,9 @@ int ransac(const int32_t* kp1, const int32_t* kp2, const Match* matches, int m, 
       continue;
     }
     int inlierCount = 0;
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : inlierCount) schedule(static)
+#endif
     for (int i = 0; i < m; i++) {
       const Match& mm = matches[i];
       if (is_inlier(H, (float)kp1[2 * mm.queryIdx], (float)kp1[2 * mm.queryIdx + 1],
@@ -536,6 +542,9 @@ void warp_perspective(const uint8_t* src, int sw, int sh, size_t sstride, const 
   int bh0 = std::min(BLOCK_SZ / 2, dh);
   int bw0 = std::min(BLOCK_SZ * BLOCK_SZ / bh0, dw);
   bh0 = std::min(BLOCK_SZ * BLOCK_SZ / bw0, dh);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
   for (int y = 0; y < dh; y += bh0) {
     for (int x = 0; x < dw; x += bw0) {
       int bw = std::min(bw0, dw - x);

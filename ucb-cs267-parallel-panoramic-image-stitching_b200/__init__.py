@@ -40,7 +40,7 @@ EXPORTED_SYMBOLS = [
     "pano_last_error", "pano_version", "pano_kernel_launches", "pano_set_matcher", "pano_detect",
     "pano_harris_response", "pano_convolve_f64", "pano_match", "pano_ransac", "pano_canvas_geometry",
     "pano_warp_overlay", "pano_warp_perspective", "pano_stitch_pair", "pano_get_canvas", "pano_canvas_device",
-    "pano_stitch_fold",
+    "pano_stitch_fold", "pano_stitch_batch", "pano_stream",
 ]
 
 
@@ -325,6 +325,42 @@ class Engine:
                                               results))
         pano = self.getCanvas(device=(ims[0].mem == MEM_DEVICE)) if fetch else None
         return pano, [results[i].as_dict() for i in range(n - 1)]
+
+
+    def stitchBatch(self, lefts, rights, harrisOpts=None, ransacOpts=None, canvases_out=None):
+        """n independent pairs of one geometry (throughput mode).  lefts/rights: lists of host
+        arrays or CUDA tensors; canvases_out: optional list of preallocated flat uint8 buffers
+        (same memory kind) receiving the tightly packed canvases.  Returns ([result dicts],
+        device ms for the whole batch)."""
+        ho, ro = harrisOpts or HarrisCornerOptions(), ransacOpts or RansacOptions()
+        Ls, Rs = [_Img(i) for i in lefts], [_Img(i) for i in rights]
+        n = len(Ls)
+        assert n == len(Rs) and n > 0
+        L0, R0 = Ls[0], Rs[0]
+        assert all((i.w, i.h, i.stride, i.mem) == (L0.w, L0.h, L0.stride, L0.mem) for i in Ls)
+        assert all((i.w, i.h, i.stride, i.mem) == (R0.w, R0.h, R0.stride, L0.mem) for i in Rs)
+        lp = (C.c_void_p * n)(*[i.ptr for i in Ls])
+        rp = (C.c_void_p * n)(*[i.ptr for i in Rs])
+        results = (PairResult * n)()
+        cp, cap = None, 0
+        if canvases_out is not None:
+            assert len(canvases_out) == n
+            ptrs = []
+            for b in canvases_out:
+                if _is_torch_cuda(b) or hasattr(b, "data_ptr"):
+                    ptrs.append(C.c_void_p(b.data_ptr())); cap = int(b.numel())
+                else:
+                    ptrs.append(C.c_void_p(b.ctypes.data)); cap = int(b.nbytes)
+            cp = (C.c_void_p * n)(*ptrs)
+        ms = C.c_float(0)
+        self._check(self.lib.pano_stitch_batch(self.ctx, n, lp, rp, L0.w, L0.h, C.c_size_t(L0.stride), R0.w, R0.h,
+                                               C.c_size_t(R0.stride), L0.mem, C.byref(ho), C.byref(ro), results,
+                                               cp, C.c_size_t(cap), C.byref(ms)))
+        return [results[i].as_dict() for i in range(n)], ms.value
+
+    def stream_ptr(self):
+        self.lib.pano_stream.restype = C.c_void_p
+        return self.lib.pano_stream(self.ctx)
 
 
 # reference-style free functions bound to a default engine ------------------------------

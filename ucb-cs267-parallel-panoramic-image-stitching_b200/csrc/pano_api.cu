@@ -534,4 +534,50 @@ int pano_stitch_fold(pano_ctx* c, const uint8_t* const* images, const int* ws, c
   API_CATCH(c)
 }
 
+void* pano_stream(pano_ctx* c) { return c ? (void*)c->st : nullptr; }
+
+int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uint8_t* const* rights, int wl, int hl,
+                      size_t stride_l, int wr, int hr, size_t stride_r, int mem, const pano_harris_opts* hopts,
+                      const pano_ransac_opts* ropts, pano_pair_result* results, uint8_t* const* canvases_out,
+                      size_t canvas_cap_bytes, float* ms_batch) {
+  API_TRY(c)
+  if (n < 0 || !lefts || !rights || !hopts || !ropts || !results)
+    return fail(c, PANO_ERR_INVALID, "pano_stitch_batch: bad argument");
+  for (int i = 0; i < n; i++)
+    if (!valid_image(lefts[i], wl, hl, stride_l) || !valid_image(rights[i], wr, hr, stride_r))
+      return fail(c, PANO_ERR_INVALID, "pano_stitch_batch: bad image");
+  if (int e = check_harris(*hopts)) return fail(c, e, "pano_stitch_batch: unsupported option");
+  if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
+  cudaEvent_t e0, e1;
+  PANO_CUDA(cudaEventCreate(&e0));
+  PANO_CUDA(cudaEventCreate(&e1));
+  PANO_CUDA(cudaEventRecord(e0, c->st));
+  int rc = PANO_OK;
+  for (int i = 0; i < n; i++) {
+    DevImage L = to_device(c, lefts[i], wl, hl, stride_l, mem, 0);
+    DevImage R = to_device(c, rights[i], wr, hr, stride_r, mem, 1);
+    int s = stitch_pair_device(c, L, R, *hopts, *ropts, &results[i]);
+    if (s == PANO_ERR_CUDA) { rc = s; break; }
+    if (s == PANO_OK && canvases_out && canvases_out[i]) {
+      size_t row = (size_t)c->cw * 3;
+      if (row * (size_t)c->ch > canvas_cap_bytes) {
+        results[i].status = PANO_ERR_CAPACITY;
+      } else {
+        PANO_CUDA(cudaMemcpy2DAsync(canvases_out[i], row, c->canvas[c->cur].p, c->cstride, row, c->ch,
+                                    mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                    c->st));
+      }
+    }
+  }
+  PANO_CUDA(cudaEventRecord(e1, c->st));
+  PANO_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_batch) *ms_batch = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+  API_CATCH(c)
+}
+
 }  // extern "C"

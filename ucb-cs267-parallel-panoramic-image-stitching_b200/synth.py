@@ -9,15 +9,23 @@ through a known homography (shift + small rotation + small perspective) plus +-2
 import numpy as np
 
 
+def _interp_matrix(n_out, n_in):
+    pos = np.linspace(0, n_in - 1.001, n_out)
+    i0 = pos.astype(np.int64)
+    f = (pos - i0).astype(np.float32)
+    W = np.zeros((n_out, n_in), np.float32)
+    W[np.arange(n_out), i0] = 1 - f
+    W[np.arange(n_out), i0 + 1] += f
+    return W
+
+
 def _upsample_bilinear(g, h, w):
-    gh, gw = g.shape[:2]
-    ys = np.linspace(0, gh - 1.001, h).astype(np.float32)
-    xs = np.linspace(0, gw - 1.001, w).astype(np.float32)
-    y0 = ys.astype(np.int32); fy = (ys - y0)[:, None, None]
-    x0 = xs.astype(np.int32); fx = (xs - x0)[None, :, None]
-    r0 = g[y0]; r1 = g[y0 + 1]
-    rows = r0 * (1 - fy) + r1 * fy            # (h, gw, 3)
-    return rows[:, x0] * (1 - fx) + rows[:, x0 + 1] * fx
+    """separable bilinear upsampling of a small (gh, gw, 3) grid as two dense mat-muls"""
+    Wy, Wx = _interp_matrix(h, g.shape[0]), _interp_matrix(w, g.shape[1])
+    out = np.empty((h, w, 3), np.float32)
+    for c in range(3):
+        out[:, :, c] = (Wy @ g[:, :, c]) @ Wx.T
+    return out
 
 
 def make_world(h, w, seed, n_rect=None, rect_px=(10, 70)):
@@ -37,14 +45,21 @@ def make_world(h, w, seed, n_rect=None, rect_px=(10, 70)):
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def _sample_bilinear(world, X, Y):
+def _sample_bilinear(world, X, Y, chunk=128):
+    """bilinear lookup world(X, Y) for coordinate planes X, Y (row chunks keep it cache-sized)"""
     H, W = world.shape[:2]
-    X = np.clip(X, 0, W - 1.001); Y = np.clip(Y, 0, H - 1.001)
-    x0 = X.astype(np.int32); y0 = Y.astype(np.int32)
-    fx = (X - x0)[..., None].astype(np.float32); fy = (Y - y0)[..., None].astype(np.float32)
-    w00 = world[y0, x0].astype(np.float32); w01 = world[y0, x0 + 1].astype(np.float32)
-    w10 = world[y0 + 1, x0].astype(np.float32); w11 = world[y0 + 1, x0 + 1].astype(np.float32)
-    return (w00 * (1 - fx) + w01 * fx) * (1 - fy) + (w10 * (1 - fx) + w11 * fx) * fy
+    flat = world.reshape(-1, 3)
+    out = np.empty(X.shape + (3,), np.float32)
+    for r in range(0, X.shape[0], chunk):
+        x = np.clip(X[r:r + chunk], 0, W - 1.001).astype(np.float32)
+        y = np.clip(Y[r:r + chunk], 0, H - 1.001).astype(np.float32)
+        x0 = x.astype(np.int32); y0 = y.astype(np.int32)
+        fx = (x - x0)[..., None]; fy = (y - y0)[..., None]
+        i = y0 * W + x0
+        top = flat[i] * (1 - fx) + flat[i + 1] * fx
+        bot = flat[i + W] * (1 - fx) + flat[i + W + 1] * fx
+        out[r:r + chunk] = top * (1 - fy) + bot * fy
+    return out
 
 
 def make_pair(w=3840, h=2160, seed=267, overlap=0.5, rot_deg=0.3, persp=1e-6, noise=2, n_rect=None):
