@@ -53,8 +53,9 @@ void hs_warp_perspective(const uint8_t* src, int w, int h, size_t stride, const 
     }
 }
 
-// emulates replay_walk_kernel + replay_chain_kernel chunk by chunk.
-// returns 0 ok, 1 window miss, 2 stream too short.  stats: G, n_cand, max_w, chunks
+// emulates replay_offsets_kernel + replay_chain_kernel chunk by chunk, then replay_samples_kernel.
+// returns 0 ok, bit 0 window miss, bit 1 stream too short, bit 2 pass-1/pass-2 disagreement.
+// stats: G, n_cand, max_w, chunks, mu, sigma
 int hs_replay(uint32_t seed, uint32_t n, int iters, int window_scale, int32_t* samples, uint64_t* end_offset,
               double* stats) {
   ReplayPlan P = plan_replay(n, iters, window_scale);
@@ -67,34 +68,51 @@ int hs_replay(uint32_t seed, uint32_t n, int iters, int window_scale, int32_t* s
     for (uint64_t i = 0; i < P.stream_need; i++) X[i] = e();
   }
   if (stats) { stats[0] = P.G; stats[1] = P.n_cand; stats[2] = P.max_w; stats[3] = (iters + P.G - 1) / P.G; stats[4] = P.mu; stats[5] = P.sigma; }
+  const int nseg = (int)((steps + PANO_SEG_STEPS - 1) / PANO_SEG_STEPS);
   std::vector<uint32_t> cand_end(P.n_cand);
-  std::vector<int> cand_samp((size_t)P.n_cand * 4);
+  std::vector<uint32_t> seg_off((size_t)P.n_cand * (size_t)std::max(nseg - 1, 1));
+  std::vector<uint64_t> seg_tab((size_t)iters * nseg);
   uint64_t base = 0;
   for (int c0 = 0; c0 < iters; c0 += P.G) {
     int Gc = std::min(P.G, iters - c0);
-    for (int g = 0; g < Gc; g++) {
+    for (int g = 0; g < Gc; g++) {          // replay_offsets_kernel
       const WinEntry& we = P.win[g];
       for (uint32_t j = 0; j < we.width; j++) {
         uint64_t start = base + (uint64_t)g * steps + we.lo + j;
         if (start + 2ull * steps + 64ull >= P.stream_need) return 2;
-        int a[4];
-        uint32_t rel0 = (uint32_t)(start - base);
-        uint32_t end = pairs ? walk_shuffle<true>(X.data() + base, rel0, n, steps, P.thr.data(), a)
-                             : walk_shuffle<false>(X.data() + base, rel0, n, steps, P.thr.data(), a);
-        cand_end[we.first + j] = end;
-        memcpy(&cand_samp[(size_t)(we.first + j) * 4], a, sizeof a);
+        cand_end[we.first + j] = walk_offsets(X.data() + base, (uint32_t)(start - base), steps, P.rt.data(),
+                                              seg_off.data() + we.first + j, (size_t)P.n_cand);
       }
     }
-    uint32_t rel = 0;
+    uint32_t rel = 0;                        // replay_chain_kernel
     for (int g = 0; g < Gc; g++) {
       const WinEntry& we = P.win[g];
       long long j = (long long)rel - ((long long)g * steps + we.lo);
       if (j < 0 || j >= (long long)we.width) return 1;
       uint32_t pick = we.first + (uint32_t)j;
-      memcpy(&samples[(size_t)(c0 + g) * 4], &cand_samp[(size_t)pick * 4], 4 * sizeof(int));
+      seg_tab[((size_t)c0 + g) * nseg] = base + rel;
+      for (int sg = 1; sg < nseg; sg++) seg_tab[((size_t)c0 + g) * nseg + sg] = base + seg_off[(size_t)(sg - 1) * P.n_cand + pick];
       rel = cand_end[pick];
     }
     base += rel;
+  }
+  std::vector<int> seg_w((size_t)iters * nseg * 4);
+  for (int i = 0; i < iters * nseg; i++) {   // replay_segments_kernel
+    int sg = i % nseg;
+    uint32_t k0 = (uint32_t)sg * PANO_SEG_STEPS, k1 = std::min(steps, k0 + PANO_SEG_STEPS);
+    int w[4];
+    uint32_t end = pairs ? walk_track_segment<true>(X.data() + seg_tab[i], 0u, n, k0, k1, P.rt.data(), w)
+                         : walk_track_segment<false>(X.data() + seg_tab[i], 0u, n, k0, k1, P.rt.data(), w);
+    memcpy(&seg_w[(size_t)i * 4], w, sizeof w);
+    uint64_t next = i + 1 < iters * nseg ? seg_tab[i + 1] : base;
+    if (seg_tab[i] + end != next) return 4;
+  }
+  for (int t = 0; t < iters; t++) {          // combine_samples_kernel
+    int a[4] = {-1, -1, -1, -1};
+    for (int sg = nseg - 1; sg >= 0; sg--)
+      for (int p = 0; p < 4; p++)
+        if (a[p] < 0) a[p] = seg_w[((size_t)t * nseg + sg) * 4 + p];
+    memcpy(&samples[(size_t)t * 4], a, sizeof a);
   }
   if (end_offset) *end_offset = base;
   return 0;

@@ -393,9 +393,70 @@ PANO_HD uint32_t shuffle_steps(uint32_t n) {
 // 2^32 mod r for 1 <= r < 2^32
 PANO_HD uint32_t lemire_threshold(uint32_t r) { return (uint32_t)(0u - r) % r; }
 
-// One full shuffle of n elements starting at stream offset o (relative to X).  Returns the
-// end offset; a[0..3] receive the elements that end up in positions 0..3 (the identity start
-// means an element index IS a match index).  thr[k] = lemire_threshold(range of step k).
+// ----------------------------------------------------------------------------------------
+// Walks of one shuffle through the engine's output stream X (offsets relative to X).
+// rt[k] = (range r_k, Lemire threshold T_k) of step k: a draw x is rejected iff
+// lo32(x * r_k) < T_k (for paired steps r_k = b0*b1 < 2^32, and lo32(lo32(x*b0)*b1) is the same
+// low word).  Step 0 of an even-sized paired shuffle is the d{0,1} draw: (2, 0), never rejects.
+//
+// Both walks process 8 steps at a time under the assumption that none of them rejects (and,
+// for the tracking walk, that none touches positions 0..3); the 8 loads and tests are
+// independent, which is what hides the memory latency.  On a flagged step they fall back to
+// the exact one-step path from the first flagged step on.
+// ----------------------------------------------------------------------------------------
+struct alignas(8) RT {
+  uint32_t r, T;
+};
+
+PANO_HD int first_bit8(uint32_t m) {
+  int i = 0;
+  while (!((m >> i) & 1u)) i++;
+  return i;
+}
+
+// Steps per pass-2 segment.  Pass 1 records each candidate's offset at every segment
+// boundary so that pass 2 can walk all segments of all iterations in parallel.
+#define PANO_SEG_STEPS 512u
+
+// pass 1: end offset (and, if seg_off != nullptr, the offset at the start of segments 1, 2, ...
+// written to seg_off[(s - 1) * seg_stride])
+PANO_HD uint32_t walk_offsets(const uint32_t* X, uint32_t o, uint32_t steps, const RT* rt, uint32_t* seg_off,
+                              size_t seg_stride) {
+  const uint32_t* px = X + o;  // advancing pointers: loads use immediate offsets
+  uint32_t k0 = 0;
+  while (k0 < steps) {
+    const uint32_t k1 = (steps - k0 > PANO_SEG_STEPS) ? k0 + PANO_SEG_STEPS : steps;
+    const RT* pr = rt + k0;
+    const RT* const pr_end = rt + k1;
+    const RT* const pr_end8 = (k1 - k0 >= 8) ? pr_end - 7 : pr;  // pr < pr_end8: 8 steps remain
+    while (pr < pr_end8) {
+      uint32_t rej = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int i = 0; i < 8; i++) {
+        const RT q = pr[i];
+        rej |= (px[i] * q.r < q.T) ? (1u << i) : 0u;
+      }
+      if (rej == 0) { px += 8; pr += 8; continue; }
+      const int i0 = first_bit8(rej);
+      px += i0; pr += i0;
+      const RT q = *pr;
+      uint32_t x0 = *px++;
+      while (x0 * q.r < q.T) x0 = *px++;
+      pr++;
+    }
+    for (; pr < pr_end; pr++) {
+      const RT q = *pr;
+      uint32_t x0 = *px++;
+      while (x0 * q.r < q.T) x0 = *px++;
+    }
+    k0 = k1;
+    if (seg_off && k0 < steps) seg_off[(size_t)(k0 / PANO_SEG_STEPS - 1) * seg_stride] = (uint32_t)(px - X);
+  }
+  return (uint32_t)(px - X);
+}
+
 PANO_HD void track_swap(int (&a)[4], uint32_t idx, uint32_t p) {
   if (p < 4u) {
     if (idx < 4u) {
@@ -408,64 +469,78 @@ PANO_HD void track_swap(int (&a)[4], uint32_t idx, uint32_t p) {
   }
 }
 
+// exact single step of the tracking walk (consumes draws until one is accepted)
 template <bool PAIRS>
-PANO_HD uint32_t walk_shuffle(const uint32_t* X, uint32_t o, uint32_t n,
-                                                 uint32_t steps, const uint32_t* thr,
-                                                 int (&a)[4]) {
-  a[0] = 0; a[1] = 1; a[2] = 2; a[3] = 3;
-  uint32_t k = 0;
+PANO_HD void track_step(const uint32_t* X, uint32_t& o, uint32_t k, uint32_t n, const RT* rt, int (&a)[4]) {
+  const uint32_t r = rt[k].r, T = rt[k].T;
+  uint32_t x = X[o++];
+  while (x * r < T) x = X[o++];
   if (PAIRS) {
     const uint32_t odd = n & 1u;
-    if (!odd) {  // even n: element 1 swaps with position d{0,1}(g) = x >> 31 (never rejects)
-      uint32_t x = X[o++];
+    if (!odd && k == 0) {  // d{0,1}: element 1 swaps with position x >> 31
       track_swap(a, 1u, x >> 31);
-      k = 1;
+      return;
     }
-    uint32_t xn = X[o];
-    for (; k < steps; k++) {
-      const uint32_t idx = 2u * k + odd;
-      const uint32_t b0 = idx + 1u, b1 = idx + 2u;
-      const uint32_t T = thr[k];
-      uint32_t x = xn;
-      o++;
-      xn = X[o];
-      unsigned long long u = (unsigned long long)x * b0;
-      unsigned long long v = (unsigned long long)(uint32_t)u * b1;
-      while ((uint32_t)v < T) {  // Lemire rejection: draw again (same step)
-        x = xn;
-        o++;
-        xn = X[o];
-        u = (unsigned long long)x * b0;
-        v = (unsigned long long)(uint32_t)u * b1;
-      }
-      const uint32_t p1 = (uint32_t)(u >> 32), p2 = (uint32_t)(v >> 32);
-      if ((p1 < p2 ? p1 : p2) < 4u) {
-        track_swap(a, idx, p1);
-        track_swap(a, idx + 1u, p2);
-      }
-    }
+    const uint32_t idx = 2u * k + odd, b0 = idx + 1u, b1 = idx + 2u;
+    const unsigned long long u = (unsigned long long)x * b0;
+    const unsigned long long v = (unsigned long long)(uint32_t)u * b1;
+    track_swap(a, idx, (uint32_t)(u >> 32));
+    track_swap(a, idx + 1u, (uint32_t)(v >> 32));
   } else {
-    uint32_t xn = X[o];
-    for (; k < steps; k++) {
-      const uint32_t idx = k + 1u;
-      const uint32_t r = idx + 1u;
-      const uint32_t T = thr[k];
-      uint32_t x = xn;
-      o++;
-      xn = X[o];
-      unsigned long long u = (unsigned long long)x * r;
-      while ((uint32_t)u < T) {
-        x = xn;
-        o++;
-        xn = X[o];
-        u = (unsigned long long)x * r;
-      }
-      const uint32_t p = (uint32_t)(u >> 32);
-      if (p < 4u) track_swap(a, idx, p);
-    }
+    const uint32_t idx = k + 1u;
+    track_swap(a, idx, (uint32_t)(((unsigned long long)x * r) >> 32));
   }
-  return o;
 }
 
+// pass 2, one segment [k0, k1) of one iteration starting at offset o: returns the end offset.
+// w[p] receives the element that the segment leaves in position p (p = 0..3), or -1 if the
+// segment never writes p.  Segment 0 (k0 == 0) also carries the initial identity and the swaps
+// among the first four elements, so its w[] is always complete.  Later segments only ever
+// assign "position p <- element idx" (idx >= 4), so segments compose by last-writer-wins.
+template <bool PAIRS>
+PANO_HD uint32_t walk_track_segment(const uint32_t* X, uint32_t o, uint32_t n, uint32_t k0, uint32_t k1,
+                                    const RT* rt, int (&w)[4]) {
+  int a[4];
+  uint32_t k = k0;
+  const uint32_t odd = n & 1u;
+  if (k0 == 0) {
+    a[0] = 0; a[1] = 1; a[2] = 2; a[3] = 3;
+    // exact steps until every swap partner index is >= 4 (idx < 4 swaps exchange tracked slots)
+    while (k < k1 && (PAIRS ? 2u * k + odd : k + 1u) < 4u) { track_step<PAIRS>(X, o, k, n, rt, a); k++; }
+  } else {
+    a[0] = a[1] = a[2] = a[3] = -1;
+  }
+  while (k + 8 <= k1) {
+    const uint32_t* px = X + o;
+    const RT* pr = rt + k;
+    uint32_t flag = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 8; i++) {
+      const uint32_t x = px[i];
+      const RT q = pr[i];
+      bool f = x * q.r < q.T;
+      if (PAIRS) {
+        const uint32_t idx = 2u * (k + i) + odd, b0 = idx + 1u, b1 = idx + 2u;
+        const unsigned long long u = (unsigned long long)x * b0;
+        const unsigned long long v = (unsigned long long)(uint32_t)u * b1;
+        const uint32_t p1 = (uint32_t)(u >> 32), p2 = (uint32_t)(v >> 32);
+        f = f || ((p1 < p2 ? p1 : p2) < 4u);
+      } else {
+        f = f || ((uint32_t)(((unsigned long long)x * q.r) >> 32) < 4u);
+      }
+      flag |= f ? (1u << i) : 0u;
+    }
+    if (flag == 0) { o += 8; k += 8; continue; }
+    int i0 = first_bit8(flag);
+    o += i0; k += i0;
+    track_step<PAIRS>(X, o, k, n, rt, a);
+    k++;
+  }
+  for (; k < k1; k++) track_step<PAIRS>(X, o, k, n, rt, a);
+  w[0] = a[0]; w[1] = a[1]; w[2] = a[2]; w[3] = a[3];
+  return o;
+}
 
 }  // namespace pano

@@ -106,71 +106,130 @@ __global__ void __launch_bounds__(256) mt_generate_kernel(uint32_t* __restrict__
 // K5 walk: one full shuffle of n elements starting at stream offset o.  Returns the end
 // offset and the elements that end up in positions 0..3.
 // ---------------------------------------------------------------------------------------
-template <bool PAIRS>
-__global__ void __launch_bounds__(64)
-replay_walk_kernel(const uint32_t* __restrict__ X, uint32_t n, uint32_t steps, const uint32_t* __restrict__ thr,
-                   const WinEntry* __restrict__ win, const unsigned long long* __restrict__ base_ptr,
-                   uint32_t* __restrict__ cand_end, int4* __restrict__ cand_samp, unsigned long long stream_len,
-                   int* __restrict__ status) {
+// Pass 1 for one chunk of G iterations: thread (g, j) walks iteration g from candidate start
+// offset j of its window and records where the walk ends.  The last block to finish then
+// chains the chunk from its exact base offset: iteration g's true candidate is the one that
+// starts where iteration g-1's true candidate ended.  Exact: a true start outside its window
+// is detected (status bit 0), never guessed.
+struct ReplayCtl {
+  unsigned long long base;  // exact stream offset of the chunk's first iteration
+  int status;               // bit 0: window miss, bit 1: stream too short
+  unsigned int done;        // blocks finished (last-block-done hand-over)
+};
+
+constexpr int RW_THREADS = 128;
+constexpr size_t CHAIN_SMEM_MAX = 200 * 1024;  // + 20 KB static: under the 227 KB per-block limit
+
+__global__ void __launch_bounds__(RW_THREADS)
+replay_offsets_kernel(const uint32_t* __restrict__ X, uint32_t steps, const RT* __restrict__ rt,
+                      const WinEntry* __restrict__ win, ReplayCtl* ctl, uint32_t* __restrict__ cand_end,
+                      uint32_t* __restrict__ seg_off, int n_cand, unsigned long long stream_len) {
   const int g = blockIdx.y;
   const WinEntry we = win[g];
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= we.width) return;
-  const unsigned long long base = *base_ptr;
+  const unsigned long long base = ctl->base;
   const unsigned long long start = base + (unsigned long long)g * steps + we.lo + j;
-  // a walk never consumes more than `steps` + (drift within one shuffle); the host sized the
-  // stream with a large margin — refuse rather than read past the end
-  if (start + 2ull * steps + 64ull >= stream_len) {
-    atomicOr(status, 2);
-    cand_end[we.first + j] = 0xffffffffu;
-    return;
+  uint32_t end = 0xffffffffu;
+  if (start + 2ull * steps + 64ull < stream_len) {
+    // offsets relative to the chunk base fit 32 bits (chunk span << 2^32)
+    end = walk_offsets(X + base, (uint32_t)(start - base), steps, rt, seg_off + we.first + j, (size_t)n_cand);
+  } else {
+    atomicOr(&ctl->status, 2);
   }
-  int a[4];
-  // offsets relative to the chunk base fit 32 bits by construction (chunk span << 2^32)
-  const uint32_t rel0 = (uint32_t)(start - base);
-  uint32_t end = walk_shuffle<PAIRS>(X + base, rel0, n, steps, thr, a);
-  cand_end[we.first + j] = end;  // relative to chunk base
-  cand_samp[we.first + j] = make_int4(a[0], a[1], a[2], a[3]);
+  cand_end[we.first + j] = end;
 }
 
-// chain the chunk: from the exact base offset, follow each iteration's true candidate
+// One block: stage the chunk's candidate end offsets and windows in shared memory, chain
+// sequentially (G dependent shared-memory lookups), then copy the true candidates' segment
+// offsets into the per-iteration table used by pass 2.
+// seg_tab[(t * nseg + s)] = absolute stream offset at which segment s of iteration t starts.
 __global__ void __launch_bounds__(1024)
 replay_chain_kernel(const WinEntry* __restrict__ win, int G, uint32_t steps, const uint32_t* __restrict__ cand_end,
-                    const int4* __restrict__ cand_samp, int n_cand, unsigned long long* __restrict__ base_ptr,
-                    int4* __restrict__ samples /* for this chunk */, int* __restrict__ status) {
+                    const uint32_t* __restrict__ seg_off, int n_cand, int nseg, ReplayCtl* ctl,
+                    unsigned long long* __restrict__ seg_tab /* this chunk's slice */) {
   extern __shared__ uint32_t s_end[];
-  const bool in_smem = n_cand * sizeof(uint32_t) <= 200 * 1024;
-  if (in_smem) {
-    for (int i = threadIdx.x; i < n_cand; i += blockDim.x) s_end[i] = cand_end[i];
-  }
+  __shared__ WinEntry s_win[1024];
   __shared__ int s_pick[1024];
+  __shared__ unsigned long long s_base;
+  const bool in_smem = (size_t)n_cand * sizeof(uint32_t) <= CHAIN_SMEM_MAX;
+  if (in_smem)
+    for (int i = threadIdx.x; i < n_cand; i += blockDim.x) s_end[i] = cand_end[i];
+  for (int i = threadIdx.x; i < G; i += blockDim.x) s_win[i] = win[i];
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t rel = 0;  // offset relative to chunk base
-    bool bad = (*status != 0);
+    const unsigned long long base = ctl->base;
+    s_base = base;
+    uint32_t rel = 0;
+    bool bad = ctl->status != 0;
     for (int g = 0; g < G; g++) {
-      int pick = -1;
-      if (!bad) {
-        const WinEntry we = win[g];
-        long long j = (long long)rel - ((long long)g * steps + we.lo);
-        if (j < 0 || j >= (long long)we.width) {
-          bad = true;
-          atomicOr(status, 1);
-        } else {
-          pick = (int)(we.first + (uint32_t)j);
-          uint32_t e = in_smem ? s_end[pick] : cand_end[pick];
-          if (e == 0xffffffffu) { bad = true; pick = -1; } else rel = e;
-        }
+      s_pick[g] = -1;
+      if (bad) continue;
+      const WinEntry we = s_win[g];
+      long long j = (long long)rel - ((long long)g * steps + we.lo);
+      if (j < 0 || j >= (long long)we.width) {
+        bad = true;
+        atomicOr(&ctl->status, 1);
+        continue;
       }
-      if (g < 1024) s_pick[g] = pick; else if (pick >= 0) samples[g] = cand_samp[pick];
+      const uint32_t pick = we.first + (uint32_t)j;
+      const uint32_t e = in_smem ? s_end[pick] : cand_end[pick];
+      if (e == 0xffffffffu) { bad = true; continue; }
+      s_pick[g] = (int)pick;
+      seg_tab[(size_t)g * nseg] = base + rel;
+      rel = e;
     }
-    if (!bad) *base_ptr += rel;
+    if (!bad) ctl->base = base + rel;
   }
   __syncthreads();
-  for (int g = threadIdx.x; g < G && g < 1024; g += blockDim.x) {
-    int pick = s_pick[g];
-    samples[g] = pick >= 0 ? cand_samp[pick] : make_int4(-1, -1, -1, -1);
+  const unsigned long long base = s_base;
+  for (int i = threadIdx.x; i < G * nseg; i += blockDim.x) {
+    const int g = i / nseg, sgm = i - g * nseg;
+    const int pick = s_pick[g];
+    if (pick < 0) seg_tab[(size_t)g * nseg + sgm] = ~0ull;
+    else if (sgm > 0) seg_tab[(size_t)g * nseg + sgm] = base + seg_off[(size_t)(sgm - 1) * n_cand + pick];
   }
+}
+
+// Pass 2: every segment of every iteration has a known start offset; walk them all in
+// parallel, each recording what it leaves in positions 0..3, and check that each segment ends
+// where the next one starts.
+template <bool PAIRS>
+__global__ void __launch_bounds__(64)
+replay_segments_kernel(const uint32_t* __restrict__ X, uint32_t n, uint32_t steps, const RT* __restrict__ rt,
+                       const unsigned long long* __restrict__ seg_tab, int iters, int nseg, ReplayCtl* ctl,
+                       int4* __restrict__ seg_w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= iters * nseg) return;
+  const int t = i / nseg, sgm = i - t * nseg;
+  const unsigned long long start = seg_tab[i];
+  if (start == ~0ull) {
+    seg_w[i] = make_int4(-2, -2, -2, -2);
+    return;
+  }
+  const uint32_t k0 = (uint32_t)sgm * PANO_SEG_STEPS;
+  const uint32_t k1 = min(steps, k0 + PANO_SEG_STEPS);
+  int w[4];
+  const uint32_t end = walk_track_segment<PAIRS>(X + start, 0u, n, k0, k1, rt, w);
+  seg_w[i] = make_int4(w[0], w[1], w[2], w[3]);
+  const unsigned long long next = (i + 1 < iters * nseg) ? seg_tab[i + 1] : ctl->base;
+  if (next != ~0ull && start + end != next) atomicOr(&ctl->status, 4);  // passes disagree: never expected
+}
+
+// last writer wins across an iteration's segments
+__global__ void combine_samples_kernel(const int4* __restrict__ seg_w, int iters, int nseg, int4* __restrict__ samples) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= iters) return;
+  int a[4] = {-1, -1, -1, -1};
+  for (int sgm = nseg - 1; sgm >= 0; sgm--) {
+    const int4 w = seg_w[(size_t)t * nseg + sgm];
+    if (w.x == -2) { a[0] = a[1] = a[2] = a[3] = -1; break; }
+    if (a[0] < 0) a[0] = w.x;
+    if (a[1] < 0) a[1] = w.y;
+    if (a[2] < 0) a[2] = w.z;
+    if (a[3] < 0) a[3] = w.w;
+  }
+  samples[t] = make_int4(a[0], a[1], a[2], a[3]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -185,28 +244,234 @@ __global__ void build_points_kernel(const int32_t* __restrict__ kp1, const int32
                        (float)kp2[2 * mm.train_idx], (float)kp2[2 * mm.train_idx + 1]);
 }
 
-__global__ void __launch_bounds__(32)
+// K6: one warp per hypothesis.  Same arithmetic, in the same order, as pano_core.cuh
+// find_homography4 / jacobi9 (= OpenCV's runKernel + JacobiImpl_), with the independent
+// element updates of each Jacobi rotation spread over lanes 0..8:
+//   S   full symmetric copy of OpenCV's upper-triangular working matrix A (S[a][b] == A[min][max])
+//   rotation (k,l): for every i not in {k,l} OpenCV rotates the pair (A[.][k-side], A[.][l-side]),
+//       which in S is always (S[i][k], S[i][l]) -> lane i; eigenvector columns -> lane i.
+//   pivot: OpenCV's scan over |A[i][indR[i]]| (i = 0..7) then |A[indC[i]][i]| (i = 1..8) with a
+//       strict '<' keeps the FIRST maximum -> warp arg-max over 16 candidates, ties to the lowest
+//       scan position.  indR / indC are maintained exactly as OpenCV does (only rows k and l are
+//       refreshed after a rotation, so stale entries behave identically).
+constexpr int DLT_WARPS = 4;
+
+struct DltSmem {
+  double S[81];
+  double V[81];
+  double W[9];
+  int indR[9], indC[9];
+};
+
+__device__ __forceinline__ void warp_argmax_first(double& v, int& pos, int& k, int& l) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+    int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
+    int k2 = __shfl_xor_sync(0xffffffffu, k, o);
+    int l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    if (v2 > v || (v2 == v && p2 < pos)) { v = v2; pos = p2; k = k2; l = l2; }
+  }
+}
+
+__global__ void __launch_bounds__(DLT_WARPS * 32)
 dlt_kernel(const float4* __restrict__ pts, const int4* __restrict__ samples, int iters, double* __restrict__ Hs,
            int* __restrict__ valid) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ DltSmem sm_all[DLT_WARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int t = blockIdx.x * DLT_WARPS + wid;
   if (t >= iters) return;
-  int4 s = samples[t];
-  int idx[4] = {s.x, s.y, s.z, s.w};
-  if (s.x < 0 || s.y < 0 || s.z < 0 || s.w < 0) {  // replay did not resolve this iteration
-    valid[t] = 0;
-    for (int i = 0; i < 9; i++) Hs[(size_t)t * 9 + i] = 0.0;
+  DltSmem& sm = sm_all[wid];
+  const int4 smp = samples[t];
+  if (smp.x < 0 || smp.y < 0 || smp.z < 0 || smp.w < 0) {  // replay did not resolve this iteration
+    if (lane == 0) valid[t] = 0;
+    if (lane < 9) Hs[(size_t)t * 9 + lane] = 0.0;
     return;
   }
-  float src[8], dst[8];
+  const int idx[4] = {smp.x, smp.y, smp.z, smp.w};
+  float M[8], m[8];  // M = src (query side), m = dst
+#pragma unroll
   for (int j = 0; j < 4; j++) {
     float4 p = pts[idx[j]];
-    src[2 * j] = p.x; src[2 * j + 1] = p.y;
-    dst[2 * j] = p.z; dst[2 * j + 1] = p.w;
+    M[2 * j] = p.x; M[2 * j + 1] = p.y;
+    m[2 * j] = p.z; m[2 * j + 1] = p.w;
   }
-  double LtL[81], V[81], H[9];
-  int ok = find_homography4(src, dst, H, LtL, V);
-  valid[t] = ok;
-  for (int i = 0; i < 9; i++) Hs[(size_t)t * 9 + i] = ok ? H[i] : 0.0;
+  // ---- normalisation (every lane computes the same scalars) -----------------------------
+  const int count = 4;
+  double cMx = 0, cMy = 0, cmx = 0, cmy = 0, sMx = 0, sMy = 0, smx = 0, smy = 0;
+#pragma unroll
+  for (int i = 0; i < count; i++) {
+    cmx = __dadd_rn(cmx, (double)m[2 * i]);
+    cmy = __dadd_rn(cmy, (double)m[2 * i + 1]);
+    cMx = __dadd_rn(cMx, (double)M[2 * i]);
+    cMy = __dadd_rn(cMy, (double)M[2 * i + 1]);
+  }
+  cmx = __ddiv_rn(cmx, 4.0); cmy = __ddiv_rn(cmy, 4.0);
+  cMx = __ddiv_rn(cMx, 4.0); cMy = __ddiv_rn(cMy, 4.0);
+#pragma unroll
+  for (int i = 0; i < count; i++) {
+    smx = __dadd_rn(smx, fabs(__dsub_rn((double)m[2 * i], cmx)));
+    smy = __dadd_rn(smy, fabs(__dsub_rn((double)m[2 * i + 1], cmy)));
+    sMx = __dadd_rn(sMx, fabs(__dsub_rn((double)M[2 * i], cMx)));
+    sMy = __dadd_rn(sMy, fabs(__dsub_rn((double)M[2 * i + 1], cMy)));
+  }
+  if (fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON || fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON) {
+    if (lane == 0) valid[t] = 0;
+    if (lane < 9) Hs[(size_t)t * 9 + lane] = 0.0;
+    return;
+  }
+  smx = __ddiv_rn(4.0, smx); smy = __ddiv_rn(4.0, smy);
+  sMx = __ddiv_rn(4.0, sMx); sMy = __ddiv_rn(4.0, sMy);
+  // ---- LtL: lane j accumulates row j (k >= j), points in order --------------------------
+  if (lane < 9) {
+    double acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) acc[k] = 0.0;
+#pragma unroll
+    for (int i = 0; i < count; i++) {
+      double x = __dmul_rn(__dsub_rn((double)m[2 * i], cmx), smx);
+      double y = __dmul_rn(__dsub_rn((double)m[2 * i + 1], cmy), smy);
+      double X = __dmul_rn(__dsub_rn((double)M[2 * i], cMx), sMx);
+      double Y = __dmul_rn(__dsub_rn((double)M[2 * i + 1], cMy), sMy);
+      double Lx[9] = {X, Y, 1, 0, 0, 0, __dmul_rn(-x, X), __dmul_rn(-x, Y), -x};
+      double Ly[9] = {0, 0, 0, X, Y, 1, __dmul_rn(-y, X), __dmul_rn(-y, Y), -y};
+      double lxj = 0, lyj = 0;
+#pragma unroll
+      for (int k = 0; k < 9; k++)
+        if (k == lane) { lxj = Lx[k]; lyj = Ly[k]; }
+#pragma unroll
+      for (int k = 0; k < 9; k++)
+        if (k >= lane) acc[k] = __dadd_rn(acc[k], __dadd_rn(__dmul_rn(lxj, Lx[k]), __dmul_rn(lyj, Ly[k])));
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+      if (k >= lane) { sm.S[lane * 9 + k] = acc[k]; sm.S[k * 9 + lane] = acc[k]; }
+#pragma unroll
+    for (int k = 0; k < 9; k++) sm.V[lane * 9 + k] = (k == lane) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  // ---- Jacobi init -----------------------------------------------------------------------
+  if (lane < 9) {
+    const int k = lane;
+    sm.W[k] = sm.S[10 * k];
+    if (k < 8) {
+      int mm = k + 1;
+      double mv = fabs(sm.S[9 * k + mm]);
+      for (int i = k + 2; i < 9; i++) {
+        double val = fabs(sm.S[9 * k + i]);
+        if (mv < val) mv = val, mm = i;
+      }
+      sm.indR[k] = mm;
+    }
+    if (k > 0) {
+      int mm = 0;
+      double mv = fabs(sm.S[k]);
+      for (int i = 1; i < k; i++) {
+        double val = fabs(sm.S[9 * i + k]);
+        if (mv < val) mv = val, mm = i;
+      }
+      sm.indC[k] = mm;
+    }
+  }
+  __syncwarp();
+  const int maxIters = 9 * 9 * 30;
+  for (int iter = 0; iter < maxIters; iter++) {
+    // pivot: candidates 0..7 from indR, 8..15 from indC (scan order), first maximum wins
+    double v = -1.0;
+    int pos = 64, k = 0, l = 0;
+    if (lane < 8) {
+      k = lane; l = sm.indR[lane];
+      v = fabs(sm.S[9 * k + l]); pos = lane;
+    } else if (lane < 16) {
+      const int i = lane - 7;
+      k = sm.indC[i]; l = i;
+      v = fabs(sm.S[9 * k + l]); pos = lane;
+    }
+    warp_argmax_first(v, pos, k, l);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    l = __shfl_sync(0xffffffffu, l, 0);
+    const double p = sm.S[9 * k + l];
+    if (fabs(p) <= DBL_EPSILON) break;
+    const double Wk = sm.W[k], Wl = sm.W[l];
+    double y = __dmul_rn(__dsub_rn(Wl, Wk), 0.5);
+    double tt = __dadd_rn(fabs(y), cv_hypot(p, y));
+    double s = cv_hypot(p, tt);
+    double c = __ddiv_rn(tt, s);
+    s = __ddiv_rn(p, s);
+    tt = __dmul_rn(__ddiv_rn(p, tt), p);
+    if (y < 0) s = -s, tt = -tt;
+    __syncwarp();
+    if (lane == 0) {
+      sm.S[9 * k + l] = 0; sm.S[9 * l + k] = 0;
+      sm.W[k] = __dsub_rn(Wk, tt);
+      sm.W[l] = __dadd_rn(Wl, tt);
+    }
+    if (lane < 9) {
+      const int i = lane;
+      if (i != k && i != l) {
+        double a0 = sm.S[9 * i + k], b0 = sm.S[9 * i + l];
+        double n0 = __dsub_rn(__dmul_rn(a0, c), __dmul_rn(b0, s));
+        double n1 = __dadd_rn(__dmul_rn(a0, s), __dmul_rn(b0, c));
+        sm.S[9 * i + k] = n0; sm.S[9 * k + i] = n0;
+        sm.S[9 * i + l] = n1; sm.S[9 * l + i] = n1;
+      }
+      double a0 = sm.V[9 * k + i], b0 = sm.V[9 * l + i];
+      sm.V[9 * k + i] = __dsub_rn(__dmul_rn(a0, c), __dmul_rn(b0, s));
+      sm.V[9 * l + i] = __dadd_rn(__dmul_rn(a0, s), __dmul_rn(b0, c));
+    }
+    __syncwarp();
+    // refresh indR / indC of rows k and l only (as OpenCV does)
+    if (lane < 4) {
+      const int idx = (lane & 1) ? l : k;
+      if (lane < 2) {
+        if (idx < 8) {
+          int mm = idx + 1;
+          double mv = fabs(sm.S[9 * idx + mm]);
+          for (int i = idx + 2; i < 9; i++) {
+            double val = fabs(sm.S[9 * idx + i]);
+            if (mv < val) mv = val, mm = i;
+          }
+          sm.indR[idx] = mm;
+        }
+      } else {
+        if (idx > 0) {
+          int mm = 0;
+          double mv = fabs(sm.S[idx]);
+          for (int i = 1; i < idx; i++) {
+            double val = fabs(sm.S[9 * i + idx]);
+            if (mv < val) mv = val, mm = i;
+          }
+          sm.indC[idx] = mm;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  // ---- eigenvalue selection sort (descending, first maximum) -> row of the smallest ------
+  if (lane == 0) {
+    double Wv[9];
+    int perm[9];
+    for (int i = 0; i < 9; i++) { Wv[i] = sm.W[i]; perm[i] = i; }
+    for (int k = 0; k < 8; k++) {
+      int mm = k;
+      for (int i = k + 1; i < 9; i++)
+        if (Wv[mm] < Wv[i]) mm = i;
+      if (k != mm) {
+        double tw = Wv[mm]; Wv[mm] = Wv[k]; Wv[k] = tw;
+        int tp = perm[mm]; perm[mm] = perm[k]; perm[k] = tp;
+      }
+    }
+    const double* h0 = &sm.V[9 * perm[8]];
+    double invHnorm[9] = {__ddiv_rn(1., smx), 0, cmx, 0, __ddiv_rn(1., smy), cmy, 0, 0, 1};
+    double Hnorm2[9] = {sMx, 0, __dmul_rn(-cMx, sMx), 0, sMy, __dmul_rn(-cMy, sMy), 0, 0, 1};
+    double Htemp[9], H0[9];
+    mul33(invHnorm, h0, Htemp);
+    mul33(Htemp, Hnorm2, H0);
+    double sc = __ddiv_rn(1., H0[8]);
+    for (int i = 0; i < 9; i++) Hs[(size_t)t * 9 + i] = __dmul_rn(H0[i], sc);
+    valid[t] = 1;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -352,7 +617,6 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   // ---- per-step Lemire thresholds, rejection statistics, chunk/window plan (host, O(steps)
   //      integer work: launch-parameter planning, like the Gaussian taps) ------------------
   ReplayPlan plan = plan_replay(n, iters, window_scale);
-  const std::vector<uint32_t>& thr = plan.thr;
   const std::vector<WinEntry>& win = plan.win;
   const int G = plan.G;
   const uint32_t n_cand = plan.n_cand, max_w = plan.max_w;
@@ -363,12 +627,13 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   mt_ensure(st, mt, seed, need, (uint64_t)steps + 4096);
 
   // ---- buffers ---------------------------------------------------------------------------
-  s.thr.reserve(sizeof(uint32_t) * thr.size());
+  const int nseg = (int)((steps + PANO_SEG_STEPS - 1) / PANO_SEG_STEPS);
+  s.thr.reserve(sizeof(RT) * plan.rt.size());
   s.plan.reserve(sizeof(WinEntry) * win.size());
-  s.cand_off.reserve(sizeof(uint32_t) * (size_t)n_cand);
-  s.cand_samp.reserve(sizeof(int4) * (size_t)n_cand);
-  s.base.reserve(sizeof(unsigned long long) + 2 * sizeof(int));
-  s.samples.reserve(sizeof(int4) * (size_t)(n_chunks * G));
+  s.cand_off.reserve(sizeof(uint32_t) * (size_t)n_cand * (size_t)std::max(nseg, 1));  // end + (nseg-1) boundaries
+  s.cand_samp.reserve(sizeof(unsigned long long) * ((size_t)n_chunks * G * nseg + 1));  // segment start table
+  s.base.reserve(sizeof(ReplayCtl));
+  s.samples.reserve(sizeof(int4) * ((size_t)n_chunks * G * (nseg + 1)));
   s.pts.reserve(sizeof(float4) * (size_t)m);
   s.Hs.reserve(sizeof(double) * 9 * (size_t)iters);
   s.valid.reserve(sizeof(int) * (size_t)iters);
@@ -377,37 +642,47 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   s.mask.reserve((size_t)m);
   pin.reserve(sizeof(SelectOut) + 64);
 
-  PANO_CUDA(cudaMemcpyAsync(s.thr.p, thr.data(), sizeof(uint32_t) * thr.size(), cudaMemcpyHostToDevice, st));
+  PANO_CUDA(cudaMemcpyAsync(s.thr.p, plan.rt.data(), sizeof(RT) * plan.rt.size(), cudaMemcpyHostToDevice, st));
   PANO_CUDA(cudaMemcpyAsync(s.plan.p, win.data(), sizeof(WinEntry) * win.size(), cudaMemcpyHostToDevice, st));
-  PANO_CUDA(cudaMemsetAsync(s.base.p, 0, sizeof(unsigned long long) + 2 * sizeof(int), st));
-  unsigned long long* base_ptr = s.base.as<unsigned long long>();
-  int* status_ptr = reinterpret_cast<int*>(base_ptr + 1);
+  PANO_CUDA(cudaMemsetAsync(s.base.p, 0, sizeof(ReplayCtl), st));
+  ReplayCtl* ctl = s.base.as<ReplayCtl>();
+  int* status_ptr = &ctl->status;
+  uint32_t* cand_end = s.cand_off.as<uint32_t>();
+  uint32_t* seg_off = cand_end + n_cand;
+  unsigned long long* seg_tab = s.cand_samp.as<unsigned long long>();
+  int4* samples_dev = s.samples.as<int4>();
+  int4* seg_w = samples_dev + (size_t)n_chunks * G;
 
   build_points_kernel<<<(m + 255) / 256, 256, 0, st>>>(kp1_dev, kp2_dev, matches_dev, m, s.pts.as<float4>());
   PANO_LAUNCH_CHECK();
 
-  size_t chain_smem = (size_t)n_cand * sizeof(uint32_t) <= 200 * 1024 ? (size_t)n_cand * sizeof(uint32_t) : 0;
-  PANO_CUDA(cudaFuncSetAttribute(replay_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  size_t chain_smem = (size_t)n_cand * sizeof(uint32_t) <= CHAIN_SMEM_MAX ? (size_t)n_cand * sizeof(uint32_t) : 0;
+  PANO_CUDA(cudaFuncSetAttribute(replay_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
   for (int c = 0; c < n_chunks; c++) {
     int Gc = std::min(G, iters - c * G);
-    dim3 grid((max_w + 63) / 64, Gc);
-    if (pairs)
-      replay_walk_kernel<true><<<grid, 64, 0, st>>>(mt.x.as<uint32_t>(), n, steps, s.thr.as<uint32_t>(),
-                                                   s.plan.as<WinEntry>(), base_ptr, s.cand_off.as<uint32_t>(),
-                                                   s.cand_samp.as<int4>(), mt.len, status_ptr);
-    else
-      replay_walk_kernel<false><<<grid, 64, 0, st>>>(mt.x.as<uint32_t>(), n, steps, s.thr.as<uint32_t>(),
-                                                    s.plan.as<WinEntry>(), base_ptr, s.cand_off.as<uint32_t>(),
-                                                    s.cand_samp.as<int4>(), mt.len, status_ptr);
+    dim3 grid((max_w + RW_THREADS - 1) / RW_THREADS, Gc);
+    replay_offsets_kernel<<<grid, RW_THREADS, 0, st>>>(mt.x.as<uint32_t>(), steps, s.thr.as<RT>(), s.plan.as<WinEntry>(),
+                                                       ctl, cand_end, seg_off, (int)n_cand, mt.len);
     PANO_LAUNCH_CHECK();
-    replay_chain_kernel<<<1, 1024, chain_smem, st>>>(s.plan.as<WinEntry>(), Gc, steps, s.cand_off.as<uint32_t>(),
-                                                    s.cand_samp.as<int4>(), (int)n_cand, base_ptr,
-                                                    s.samples.as<int4>() + (size_t)c * G, status_ptr);
+    replay_chain_kernel<<<1, 1024, chain_smem, st>>>(s.plan.as<WinEntry>(), Gc, steps, cand_end, seg_off, (int)n_cand,
+                                                    nseg, ctl, seg_tab + (size_t)c * G * nseg);
+    PANO_LAUNCH_CHECK();
+  }
+  {
+    int nthr = iters * nseg;
+    if (pairs)
+      replay_segments_kernel<true><<<(nthr + 63) / 64, 64, 0, st>>>(mt.x.as<uint32_t>(), n, steps, s.thr.as<RT>(), seg_tab,
+                                                                    iters, nseg, ctl, seg_w);
+    else
+      replay_segments_kernel<false><<<(nthr + 63) / 64, 64, 0, st>>>(mt.x.as<uint32_t>(), n, steps, s.thr.as<RT>(), seg_tab,
+                                                                     iters, nseg, ctl, seg_w);
+    PANO_LAUNCH_CHECK();
+    combine_samples_kernel<<<(iters + 127) / 128, 128, 0, st>>>(seg_w, iters, nseg, samples_dev);
     PANO_LAUNCH_CHECK();
   }
 
-  dlt_kernel<<<(iters + 31) / 32, 32, 0, st>>>(s.pts.as<float4>(), s.samples.as<int4>(), iters, s.Hs.as<double>(),
-                                               s.valid.as<int>());
+  dlt_kernel<<<(iters + DLT_WARPS - 1) / DLT_WARPS, DLT_WARPS * 32, 0, st>>>(s.pts.as<float4>(), s.samples.as<int4>(), iters,
+                                                                            s.Hs.as<double>(), s.valid.as<int>());
   PANO_LAUNCH_CHECK();
   score_kernel<<<iters, 256, 0, st>>>(s.pts.as<float4>(), m, s.Hs.as<double>(), s.valid.as<int>(),
                                       o.distance_threshold, s.counts.as<int>());

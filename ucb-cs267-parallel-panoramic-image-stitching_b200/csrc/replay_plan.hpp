@@ -19,7 +19,7 @@ struct WinEntry {
 };
 
 struct ReplayPlan {
-  std::vector<uint32_t> thr;   // Lemire threshold (2^32 mod range) per step of one shuffle
+  std::vector<RT> rt;          // (range, Lemire threshold 2^32 mod range) per step of one shuffle
   std::vector<WinEntry> win;   // G entries
   int G = 0;                   // iterations per chunk
   uint32_t n_cand = 0, max_w = 0;
@@ -33,34 +33,34 @@ inline ReplayPlan plan_replay(uint32_t n, int iters, int window_scale) {
   ReplayPlan P;
   const bool pairs = shuffle_uses_pairs(n);
   const uint32_t steps = shuffle_steps(n);
-  P.thr.assign(steps ? steps : 1, 0u);
+  P.rt.assign((size_t)(steps ? steps : 1) + 8, RT{2u, 0u});  // +8: vector loads past the end stay in bounds
   double mu = 0, var = 0;
   const uint32_t odd = n & 1u;
   for (uint32_t k = 0; k < steps; k++) {
     uint32_t r;
     if (pairs) {
-      if (!odd && k == 0) { P.thr[k] = 0; continue; }  // d{0,1}: range 2 never rejects
+      if (!odd && k == 0) { P.rt[k] = RT{2u, 0u}; continue; }  // d{0,1}: range 2 never rejects
       uint32_t idx = 2u * k + odd;
       r = (idx + 1u) * (idx + 2u);
     } else {
       r = k + 2u;
     }
     uint32_t T = lemire_threshold(r);
-    P.thr[k] = T;
+    P.rt[k] = RT{r, T};
     double p = (double)T / 4294967296.0;
     mu += p / (1.0 - p);                   // extra draws of a step are geometric
     var += p / ((1.0 - p) * (1.0 - p));
   }
   P.mu = mu;
   P.sigma = std::sqrt(var);
-  // windows of +-(6 sigma sqrt(g) + 8) * scale around g * mu; chunk length chosen so a chunk
-  // has about 48k candidate walks (a few warps per SM scheduler), 8 <= G <= 1024
-  const double zs = 6.0 * window_scale, pad = 8.0 * window_scale;
+  // windows of +-(5 sigma sqrt(g) + 3) * scale around g * mu (a miss is detected and re-run
+  // wider, never guessed); chunk length chosen so a chunk has about `target` candidate walks
+  const double zs = 5.0 * window_scale, pad = 3.0 * window_scale;
   int G = 8;
   for (int cand = 8; cand <= 1024; cand *= 2) {
     double tot = 0;
     for (int g = 0; g < cand; g++) tot += 2.0 * (zs * P.sigma * std::sqrt((double)g) + pad) + 1.0;
-    if (tot <= 48000.0) G = cand; else break;
+    if (tot <= 51000.0) G = cand; else break;  // 51k end offsets = 200 KB: the chain kernel's shared memory
   }
   if (G > iters) G = iters;
   if (G < 1) G = 1;
