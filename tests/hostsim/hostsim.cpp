@@ -75,13 +75,33 @@ int hs_replay(uint32_t seed, uint32_t n, int iters, int window_scale, int32_t* s
   uint64_t base = 0;
   for (int c0 = 0; c0 < iters; c0 += P.G) {
     int Gc = std::min(P.G, iters - c0);
-    for (int g = 0; g < Gc; g++) {          // replay_offsets_kernel
+    // replay_cells_kernel: every (diagonal, step) rejection test of the chunk, packed 32 steps per word
+    const uint32_t nkb = (steps + 31u) / 32u;
+    std::vector<uint32_t> bits((size_t)P.n_diag * nkb, 0u);
+    for (int g = 0; g < Gc; g++) {
       const WinEntry& we = P.win[g];
+      const uint32_t D = (we.width + P.dextra + 31u) / 32u * 32u;
+      uint32_t* bg = bits.data() + (size_t)we.dfirst * nkb;
+      const uint64_t pos0 = base + (uint64_t)g * steps + we.lo;
+      for (uint32_t d = 0; d < D; d++)
+        for (uint32_t k = 0; k < steps; k++) {
+          uint64_t pos = pos0 + d + k;
+          if (pos >= X.size()) continue;
+          if (X[pos] * P.rt[k].r < P.rt[k].T) bg[(size_t)(k / 32u) * D + d] |= 1u << (k & 31u);
+        }
+    }
+    for (int g = 0; g < Gc; g++) {          // replay_walk_bits_kernel
+      const WinEntry& we = P.win[g];
+      const uint32_t D = (we.width + P.dextra + 31u) / 32u * 32u;
       for (uint32_t j = 0; j < we.width; j++) {
         uint64_t start = base + (uint64_t)g * steps + we.lo + j;
         if (start + 2ull * steps + 64ull >= P.stream_need) return 2;
-        cand_end[we.first + j] = walk_offsets(X.data() + base, (uint32_t)(start - base), steps, P.rt.data(),
-                                              seg_off.data() + we.first + j, (size_t)P.n_cand);
+        uint32_t end = walk_bits(bits.data() + (size_t)we.dfirst * nkb, D, nkb, j, steps, (uint32_t)g * steps + we.lo,
+                                 seg_off.data() + we.first + j, (size_t)P.n_cand);
+        if (end == 0xffffffffu) return 8;
+        // cross-check against the direct walk (the formulation the grid replaces)
+        if (end != walk_offsets(X.data() + base, (uint32_t)(start - base), steps, P.rt.data(), nullptr, 0)) return 16;
+        cand_end[we.first + j] = end;
       }
     }
     uint32_t rel = 0;                        // replay_chain_kernel

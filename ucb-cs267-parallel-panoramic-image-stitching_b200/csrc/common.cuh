@@ -133,7 +133,7 @@ int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescr
                         MatchScratch& s, pano_dmatch* out_dev, PinnedBuf& pin);
 
 struct RansacScratch {
-  DevBuf pts, thr, cand_off, cand_samp, base, samples, Hs, valid, counts, result, mask, plan;
+  DevBuf pts, thr, cand_off, cand_samp, base, samples, Hs, valid, counts, result, mask, plan, pts_bits;
 };
 struct RansacResult {
   int status;  // PANO_OK / PANO_ERR_*

@@ -271,7 +271,7 @@ void pano_destroy(pano_ctx* c) {
                     &c->ms.cnt, &c->ms.mflags, &c->ms.midx, &c->ms.mtmp, &c->dQ.desc, &c->dQ.norm, &c->dQ.orig,
                     &c->dT.desc, &c->dT.norm, &c->dT.orig, &c->best, &c->matches, &c->rs.pts, &c->rs.thr,
                     &c->rs.cand_off, &c->rs.cand_samp, &c->rs.base, &c->rs.samples, &c->rs.Hs, &c->rs.valid,
-                    &c->rs.counts, &c->rs.result, &c->rs.mask, &c->rs.plan, &c->mt.x, &c->mt.state, &c->tmp[0],
+                    &c->rs.counts, &c->rs.result, &c->rs.mask, &c->rs.plan, &c->rs.pts_bits, &c->mt.x, &c->mt.state, &c->tmp[0],
                     &c->tmp[1], &c->tmp[2], &c->canvas[0], &c->canvas[1]};
   for (DevBuf* b : bufs) b->release();
   c->pin.release();

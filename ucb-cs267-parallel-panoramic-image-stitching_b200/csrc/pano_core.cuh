@@ -416,7 +416,64 @@ PANO_HD int first_bit8(uint32_t m) {
 
 // Steps per pass-2 segment.  Pass 1 records each candidate's offset at every segment
 // boundary so that pass 2 can walk all segments of all iterations in parallel.
-#define PANO_SEG_STEPS 512u
+#define PANO_SEG_STEPS 256u
+
+PANO_HD uint32_t ctz32(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)(__ffs((int)w) - 1);
+#else
+  return (uint32_t)__builtin_ctz(w);
+#endif
+}
+
+// Pass 1, grid formulation.  For one iteration, cell (d, k) says whether the draw at stream
+// position pos0 + d + k is rejected when used for step k; d ("diagonal") = candidate start index
+// + rejections so far.  The cells are evaluated independently (replay_cells_kernel) and packed
+// 32 steps per word: word(kb, d) = bits[kb * D + d].  A walk then only scans words: it moves
+// along its diagonal until the next set bit (a rejection at step k), hops to diagonal d + 1 and
+// re-examines the same step there.  Returns the end offset pos0 + d_final + steps (relative to
+// the chunk base) or 0xffffffff if the walk leaves the D diagonals that were evaluated.
+// Segment-boundary offsets are recorded as in walk_offsets.
+PANO_HD uint32_t walk_bits(const uint32_t* bits, uint32_t D, uint32_t nkb, uint32_t d0, uint32_t steps,
+                           uint32_t pos0, uint32_t* seg_off, size_t seg_stride) {
+  uint32_t d = d0, kb = 0, mask = ~0u;
+  while (kb < nkb) {
+    // 8 words ahead on the current diagonal (independent loads); a hop discards the rest
+    uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
+    const uint32_t* p = bits + (size_t)kb * D + d;
+    const uint32_t left = nkb - kb;
+    w0 = p[0] & mask;
+    w1 = left > 1 ? p[(size_t)D] : 0u;
+    w2 = left > 2 ? p[(size_t)2 * D] : 0u;
+    w3 = left > 3 ? p[(size_t)3 * D] : 0u;
+    w4 = left > 4 ? p[(size_t)4 * D] : 0u;
+    w5 = left > 5 ? p[(size_t)5 * D] : 0u;
+    w6 = left > 6 ? p[(size_t)6 * D] : 0u;
+    w7 = left > 7 ? p[(size_t)7 * D] : 0u;
+    mask = ~0u;
+    uint32_t adv, w;  // words without a rejection before the first one that has one
+    if (w0) { adv = 0; w = w0; }
+    else if (w1) { adv = 1; w = w1; }
+    else if (w2) { adv = 2; w = w2; }
+    else if (w3) { adv = 3; w = w3; }
+    else if (w4) { adv = 4; w = w4; }
+    else if (w5) { adv = 5; w = w5; }
+    else if (w6) { adv = 6; w = w6; }
+    else if (w7) { adv = 7; w = w7; }
+    else { adv = left < 8u ? left : 8u; w = 0; }
+    // at most one segment boundary (multiple of PANO_SEG_STEPS / 32 = 8 words) lies in (kb, kb + adv]
+    const uint32_t nb = (kb + adv) & ~(PANO_SEG_STEPS / 32u - 1u);
+    if (nb > kb && nb < nkb && seg_off)
+      seg_off[(size_t)(nb / (PANO_SEG_STEPS / 32u) - 1u) * seg_stride] = pos0 + d + nb * 32u;
+    kb += adv;
+    if (w) {
+      d++;
+      if (d >= D) return 0xffffffffu;
+      mask = ~0u << ctz32(w);
+    }
+  }
+  return pos0 + d + steps;
+}
 
 // pass 1: end offset (and, if seg_off != nullptr, the offset at the start of segments 1, 2, ...
 // written to seg_off[(s - 1) * seg_stride])

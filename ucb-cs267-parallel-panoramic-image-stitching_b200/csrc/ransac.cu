@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace pano {
 
@@ -120,20 +121,63 @@ struct ReplayCtl {
 constexpr int RW_THREADS = 128;
 constexpr size_t CHAIN_SMEM_MAX = 200 * 1024;  // + 20 KB static: under the 227 KB per-block limit
 
+// Pass 1a: rejection cells of a whole chunk.  One warp = one (32-step block kb, block of 32
+// diagonals) task: lane = step within the block (its (r, T) stays in registers), loop over the
+// 32 diagonals; every load is independent and coalesced, the 32 tests of a diagonal are packed
+// with one ballot, and the 32 words are written as one 128-byte row.
+__global__ void __launch_bounds__(256)
+replay_cells_kernel(const uint32_t* __restrict__ X, uint32_t steps, const RT* __restrict__ rt,
+                    const WinEntry* __restrict__ win, const int* __restrict__ diag_block_iter, int n_dblocks,
+                    uint32_t nkb, uint32_t dextra, const ReplayCtl* ctl, uint32_t* __restrict__ bits,
+                    unsigned long long x_limit) {
+  __shared__ uint32_t s_x[8][64];    // the 64 stream words a warp's 32x32 cell tile touches
+  __shared__ uint32_t s_w[8][32];    // its 32 result words
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
+  if (wg >= (long long)n_dblocks * nkb) return;
+  const uint32_t kb = (uint32_t)(wg / n_dblocks);
+  const int db = (int)(wg - (long long)kb * n_dblocks);
+  const int g = diag_block_iter[db];
+  const WinEntry we = win[g];
+  const uint32_t D = (we.width + dextra + 31u) / 32u * 32u;
+  const uint32_t dloc0 = (uint32_t)db * 32u - we.dfirst;
+  const uint32_t k = kb * 32u + lane;
+  const bool live = k < steps;
+  RT q;
+  q.r = 0; q.T = 0;
+  if (live) q = rt[k];
+  // cell (diagonal dloc0 + dd, step kb*32 + lane) reads stream word pos + dd + lane
+  const unsigned long long pos = ctl->base + (unsigned long long)g * steps + we.lo + dloc0 + (unsigned long long)kb * 32u;
+  const bool in_range = pos + 64ull < x_limit;
+  s_x[wid][lane] = in_range ? X[pos + lane] : 0xffffffffu;
+  s_x[wid][32 + lane] = in_range ? X[pos + 32 + lane] : 0xffffffffu;
+  __syncwarp();
+#pragma unroll
+  for (int dd = 0; dd < 32; dd++) {
+    const bool rej = s_x[wid][dd + lane] * q.r < q.T;  // dead lanes carry (r, T) = (0, 0): never set
+    const uint32_t w = __ballot_sync(0xffffffffu, rej);
+    if (lane == 0) s_w[wid][dd] = w;
+  }
+  __syncwarp();
+  bits[(size_t)we.dfirst * nkb + (size_t)kb * D + dloc0 + lane] = s_w[wid][lane];
+}
+
+// Pass 1b: thread (g, j) scans the cell words of iteration g from candidate start j.
 __global__ void __launch_bounds__(RW_THREADS)
-replay_offsets_kernel(const uint32_t* __restrict__ X, uint32_t steps, const RT* __restrict__ rt,
-                      const WinEntry* __restrict__ win, ReplayCtl* ctl, uint32_t* __restrict__ cand_end,
-                      uint32_t* __restrict__ seg_off, int n_cand, unsigned long long stream_len) {
+replay_walk_bits_kernel(uint32_t steps, const WinEntry* __restrict__ win, uint32_t nkb, uint32_t dextra,
+                        ReplayCtl* ctl, const uint32_t* __restrict__ bits, uint32_t* __restrict__ cand_end,
+                        uint32_t* __restrict__ seg_off, int n_cand, unsigned long long stream_len) {
   const int g = blockIdx.y;
   const WinEntry we = win[g];
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= we.width) return;
-  const unsigned long long base = ctl->base;
-  const unsigned long long start = base + (unsigned long long)g * steps + we.lo + j;
+  const uint32_t D = (we.width + dextra + 31u) / 32u * 32u;
+  const unsigned long long start = ctl->base + (unsigned long long)g * steps + we.lo + j;
   uint32_t end = 0xffffffffu;
   if (start + 2ull * steps + 64ull < stream_len) {
-    // offsets relative to the chunk base fit 32 bits (chunk span << 2^32)
-    end = walk_offsets(X + base, (uint32_t)(start - base), steps, rt, seg_off + we.first + j, (size_t)n_cand);
+    end = walk_bits(bits + (size_t)we.dfirst * nkb, D, nkb, j, steps, (uint32_t)g * steps + we.lo,
+                    seg_off + we.first + j, (size_t)n_cand);
+    if (end == 0xffffffffu) atomicOr(&ctl->status, 8);  // left the evaluated diagonals: re-plan wider
   } else {
     atomicOr(&ctl->status, 2);
   }
@@ -616,7 +660,12 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
 
   // ---- per-step Lemire thresholds, rejection statistics, chunk/window plan (host, O(steps)
   //      integer work: launch-parameter planning, like the Gaussian taps) ------------------
-  ReplayPlan plan = plan_replay(n, iters, window_scale);
+  static const double target_cand = [] {
+    const char* e = getenv("PANO_REPLAY_TARGET");  // candidate walks per chunk (tuning knob)
+    double v = e ? atof(e) : 0.0;
+    return (v >= 64.0 && v <= 51000.0) ? v : 50000.0;
+  }();
+  ReplayPlan plan = plan_replay(n, iters, window_scale, target_cand);
   const std::vector<WinEntry>& win = plan.win;
   const int G = plan.G;
   const uint32_t n_cand = plan.n_cand, max_w = plan.max_w;
@@ -633,6 +682,9 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   s.cand_off.reserve(sizeof(uint32_t) * (size_t)n_cand * (size_t)std::max(nseg, 1));  // end + (nseg-1) boundaries
   s.cand_samp.reserve(sizeof(unsigned long long) * ((size_t)n_chunks * G * nseg + 1));  // segment start table
   s.base.reserve(sizeof(ReplayCtl));
+  const uint32_t nkb = (steps + 31u) / 32u;
+  const int n_dblocks = (int)plan.diag_block_iter.size();
+  s.pts_bits.reserve(sizeof(uint32_t) * (size_t)plan.n_diag * nkb + sizeof(int) * (size_t)n_dblocks + 256);
   s.samples.reserve(sizeof(int4) * ((size_t)n_chunks * G * (nseg + 1)));
   s.pts.reserve(sizeof(float4) * (size_t)m);
   s.Hs.reserve(sizeof(double) * 9 * (size_t)iters);
@@ -645,6 +697,9 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   PANO_CUDA(cudaMemcpyAsync(s.thr.p, plan.rt.data(), sizeof(RT) * plan.rt.size(), cudaMemcpyHostToDevice, st));
   PANO_CUDA(cudaMemcpyAsync(s.plan.p, win.data(), sizeof(WinEntry) * win.size(), cudaMemcpyHostToDevice, st));
   PANO_CUDA(cudaMemsetAsync(s.base.p, 0, sizeof(ReplayCtl), st));
+  uint32_t* bits = s.pts_bits.as<uint32_t>();
+  int* dbi = reinterpret_cast<int*>(bits + (size_t)plan.n_diag * nkb);
+  PANO_CUDA(cudaMemcpyAsync(dbi, plan.diag_block_iter.data(), sizeof(int) * (size_t)n_dblocks, cudaMemcpyHostToDevice, st));
   ReplayCtl* ctl = s.base.as<ReplayCtl>();
   int* status_ptr = &ctl->status;
   uint32_t* cand_end = s.cand_off.as<uint32_t>();
@@ -661,8 +716,16 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   for (int c = 0; c < n_chunks; c++) {
     int Gc = std::min(G, iters - c * G);
     dim3 grid((max_w + RW_THREADS - 1) / RW_THREADS, Gc);
-    replay_offsets_kernel<<<grid, RW_THREADS, 0, st>>>(mt.x.as<uint32_t>(), steps, s.thr.as<RT>(), s.plan.as<WinEntry>(),
-                                                       ctl, cand_end, seg_off, (int)n_cand, mt.len);
+    {
+      // diagonal blocks of iterations >= Gc (short last chunk) are evaluated too; they are cheap
+      long long warps = (long long)n_dblocks * nkb;
+      replay_cells_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(mt.x.as<uint32_t>(), steps, s.thr.as<RT>(),
+                                                                      s.plan.as<WinEntry>(), dbi, n_dblocks, nkb,
+                                                                      plan.dextra, ctl, bits, mt.len + mt.guard - 64);
+      PANO_LAUNCH_CHECK();
+    }
+    replay_walk_bits_kernel<<<grid, RW_THREADS, 0, st>>>(steps, s.plan.as<WinEntry>(), nkb, plan.dextra, ctl, bits,
+                                                         cand_end, seg_off, (int)n_cand, mt.len);
     PANO_LAUNCH_CHECK();
     replay_chain_kernel<<<1, 1024, chain_smem, st>>>(s.plan.as<WinEntry>(), Gc, steps, cand_end, seg_off, (int)n_cand,
                                                     nseg, ctl, seg_tab + (size_t)c * G * nseg);

@@ -15,7 +15,7 @@ struct WinEntry {
   uint32_t lo;     // window lower bound, relative to (chunk base offset + g * steps)
   uint32_t width;  // number of candidate start offsets
   uint32_t first;  // index of candidate 0 in the chunk's candidate arrays
-  uint32_t pad;
+  uint32_t dfirst; // index of diagonal 0 in the chunk's diagonal space (multiple of 32)
 };
 
 struct ReplayPlan {
@@ -25,11 +25,14 @@ struct ReplayPlan {
   uint32_t n_cand = 0, max_w = 0;
   double mu = 0, sigma = 0;    // mean / std-dev of the rejections of one shuffle
   uint64_t stream_need = 0;    // engine outputs the replay may touch
+  uint32_t dextra = 0;         // diagonals beyond a window: room for one walk's own rejections
+  uint32_t n_diag = 0;         // diagonals per chunk (each window padded to a multiple of 32)
+  std::vector<int> diag_block_iter;  // iteration of every 32-diagonal block
 };
 
 // n = number of shuffled elements (matches), iters = RANSAC iterations,
 // window_scale = 1, 2, 4, ... (doubled by the caller after a detected window miss).
-inline ReplayPlan plan_replay(uint32_t n, int iters, int window_scale) {
+inline ReplayPlan plan_replay(uint32_t n, int iters, int window_scale, double target_cand = 50000.0) {
   ReplayPlan P;
   const bool pairs = shuffle_uses_pairs(n);
   const uint32_t steps = shuffle_steps(n);
@@ -60,7 +63,7 @@ inline ReplayPlan plan_replay(uint32_t n, int iters, int window_scale) {
   for (int cand = 8; cand <= 1024; cand *= 2) {
     double tot = 0;
     for (int g = 0; g < cand; g++) tot += 2.0 * (zs * P.sigma * std::sqrt((double)g) + pad) + 1.0;
-    if (tot <= 51000.0) G = cand; else break;  // 51k end offsets = 200 KB: the chain kernel's shared memory
+    if (tot <= target_cand) G = cand; else break;  // (<= 51k: the chain kernel stages end offsets in smem)
   }
   if (G > iters) G = iters;
   if (G < 1) G = 1;
@@ -74,10 +77,19 @@ inline ReplayPlan plan_replay(uint32_t n, int iters, int window_scale) {
     P.win[g].lo = (uint32_t)lo;
     P.win[g].width = (uint32_t)(hi - lo) + 1u;
     P.win[g].first = P.n_cand;
-    P.win[g].pad = 0;
+    P.win[g].dfirst = 0;
     P.n_cand += P.win[g].width;
     P.max_w = std::max(P.max_w, P.win[g].width);
     max_hi = std::max(max_hi, hi);
+  }
+  // a walk moves up one diagonal per rejection: mu + 8 sigma (+ margin) extra diagonals; a walk
+  // that would leave them is flagged and the caller re-plans wider, like a window miss
+  P.dextra = (uint32_t)std::ceil(mu + (8.0 * window_scale) * P.sigma + 8.0 * window_scale);
+  for (int g = 0; g < G; g++) {
+    P.win[g].dfirst = P.n_diag;
+    uint32_t D = (P.win[g].width + P.dextra + 31u) / 32u * 32u;
+    for (uint32_t b = 0; b < D / 32u; b++) P.diag_block_iter.push_back(g);
+    P.n_diag += D;
   }
   P.stream_need = (uint64_t)((double)iters * ((double)steps + mu) +
                              12.0 * window_scale * P.sigma * std::sqrt((double)iters) + max_hi + 4.0 * steps + 4096.0);
