@@ -1,6 +1,332 @@
-// match_tc.cu — K4 tensor-core matcher (placeholder until the tcgen05 kernel lands).
+// match_tc.cu — K4 tensor-core matcher: brute-force 1-NN over 5x5x3 u8 patches as an integer
+// distance GEMM on the 5th-gen tensor cores (tcgen05.mma kind::i8, u8 x u8 -> s32 in TMEM)
+// with a fused arg-min epilogue.  The Nq x Nt distance matrix is never written.
+//
+// Semantics: ref src/serial/main.cpp:188-244.  SSD(q, t) = |q|^2 + |t|^2 - 2 q.t, all exact
+// integers (q.t <= 75 * 255^2 < 2^23).  For a query row the epilogue minimises the packed key
+//      key(j) = (|t_j|^2 - 2 q.t_j) * 256 + (j mod 256)         (fits a signed 32-bit word)
+// over the 256 columns of a tile with one IMAD + one signed MIN per element; lexicographic order
+// on (partial SSD, column) gives "first strict minimum in train order" (:230-233) inside a tile,
+// tiles are visited in train order with a strict '<', and CTAs that split the train range merge
+// through atomicMin on (ssd << 32 | j).
+//
+// Structure (one persistent CTA per SM, 288 threads):
+//   warps 0-3  epilogue: TMEM -> registers (tcgen05.ld 32x32b.x32), key/min, atomicMin
+//   warps 4-7  loaders : descriptor rows (global, row-major [rows][128 B]) -> shared memory in the
+//                        128-byte-swizzled K-major layout the UMMA descriptors expect
+//   warp  8    one lane issues tcgen05.mma (4 K-steps of 32 bytes per 128x256 tile) and commits
+// Pipelines (mbarriers): B stages full/empty (3 deep), A buffer full/empty (2 deep),
+// TMEM accumulators full/empty (2 x 256 columns).
+// Every wait is bounded: a bring-up bug raises an error flag instead of hanging the device.
 #include "common.cuh"
+
 namespace pano {
-bool match_tc_available() { return false; }
-void match_tc_device(cudaStream_t, const DevDescriptors&, const DevDescriptors&, unsigned long long*) {}
+
+namespace {
+
+constexpr int TM = 128;            // query rows per tile (UMMA M)
+constexpr int TN = 256;            // train rows per tile (UMMA N)
+constexpr int KB = PANO_DESC_STRIDE;  // 128 bytes of K per row = one 128B swizzle atom
+constexpr int NSTAGE = 3;
+constexpr int A_BYTES = TM * KB;   // 16 KB
+constexpr int B_BYTES = TN * KB;   // 32 KB
+constexpr int TC_THREADS = 288;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+// instruction descriptor, kind::i8: D = S32 (2 << 4), A = B = UINT8 (0), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24   (cute::UMMA::InstrDescriptor layout)
+constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+struct Smem {
+  // tiles first: 1024-byte aligned (SWIZZLE_128B requirement)
+  uint8_t A[2][A_BYTES];
+  uint8_t B[NSTAGE][B_BYTES];
+  int cvec[2][TN];                 // per TMEM buffer: |t_j|^2 * 256 + (j mod 256), INT_MAX for padding
+  unsigned long long b_full[NSTAGE], b_empty[NSTAGE];
+  unsigned long long a_full[2], a_empty[2];
+  unsigned long long t_full[2], t_empty[2];
+  uint32_t tmem_base;
+  int abort_flag;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded polling wait (test_wait never blocks, so the spin bound is a real time bound);
+// returns false if it gave up (or another role already aborted)
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity, volatile int* abort_flag) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < SPIN_LIMIT; spin++) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return true;
+    if ((spin & 1023u) == 1023u && *abort_flag) return false;
+  }
+  *abort_flag = 1;
+  return false;
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4 [0,14), LBO >> 4 [16,30) (unused for swizzled K-major: 1), SBO >> 4 [32,46)
+// = 1024 bytes between 8-row groups, version 1 at [46,48), layout type 2 (SWIZZLE_128B) at [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// rows [row0, row0 + rows) of a row-major [.][128 B] descriptor matrix -> swizzled K-major tile.
+// 128 threads, 8 independent 16-byte loads in flight per thread before the stores.
+__device__ __forceinline__ void load_tile(uint8_t* dst, const uint8_t* __restrict__ src, int row0, int rows, int tid,
+                                          int nthreads) {
+  const uint4* g = reinterpret_cast<const uint4*>(src + (size_t)row0 * KB);
+  const int total = rows * 8;
+  for (int e0 = tid; e0 < total; e0 += nthreads * 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int e = e0 + u * nthreads;
+      v[u] = e < total ? g[e] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int e = e0 + u * nthreads;
+      if (e < total) {
+        const int r = e >> 3, q = e & 7;
+        *reinterpret_cast<uint4*>(dst + r * KB + ((q ^ (r & 7)) << 4)) = v[u];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+match_tc_kernel(const uint8_t* __restrict__ qd, const uint32_t* __restrict__ qn, int nq,
+                const uint8_t* __restrict__ td, const uint32_t* __restrict__ tn, int nt, int n_qtiles,
+                int n_ttiles, int tiles_per_item, int n_items, unsigned long long* __restrict__ best,
+                int* __restrict__ err) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  volatile int* abort_flag = &S.abort_flag;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; i++) { mbar_init(&S.b_full[i], 128); mbar_init(&S.b_empty[i], 1); }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&S.a_full[i], 128); mbar_init(&S.a_empty[i], 1);
+      mbar_init(&S.t_full[i], 1);   mbar_init(&S.t_empty[i], 128);
+    }
+    S.abort_flag = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {  // TMEM: all 512 columns (two 128 x 256 s32 accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = S.tmem_base;
+
+  const int per_q = (n_ttiles + tiles_per_item - 1) / tiles_per_item;  // items per query tile
+
+  if (warp < 4) {
+    // ================= epilogue =================
+    uint32_t tile_ctr = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int qt = item / per_q, c = item - qt * per_q;
+      const int t0 = c * tiles_per_item, t1 = min(n_ttiles, t0 + tiles_per_item);
+      const int qrow = qt * TM + (int)threadIdx.x;
+      const int myqn = qrow < nq ? (int)qn[qrow] : 0;
+      int best_ssd = 0x7fffffff, best_j = -1;
+      bool ok = true;
+      for (int tt = t0; tt < t1 && ok; tt++, tile_ctr++) {
+        const uint32_t tb = tile_ctr & 1u, ph = (tile_ctr >> 1) & 1u;
+        const uint32_t s = tile_ctr % NSTAGE, sph = (tile_ctr / NSTAGE) & 1u;
+        // b_full: acquires the loaders' cvec[tb] writes; t_full: the accumulator is complete
+        ok = mbar_wait(&S.b_full[s], sph, abort_flag) && mbar_wait(&S.t_full[tb], ph, abort_flag);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + tb * TN;
+        int kmin = 0x7fffffff;
+        uint32_t r[32];
+        tmem_ld32(taddr, r);
+        tmem_ld_wait();
+#pragma unroll 1
+        for (int cb = 0; cb < TN / 32; cb++) {
+          uint32_t cur[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) cur[i] = r[i];
+          if (cb + 1 < TN / 32) tmem_ld32(taddr + (cb + 1) * 32, r);  // next chunk in flight
+          const int4* cv = reinterpret_cast<const int4*>(&S.cvec[tb][cb * 32]);
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int4 c4 = cv[i];
+            kmin = min(kmin, (int)((uint32_t)c4.x - 512u * cur[4 * i]));
+            kmin = min(kmin, (int)((uint32_t)c4.y - 512u * cur[4 * i + 1]));
+            kmin = min(kmin, (int)((uint32_t)c4.z - 512u * cur[4 * i + 2]));
+            kmin = min(kmin, (int)((uint32_t)c4.w - 512u * cur[4 * i + 3]));
+          }
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(&S.t_empty[tb]);
+        const int v = kmin >> 8, jl = kmin & 255;
+        const int ssd = v + myqn;
+        if (kmin != 0x7fffffff && ssd < best_ssd) { best_ssd = ssd; best_j = tt * TN + jl; }
+      }
+      if (ok && qrow < nq && best_j >= 0 && best_j < nt)
+        atomicMin(&best[qrow], ((unsigned long long)(uint32_t)best_ssd << 32) | (uint32_t)best_j);
+    }
+  } else if (warp < 8) {
+    // ================= loaders =================
+    const int ltid = threadIdx.x - 128;
+    uint32_t tile_ctr = 0, item_ctr = 0;
+    bool ok = true;
+    for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, item_ctr++) {
+      const int qt = item / per_q, c = item - qt * per_q;
+      const int t0 = c * tiles_per_item, t1 = min(n_ttiles, t0 + tiles_per_item);
+      const uint32_t ab = item_ctr & 1u, aph = (item_ctr >> 1) & 1u;
+      ok = mbar_wait(&S.a_empty[ab], aph ^ 1u, abort_flag);
+      if (!ok) break;
+      load_tile(S.A[ab], qd, qt * TM, TM, ltid, 128);
+      fence_async_smem();
+      mbar_arrive(&S.a_full[ab]);
+      for (int tt = t0; tt < t1; tt++, tile_ctr++) {
+        const uint32_t s = tile_ctr % NSTAGE, sph = (tile_ctr / NSTAGE) & 1u;
+        const uint32_t tb = tile_ctr & 1u, tph = (tile_ctr >> 1) & 1u;
+        ok = mbar_wait(&S.b_empty[s], sph ^ 1u, abort_flag) && mbar_wait(&S.t_empty[tb], tph ^ 1u, abort_flag);
+        if (!ok) break;
+        load_tile(S.B[s], td, tt * TN, TN, ltid, 128);
+        for (int j = ltid; j < TN; j += 128) {
+          const int col = tt * TN + j;
+          S.cvec[tb][j] = col < nt ? (int)(tn[col] * 256u + (uint32_t)j) : 0x7fffffff;
+        }
+        fence_async_smem();
+        mbar_arrive(&S.b_full[s]);
+      }
+    }
+  } else if (lane == 0) {
+    // ================= MMA issuer (one thread) =================
+    uint32_t tile_ctr = 0, item_ctr = 0;
+    bool ok = true;
+    for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, item_ctr++) {
+      const int qt = item / per_q, c = item - qt * per_q;
+      const int t0 = c * tiles_per_item, t1 = min(n_ttiles, t0 + tiles_per_item);
+      (void)qt;
+      const uint32_t ab = item_ctr & 1u, aph = (item_ctr >> 1) & 1u;
+      ok = mbar_wait(&S.a_full[ab], aph, abort_flag);
+      if (!ok) break;
+      const uint64_t adesc = make_desc(smem_u32(S.A[ab]));
+      for (int tt = t0; tt < t1; tt++, tile_ctr++) {
+        const uint32_t s = tile_ctr % NSTAGE, sph = (tile_ctr / NSTAGE) & 1u;
+        const uint32_t tb = tile_ctr & 1u, tph = (tile_ctr >> 1) & 1u;
+        ok = mbar_wait(&S.b_full[s], sph, abort_flag) && mbar_wait(&S.t_empty[tb], tph ^ 1u, abort_flag);
+        if (!ok) break;
+        tc_fence_after();
+        const uint64_t bdesc = make_desc(smem_u32(S.B[s]));
+        const uint32_t d_tmem = tmem_base + tb * TN;
+#pragma unroll
+        for (int ks = 0; ks < KB / 32; ks++)  // 32 bytes of K per MMA: descriptor start advances 32 B
+          mma_i8(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), ks > 0 ? 1u : 0u);
+        mma_commit(&S.b_empty[s]);   // smem stage reusable once these MMAs have read it
+        mma_commit(&S.t_full[tb]);   // accumulator ready for the epilogue
+      }
+      mma_commit(&S.a_empty[ab]);    // A buffer reusable after the item's last MMA
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && S.abort_flag) atomicExch(err, 1);
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+int g_tc_state = 0;  // 0 unknown, 1 usable, -1 disabled after a failure
+
+}  // namespace
+
+bool match_tc_available() { return g_tc_state >= 0; }
+
+void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t, unsigned long long* best) {
+  PANO_CUDA(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * (size_t)q.count, st));
+  if (q.count == 0 || t.count == 0) return;
+  static DevBuf errbuf;
+  errbuf.reserve(sizeof(int));
+  PANO_CUDA(cudaMemsetAsync(errbuf.p, 0, sizeof(int), st));
+  const int n_qtiles = (q.count + TM - 1) / TM;
+  const int n_ttiles = (t.count + TN - 1) / TN;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // work items = (query tile, run of train tiles); aim at ~4 items per SM for balance
+  int per_q = (4 * sms + n_qtiles - 1) / n_qtiles;
+  if (per_q > n_ttiles) per_q = n_ttiles;
+  if (per_q < 1) per_q = 1;
+  int tiles_per_item = (n_ttiles + per_q - 1) / per_q;
+  per_q = (n_ttiles + tiles_per_item - 1) / tiles_per_item;
+  const int n_items = n_qtiles * per_q;
+  const int grid = n_items < sms ? n_items : sms;
+  const size_t smem = sizeof(Smem) + 1024;
+  PANO_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(q.desc.as<uint8_t>(), q.norm.as<uint32_t>(), q.count,
+                                                  t.desc.as<uint8_t>(), t.norm.as<uint32_t>(), t.count, n_qtiles,
+                                                  n_ttiles, tiles_per_item, n_items, best, errbuf.as<int>());
+  PANO_LAUNCH_CHECK();
+  if (g_tc_state == 0) {
+    // first use on this process: make sure the pipeline ran to completion
+    int e = 0;
+    PANO_CUDA(cudaMemcpyAsync(&e, errbuf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PANO_CUDA(cudaStreamSynchronize(st));
+    if (e != 0) {
+      g_tc_state = -1;
+      throw CudaError{cudaErrorLaunchFailure, "tensor-core matcher pipeline timed out", __FILE__, __LINE__};
+    }
+    g_tc_state = 1;
+  }
+}
+
 }  // namespace pano
