@@ -202,47 +202,62 @@ def run_engine(a):
                                   canvases_out=[c.numpy() for c in Ch])
         return res, ms
 
+    pdist = importlib.import_module(PKG + ".dist")
+    n_total = world * P
+    my_idx = [rank * P + i for i in range(P)]   # bench shards: P resident pairs per GPU (weak scaling)
+    est = torch.cuda.ExternalStream(eng.stream_ptr())
+
+    def exchange(res):
+        """the path's only collective: all-gather of the per-pair homographies (96 B each)"""
+        if world > 1:
+            return pdist.all_gather_results(pdist.pack_results(my_idx, res), n_total, device="cuda")
+        return None
+
+    def timed(step_fn, steps):
+        """K steps bracketed by barrier + synchronize; device time between two events on the
+        engine's stream (includes every host gap inside the region)"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(est)
+        stage = {"detect": 0.0, "match": 0.0, "ransac": 0.0, "warp": 0.0}
+        last = None
+        for _ in range(steps):
+            last, _ms = step_fn()
+            exchange(last)
+            for r in last:
+                for k in stage:
+                    stage[k] += r["ms"][k]
+        e1.record(est)
+        e1.synchronize()
+        barrier()
+        return e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0, stage, last
+
     # ---- resident-input throughput --------------------------------------------------------
     for _ in range(a.warmup):
         res, _ = step_resident()
+        exchange(res)
     assert all(r["status"] == 0 for r in res), [r["status_name"] for r in res]
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
     n0 = eng.kernel_launches()
-    ms_dev, t0 = 0.0, time.perf_counter()
-    stage = {"detect": 0.0, "match": 0.0, "ransac": 0.0, "warp": 0.0}
-    for _ in range(a.steps):
-        res, ms = step_resident()
-        ms_dev += ms
-        for r in res:
-            for k in stage:
-                stage[k] += r["ms"][k]
-    barrier()
-    wall = time.perf_counter() - t0
+    ms_dev, wall_ms, stage, res = timed(step_resident, a.steps)
     launches = eng.kernel_launches() - n0
     clocks = sampler.stop() if rank == 0 else None
     # ---- end-to-end (host buffers) ----------------------------------------------------------
     for _ in range(min(a.warmup, 2)):
         step_e2e()
-    barrier()
-    ms_e2e = 0.0
-    for _ in range(a.steps):
-        res_e, ms = step_e2e()
-        ms_e2e += ms
-    barrier()
+    ms_e2e, _, _, res_e = timed(step_e2e, a.steps)
     d2h = sum(3 * r["canvas"][0] * r["canvas"][1] for r in res_e)
     h2d = P * 2 * 3 * w * h
     if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e, wall * 1000.0], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_dev, ms_e2e, wall_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e, wall_ms = [float(x) for x in t]
         lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt[0])
-    else:
-        wall_ms = wall * 1000.0
     mp_step = world * P * 2 * w * h / 1e6
     value = mp_step * a.steps / (ms_dev / 1000.0)
     e2e_val = mp_step * a.steps / (ms_e2e / 1000.0)
@@ -274,6 +289,27 @@ def run_engine(a):
                                                  C.c_size_t(canvas.stride(0)), C.c_size_t(canvas.numel()),
                                                  C.byref(info)))
         t_warp = time_kernel(eng, torch, k_warp)
+        # matcher stage (descriptor gather + tcgen05 distance GEMM + emit) on resident inputs
+        kl_t = torch.zeros((max(r0["kl"], 1), 2), dtype=torch.int32, device="cuda")
+        kr_t = torch.zeros((max(r0["kr"], 1), 2), dtype=torch.int32, device="cuda")
+        cnt = C.c_int(0)
+        ho = pkg.HarrisCornerOptions()
+        eng._check(eng.lib.pano_detect(eng.ctx, C.c_void_p(Ld[0].data_ptr()), w, h, C.c_size_t(Ld[0].stride(0)), 1,
+                                       C.byref(ho), C.c_void_p(kl_t.data_ptr()), r0["kl"], C.byref(cnt)))
+        eng._check(eng.lib.pano_detect(eng.ctx, C.c_void_p(Rd[0].data_ptr()), w, h, C.c_size_t(Rd[0].stride(0)), 1,
+                                       C.byref(ho), C.c_void_p(kr_t.data_ptr()), r0["kr"], C.byref(cnt)))
+        m_t = torch.empty((max(r0["kr"], 1), 3), dtype=torch.int32, device="cuda")
+
+        def k_match():
+            eng._check(eng.lib.pano_match(eng.ctx, C.c_void_p(kr_t.data_ptr()), r0["kr"], C.c_void_p(kl_t.data_ptr()),
+                                          r0["kl"], C.c_void_p(Rd[0].data_ptr()), w, h, C.c_size_t(Rd[0].stride(0)),
+                                          C.c_void_p(Ld[0].data_ptr()), w, h, C.c_size_t(Ld[0].stride(0)), 1,
+                                          C.byref(ho), 0, C.c_void_p(m_t.data_ptr()), r0["kr"], C.byref(cnt)))
+        t_match = time_kernel(eng, torch, k_match)
+        traffic = {}
+        tf = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from ncu --set full
+        if os.path.exists(tf):
+            traffic = json.load(open(tf))
         kernels = {
             "harris_response_kernel": {"ms": t_harris, "alg_bytes": 3 * npx, "launches_per_pair": 2,
                                        "note": "FP64-pipe bound by construction (157 non-fusable FP64 ops/px); "
@@ -283,16 +319,23 @@ def run_engine(a):
         }
         share = {k: v["ms"] * v["launches_per_pair"] for k, v in kernels.items()}
         dom = max(stage_ms, key=stage_ms.get)
-        # the roofline object describes the dominant HBM-type kernel of the step; the stage
-        # table next to it shows where the rest of the time goes (RANSAC replay is latency /
-        # issue bound, not bandwidth bound — see DESIGN.md)
+        # The roofline object describes the dominant kernel of the step among those that have an
+        # HBM roofline (stencil / warp).  The RANSAC replay kernels that dominate the step are
+        # integer issue/latency bound, so neither roofline applies to them; the
+        # stage table and the ncu launch list under profiles/ show their share.
         top = max(share, key=share.get)
         ach = kernels[top]["alg_bytes"] / (kernels[top]["ms"] / 1000.0) / 1e9
+        match_ops = 2.0 * r0["kr"] * r0["kl"] * 75
         roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                    "traffic": None, "peak_source": how + " copy bandwidth (MEASURED_PEAKS.json)",
+                    "traffic": traffic.get(top), "peak_source": how + " copy bandwidth (MEASURED_PEAKS.json)",
                     "kernel_ms": kernels[top]["ms"], "note": kernels[top]["note"],
                     "other_kernels": {k: {"ms": v["ms"], "achieved_GBs": v["alg_bytes"] / (v["ms"] / 1e3) / 1e9,
-                                          "frac": v["alg_bytes"] / (v["ms"] / 1e3) / 1e9 / hbm} for k, v in kernels.items()},
+                                          "frac": v["alg_bytes"] / (v["ms"] / 1e3) / 1e9 / hbm,
+                                          "traffic": traffic.get(k)} for k, v in kernels.items()},
+                    "matcher": {"bound": "tensor", "stage_ms": t_match, "pairs": r0["kr"] * r0["kl"],
+                                "achieved_TOPs": match_ops / (t_match / 1e3) / 1e12,
+                                "note": "whole match stage (gather + tcgen05 kind::i8 GEMM with fused arg-min + emit); "
+                                        "K = 75 makes it epilogue/loader bound, see profiles/ for the tensor-pipe share"},
                     "stage_ms_per_pair": stage_ms, "dominant_stage": dom}
         # ---- CPU baseline: serial oracle on one core, bounded sample ---------------------------
         cpu = None
@@ -320,7 +363,7 @@ def run_engine(a):
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_pair": ms_e2e / (a.steps * P)},
-                "wall_ms_per_step": wall_ms / a.steps, "roofline": roofline, "cpu_baseline": cpu}
+                "wall_ms_per_step": wall_ms / a.steps, "collective": "all_gather of %d x 96 B homography records per step (NCCL)" % n_total if world > 1 else "none (single GPU)", "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line, default=float), flush=True)
     eng.close()
     if world > 1:
