@@ -176,6 +176,7 @@ def run_engine(a):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("PANO_NCCL_DEBUG", "WARN")   # stdout must be one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     eng = pkg.Engine(device=local, seed=SEED)

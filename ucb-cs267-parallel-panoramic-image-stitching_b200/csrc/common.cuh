@@ -1,6 +1,7 @@
 // common.cuh — internal declarations shared by the engine's translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -26,7 +27,7 @@ struct CudaError {
   } while (0)
 
 // every engine kernel launch goes through this: counts it and surfaces launch errors
-extern uint64_t g_kernel_launches;
+extern std::atomic<uint64_t> g_kernel_launches;
 #define PANO_LAUNCH_CHECK()            \
   do {                                 \
     ++::pano::g_kernel_launches;       \
@@ -117,7 +118,7 @@ void compact_flagged(cudaStream_t st, const uint8_t* flags, int n, int32_t* out_
                      uint32_t* count_dev, DevBuf& tmp);
 
 struct MatchScratch {
-  DevBuf flags, tmp, best, cnt, mflags, midx, mtmp;
+  DevBuf flags, tmp, best, cnt, mflags, midx, mtmp, tc_err;
 };
 int build_descriptors_device(cudaStream_t st, const DevImage& img, const int32_t* xy, int n, int patch,
                              MatchScratch& s, DevDescriptors& d, PinnedBuf& pin);
@@ -125,7 +126,7 @@ int build_descriptors_device(cudaStream_t st, const DevImage& img, const int32_t
 void match_simt_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
                        unsigned long long* best);
 void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
-                     unsigned long long* best);
+                     unsigned long long* best, DevBuf& errbuf);
 bool match_tc_available();
 // turns best[] into pano_match records (ascending query order), applying maxSSD; returns count
 int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,

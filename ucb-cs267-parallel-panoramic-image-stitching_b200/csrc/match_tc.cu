@@ -285,16 +285,16 @@ match_tc_kernel(const uint8_t* __restrict__ qd, const uint32_t* __restrict__ qn,
   }
 }
 
-int g_tc_state = 0;  // 0 unknown, 1 usable, -1 disabled after a failure
+std::atomic<int> g_tc_state{0};  // 0 unknown, 1 usable, -1 disabled after a failure
 
 }  // namespace
 
 bool match_tc_available() { return g_tc_state >= 0; }
 
-void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t, unsigned long long* best) {
+void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t, unsigned long long* best,
+                     DevBuf& errbuf) {
   PANO_CUDA(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * (size_t)q.count, st));
   if (q.count == 0 || t.count == 0) return;
-  static DevBuf errbuf;
   errbuf.reserve(sizeof(int));
   PANO_CUDA(cudaMemsetAsync(errbuf.p, 0, sizeof(int), st));
   const int n_qtiles = (q.count + TM - 1) / TM;

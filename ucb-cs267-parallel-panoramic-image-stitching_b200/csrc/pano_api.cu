@@ -8,9 +8,10 @@
 #include <algorithm>
 #include <exception>
 #include <new>
+#include <thread>
 
 namespace pano {
-uint64_t g_kernel_launches = 0;
+std::atomic<uint64_t> g_kernel_launches{0};
 }
 
 using namespace pano;
@@ -38,6 +39,7 @@ struct pano_ctx {
   size_t cstride = 0;
   bool has_canvas = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<pano_ctx*> lanes;  // child contexts (own stream + scratch) used by pano_stitch_batch
 };
 
 namespace {
@@ -107,7 +109,7 @@ int check_harris(const pano_harris_opts& o) {
 void run_matcher(pano_ctx* c, const DevDescriptors& q, const DevDescriptors& t) {
   c->best.reserve(sizeof(unsigned long long) * (size_t)std::max(q.count, 1));
   if (c->matcher == 0 && match_tc_available())
-    match_tc_device(c->st, q, t, c->best.as<unsigned long long>());
+    match_tc_device(c->st, q, t, c->best.as<unsigned long long>(), c->ms.tc_err);
   else
     match_simt_device(c->st, q, t, c->best.as<unsigned long long>());
 }
@@ -264,11 +266,13 @@ int pano_create(int device, uint32_t seed, pano_ctx** out) {
 
 void pano_destroy(pano_ctx* c) {
   if (!c) return;
+  for (pano_ctx* l : c->lanes) pano_destroy(l);
+  c->lanes.clear();
   cudaSetDevice(c->device);
   if (c->st) cudaStreamSynchronize(c->st);
   DevBuf* bufs[] = {&c->up[0], &c->up[1], &c->kpup[0], &c->kpup[1], &c->mup, &c->hs.resp, &c->hs.mask, &c->hs.rowcnt,
                     &c->hs.rowoff, &c->hs.total, &c->kpL.xy, &c->kpR.xy, &c->ms.flags, &c->ms.tmp, &c->ms.best,
-                    &c->ms.cnt, &c->ms.mflags, &c->ms.midx, &c->ms.mtmp, &c->dQ.desc, &c->dQ.norm, &c->dQ.orig,
+                    &c->ms.cnt, &c->ms.mflags, &c->ms.midx, &c->ms.mtmp, &c->ms.tc_err, &c->dQ.desc, &c->dQ.norm, &c->dQ.orig,
                     &c->dT.desc, &c->dT.norm, &c->dT.orig, &c->best, &c->matches, &c->rs.pts, &c->rs.thr,
                     &c->rs.cand_off, &c->rs.cand_samp, &c->rs.base, &c->rs.samples, &c->rs.Hs, &c->rs.valid,
                     &c->rs.counts, &c->rs.result, &c->rs.mask, &c->rs.plan, &c->rs.pts_bits, &c->mt.x, &c->mt.state, &c->tmp[0],
@@ -295,7 +299,7 @@ int pano_set_matcher(pano_ctx* c, int which) {
 
 const char* pano_last_error(const pano_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
-uint64_t pano_kernel_launches(const pano_ctx*) { return g_kernel_launches; }
+uint64_t pano_kernel_launches(const pano_ctx*) { return g_kernel_launches.load(); }
 
 int pano_detect(pano_ctx* c, const uint8_t* bgr, int w, int h, size_t stride, int mem, const pano_harris_opts* opts,
                 int32_t* xy_out, int cap, int* count) {
@@ -548,27 +552,68 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
       return fail(c, PANO_ERR_INVALID, "pano_stitch_batch: bad image");
   if (int e = check_harris(*hopts)) return fail(c, e, "pano_stitch_batch: unsupported option");
   if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
+  // Pairs are independent: run them on several lanes (child contexts, each with its own stream,
+  // scratch and host thread) so that one pair's host synchronisations, copies and low-occupancy
+  // kernels overlap with another pair's work.  PANO_BATCH_LANES (default 4, 1 = sequential).
+  int n_lanes = 4;
+  if (const char* e = getenv("PANO_BATCH_LANES")) n_lanes = atoi(e);
+  if (n_lanes < 1) n_lanes = 1;
+  if (n_lanes > 8) n_lanes = 8;
+  if (n_lanes > n) n_lanes = n > 0 ? n : 1;
+  while ((int)c->lanes.size() < n_lanes) {
+    pano_ctx* l = nullptr;
+    int s = pano_create(c->device, c->seed, &l);
+    if (s != PANO_OK) return fail(c, s, "pano_stitch_batch: cannot create a lane context");
+    c->lanes.push_back(l);
+  }
   cudaEvent_t e0, e1;
   PANO_CUDA(cudaEventCreate(&e0));
   PANO_CUDA(cudaEventCreate(&e1));
+  PANO_CUDA(cudaStreamSynchronize(c->st));
   PANO_CUDA(cudaEventRecord(e0, c->st));
-  int rc = PANO_OK;
-  for (int i = 0; i < n; i++) {
-    DevImage L = to_device(c, lefts[i], wl, hl, stride_l, mem, 0);
-    DevImage R = to_device(c, rights[i], wr, hr, stride_r, mem, 1);
-    int s = stitch_pair_device(c, L, R, *hopts, *ropts, &results[i]);
-    if (s == PANO_ERR_CUDA) { rc = s; break; }
-    if (s == PANO_OK && canvases_out && canvases_out[i]) {
-      size_t row = (size_t)c->cw * 3;
-      if (row * (size_t)c->ch > canvas_cap_bytes) {
-        results[i].status = PANO_ERR_CAPACITY;
-      } else {
-        PANO_CUDA(cudaMemcpy2DAsync(canvases_out[i], row, c->canvas[c->cur].p, c->cstride, row, c->ch,
-                                    mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                                    c->st));
+  std::vector<int> lane_rc((size_t)n_lanes, PANO_OK);
+  auto work = [&](int li) {
+    pano_ctx* l = c->lanes[li];
+    l->seed = c->seed;
+    l->matcher = c->matcher;
+    try {
+      PANO_CUDA(cudaSetDevice(l->device));
+      for (int i = li; i < n; i += n_lanes) {
+        DevImage L = to_device(l, lefts[i], wl, hl, stride_l, mem, 0);
+        DevImage R = to_device(l, rights[i], wr, hr, stride_r, mem, 1);
+        int s = stitch_pair_device(l, L, R, *hopts, *ropts, &results[i]);
+        if (s == PANO_ERR_CUDA) { lane_rc[li] = s; c->err = l->err; return; }
+        if (s == PANO_OK && canvases_out && canvases_out[i]) {
+          size_t row = (size_t)l->cw * 3;
+          if (row * (size_t)l->ch > canvas_cap_bytes) {
+            results[i].status = PANO_ERR_CAPACITY;
+          } else {
+            PANO_CUDA(cudaMemcpy2DAsync(canvases_out[i], row, l->canvas[l->cur].p, l->cstride, row, l->ch,
+                                        mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                        l->st));
+          }
+        }
       }
+      PANO_CUDA(cudaStreamSynchronize(l->st));
+    } catch (const CudaError& e) {
+      char buf[512];
+      snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e.e, cudaGetErrorString(e.e), e.file, e.line,
+               e.what);
+      c->err = buf;
+      cudaGetLastError();
+      lane_rc[li] = PANO_ERR_CUDA;
     }
+  };
+  if (n_lanes == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int li = 0; li < n_lanes; li++) th.emplace_back(work, li);
+    for (auto& t : th) t.join();
   }
+  int rc = PANO_OK;
+  for (int s : lane_rc)
+    if (s != PANO_OK) rc = s;
   PANO_CUDA(cudaEventRecord(e1, c->st));
   PANO_CUDA(cudaEventSynchronize(e1));
   float ms = 0;

@@ -319,23 +319,35 @@ PANO_HD void canvas_geometry(int wl, int hl, int wr, int hr, const double* H, Ca
   g->bw0 = bw0;
 }
 
-// One destination pixel of cv::warpPerspective (INTER_LINEAR, BORDER_CONSTANT 0): returns the
-// source coordinate in 1/32-px fixed point exactly as OpenCV's WarpPerspectiveInvoker does:
-// numerators evaluated at the block origin xb (= x - x % bw0) and advanced by x1 = x - xb.
-PANO_HD void warp_coord(const double* M, int x, int y, int bw0, int* Xo, int* Yo) {
-  int xb = (x / bw0) * bw0, x1 = x - xb;
-  double xbd = (double)xb, yd = (double)y, x1d = (double)x1;
-  double X0 = PANO_DADD(PANO_DADD(PANO_DMUL(M[0], xbd), PANO_DMUL(M[1], yd)), M[2]);
-  double Y0 = PANO_DADD(PANO_DADD(PANO_DMUL(M[3], xbd), PANO_DMUL(M[4], yd)), M[5]);
-  double W0 = PANO_DADD(PANO_DADD(PANO_DMUL(M[6], xbd), PANO_DMUL(M[7], yd)), M[8]);
-  double W = PANO_DADD(W0, PANO_DMUL(M[6], x1d));
+// Destination pixel -> source coordinate of cv::warpPerspective (INTER_LINEAR), in 1/32-px fixed
+// point, exactly as OpenCV's WarpPerspectiveInvoker evaluates it: the three numerators are
+// computed once per row at the block origin xb (= x - x % bw0) and advanced by x1 = x - xb.
+struct WarpRow {
+  double X0, Y0, W0;
+};
+PANO_HD WarpRow warp_row_origin(const double* M, int xb, int y) {
+  const double xbd = (double)xb, yd = (double)y;
+  WarpRow r;
+  r.X0 = PANO_DADD(PANO_DADD(PANO_DMUL(M[0], xbd), PANO_DMUL(M[1], yd)), M[2]);
+  r.Y0 = PANO_DADD(PANO_DADD(PANO_DMUL(M[3], xbd), PANO_DMUL(M[4], yd)), M[5]);
+  r.W0 = PANO_DADD(PANO_DADD(PANO_DMUL(M[6], xbd), PANO_DMUL(M[7], yd)), M[8]);
+  return r;
+}
+PANO_HD void warp_coord_from(const double* M, const WarpRow& r, int x1, int* Xo, int* Yo) {
+  const double x1d = (double)x1;
+  double W = PANO_DADD(r.W0, PANO_DMUL(M[6], x1d));
   W = (W != 0.) ? PANO_DDIV(32., W) : 0.;
-  double fX = PANO_DMUL(PANO_DADD(X0, PANO_DMUL(M[0], x1d)), W);
-  double fY = PANO_DMUL(PANO_DADD(Y0, PANO_DMUL(M[3], x1d)), W);
+  double fX = PANO_DMUL(PANO_DADD(r.X0, PANO_DMUL(M[0], x1d)), W);
+  double fY = PANO_DMUL(PANO_DADD(r.Y0, PANO_DMUL(M[3], x1d)), W);
   fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
   fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
   *Xo = PANO_RINT_I(fX);
   *Yo = PANO_RINT_I(fY);
+}
+PANO_HD void warp_coord(const double* M, int x, int y, int bw0, int* Xo, int* Yo) {
+  const int xb = (x / bw0) * bw0;
+  const WarpRow r = warp_row_origin(M, xb, y);
+  warp_coord_from(M, r, x - xb, Xo, Yo);
 }
 
 PANO_HD int sat_short(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
