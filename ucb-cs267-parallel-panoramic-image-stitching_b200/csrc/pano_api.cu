@@ -20,6 +20,7 @@ struct pano_ctx {
   int device = 0;
   uint32_t seed = 0;
   int matcher = 0;  // 0 tensor-core, 1 SIMT
+  double replay_target = 0;  // candidate walks per replay chunk (0 = default)
   cudaStream_t st = nullptr;
   std::string err;
   PinnedBuf pin;
@@ -131,7 +132,8 @@ RansacResult ransac_retry(pano_ctx* c, const int32_t* kp1, const int32_t* kp2, c
   RansacResult r;
   int scale = 1;
   for (;;) {
-    r = ransac_device(c->st, kp1, kp2, m, n, o, c->seed, c->mt, c->rs, c->pin, samples, counts, mask, scale);
+    r = ransac_device(c->st, kp1, kp2, m, n, o, c->seed, c->mt, c->rs, c->pin, samples, counts, mask, scale,
+                      c->replay_target);
     if (r.status >= 0 || scale >= 16) break;
     scale *= 2;  // a speculation window was missed: re-run wider (exactness is never traded)
   }
@@ -576,6 +578,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
     pano_ctx* l = c->lanes[li];
     l->seed = c->seed;
     l->matcher = c->matcher;
+    l->replay_target = n_lanes > 1 ? 16000.0 : 0.0;
     try {
       PANO_CUDA(cudaSetDevice(l->device));
       for (int i = li; i < n; i += n_lanes) {

@@ -121,45 +121,57 @@ struct ReplayCtl {
 constexpr int RW_THREADS = 128;
 constexpr size_t CHAIN_SMEM_MAX = 200 * 1024;  // + 20 KB static: under the 227 KB per-block limit
 
-// Pass 1a: rejection cells of a whole chunk.  One warp = one (32-step block kb, block of 32
-// diagonals) task: lane = step within the block (its (r, T) stays in registers), loop over the
-// 32 diagonals; every load is independent and coalesced, the 32 tests of a diagonal are packed
-// with one ballot, and the 32 words are written as one 128-byte row.
+// Pass 1a: rejection cells of a whole chunk.  One warp = one (iteration g, 32-step block kb)
+// task; it keeps the block's 32 (range, threshold) pairs in registers and sweeps all diagonal
+// blocks of the iteration.  Lane = diagonal: for step k it reads stream word pos + lane + k from
+// a 64-word shared-memory window (conflict free) and shifts the test bit into its own word with
+// an add-with-carry pair: ~lo = x*(-r) - 1 (one IMAD), and T + ~lo carries out of 32 bits exactly
+// when lo32(x*r) < T, so "add.cc; addc w, w, w" is w = 2w + rejected.  Steps are visited from 31
+// down to 0 so that bit k is step k.  3 ALU + 1 LDS instructions per 32 cells; the 32 words of a
+// diagonal block are one 128-byte row.
+__device__ __forceinline__ void cell_step(uint32_t& w, uint32_t x, uint32_t neg_r, uint32_t T) {
+  const uint32_t nlo = x * neg_r + 0xffffffffu;   // ~(x * r)
+  asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, %0;\n\t}" : "+r"(w) : "r"(T), "r"(nlo));
+}
+
 __global__ void __launch_bounds__(256)
 replay_cells_kernel(const uint32_t* __restrict__ X, uint32_t steps, const RT* __restrict__ rt,
-                    const WinEntry* __restrict__ win, const int* __restrict__ diag_block_iter, int n_dblocks,
-                    uint32_t nkb, uint32_t dextra, const ReplayCtl* ctl, uint32_t* __restrict__ bits,
-                    unsigned long long x_limit) {
-  __shared__ uint32_t s_x[8][64];    // the 64 stream words a warp's 32x32 cell tile touches
-  __shared__ uint32_t s_w[8][32];    // its 32 result words
+                    const WinEntry* __restrict__ win, int G, uint32_t nkb, uint32_t dextra, const ReplayCtl* ctl,
+                    uint32_t* __restrict__ bits, unsigned long long x_limit) {
+  __shared__ uint32_t s_x[8][64];  // the 64 stream words a 32-diagonal x 32-step tile touches
+  __shared__ RT s_rt[8][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
-  if (wg >= (long long)n_dblocks * nkb) return;
-  const uint32_t kb = (uint32_t)(wg / n_dblocks);
-  const int db = (int)(wg - (long long)kb * n_dblocks);
-  const int g = diag_block_iter[db];
+  if (wg >= (long long)G * nkb) return;
+  const int g = (int)(wg / nkb);
+  const uint32_t kb = (uint32_t)(wg - (long long)g * nkb);
   const WinEntry we = win[g];
   const uint32_t D = (we.width + dextra + 31u) / 32u * 32u;
-  const uint32_t dloc0 = (uint32_t)db * 32u - we.dfirst;
-  const uint32_t k = kb * 32u + lane;
-  const bool live = k < steps;
-  RT q;
-  q.r = 0; q.T = 0;
-  if (live) q = rt[k];
-  // cell (diagonal dloc0 + dd, step kb*32 + lane) reads stream word pos + dd + lane
-  const unsigned long long pos = ctl->base + (unsigned long long)g * steps + we.lo + dloc0 + (unsigned long long)kb * 32u;
-  const bool in_range = pos + 64ull < x_limit;
-  s_x[wid][lane] = in_range ? X[pos + lane] : 0xffffffffu;
-  s_x[wid][32 + lane] = in_range ? X[pos + 32 + lane] : 0xffffffffu;
-  __syncwarp();
-#pragma unroll
-  for (int dd = 0; dd < 32; dd++) {
-    const bool rej = s_x[wid][dd + lane] * q.r < q.T;  // dead lanes carry (r, T) = (0, 0): never set
-    const uint32_t w = __ballot_sync(0xffffffffu, rej);
-    if (lane == 0) s_w[wid][dd] = w;
+  {
+    const uint32_t k = kb * 32u + lane;   // steps past the end carry (0, 0): lo < 0 never holds
+    RT q;
+    q.r = 0; q.T = 0;
+    if (k < steps) q = rt[k];
+    s_rt[wid][lane] = q;
   }
   __syncwarp();
-  bits[(size_t)we.dfirst * nkb + (size_t)kb * D + dloc0 + lane] = s_w[wid][lane];
+  uint32_t rr[32], tt[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) { rr[i] = 0u - s_rt[wid][i].r; tt[i] = s_rt[wid][i].T; }
+  const unsigned long long pos0 = ctl->base + (unsigned long long)g * steps + we.lo + (unsigned long long)kb * 32u;
+  uint32_t* out = bits + (size_t)we.dfirst * nkb + (size_t)kb * D;
+  for (uint32_t d0 = 0; d0 < D; d0 += 32u) {
+    const unsigned long long pos = pos0 + d0;   // cell (d0 + lane, step i) reads word pos + lane + i
+    const bool in_range = pos + 64ull < x_limit;
+    __syncwarp();
+    s_x[wid][lane] = in_range ? X[pos + lane] : 0xffffffffu;
+    s_x[wid][32 + lane] = in_range ? X[pos + 32 + lane] : 0xffffffffu;
+    __syncwarp();
+    uint32_t w = 0;
+#pragma unroll
+    for (int i = 31; i >= 0; i--) cell_step(w, s_x[wid][lane + i], rr[i], tt[i]);
+    out[d0 + lane] = w;
+  }
 }
 
 // Pass 1b: thread (g, j) scans the cell words of iteration g from candidate start j.
@@ -192,13 +204,31 @@ __global__ void __launch_bounds__(1024)
 replay_chain_kernel(const WinEntry* __restrict__ win, int G, uint32_t steps, const uint32_t* __restrict__ cand_end,
                     const uint32_t* __restrict__ seg_off, int n_cand, int nseg, ReplayCtl* ctl,
                     unsigned long long* __restrict__ seg_tab /* this chunk's slice */) {
-  extern __shared__ uint32_t s_end[];
+  extern __shared__ __align__(16) uint32_t s_end[];
   __shared__ WinEntry s_win[1024];
   __shared__ int s_pick[1024];
   __shared__ unsigned long long s_base;
   const bool in_smem = (size_t)n_cand * sizeof(uint32_t) <= CHAIN_SMEM_MAX;
-  if (in_smem)
-    for (int i = threadIdx.x; i < n_cand; i += blockDim.x) s_end[i] = cand_end[i];
+  if (in_smem) {
+    // 16-byte loads, 4 in flight per thread (cand_end is a cudaMalloc'ed array: 16-byte aligned)
+    const int n4 = n_cand >> 2;
+    const uint4* src4 = reinterpret_cast<const uint4*>(cand_end);
+    uint4* dst4 = reinterpret_cast<uint4*>(s_end);
+    for (int i = threadIdx.x; i < n4; i += 4 * blockDim.x) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = i + u * (int)blockDim.x;
+        v[u] = e < n4 ? src4[e] : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int e = i + u * (int)blockDim.x;
+        if (e < n4) dst4[e] = v[u];
+      }
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n_cand; i += blockDim.x) s_end[i] = cand_end[i];
+  }
   for (int i = threadIdx.x; i < G; i += blockDim.x) s_win[i] = win[i];
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -645,7 +675,7 @@ void mt_ensure(cudaStream_t st, MtStream& mt, uint32_t seed, uint64_t need, uint
 RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_t* kp2_dev,
                            const pano_dmatch* matches_dev, int m, const pano_ransac_opts& o, uint32_t seed,
                            MtStream& mt, RansacScratch& s, PinnedBuf& pin, int32_t* samples_out_host,
-                           int32_t* counts_out_host, uint8_t* mask_out_host, int window_scale) {
+                           int32_t* counts_out_host, uint8_t* mask_out_host, int window_scale, double replay_target) {
   RansacResult res;
   memset(&res, 0, sizeof res);
   res.best_iter = -1;
@@ -660,11 +690,14 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
 
   // ---- per-step Lemire thresholds, rejection statistics, chunk/window plan (host, O(steps)
   //      integer work: launch-parameter planning, like the Gaussian taps) ------------------
-  static const double target_cand = [] {
-    const char* e = getenv("PANO_REPLAY_TARGET");  // candidate walks per chunk (tuning knob)
+  // candidate walks per chunk: larger chunks = fewer sequential phases (better single-pair
+  // latency), smaller chunks = less speculative work (better throughput when pairs overlap)
+  static const double env_target = [] {
+    const char* e = getenv("PANO_REPLAY_TARGET");
     double v = e ? atof(e) : 0.0;
-    return (v >= 64.0 && v <= 51000.0) ? v : 50000.0;
+    return (v >= 64.0 && v <= 51000.0) ? v : 0.0;
   }();
+  const double target_cand = env_target > 0 ? env_target : (replay_target > 0 ? replay_target : 50000.0);
   ReplayPlan plan = plan_replay(n, iters, window_scale, target_cand);
   const std::vector<WinEntry>& win = plan.win;
   const int G = plan.G;
@@ -717,11 +750,10 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
     int Gc = std::min(G, iters - c * G);
     dim3 grid((max_w + RW_THREADS - 1) / RW_THREADS, Gc);
     {
-      // diagonal blocks of iterations >= Gc (short last chunk) are evaluated too; they are cheap
-      long long warps = (long long)n_dblocks * nkb;
+      long long warps = (long long)Gc * nkb;
       replay_cells_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(mt.x.as<uint32_t>(), steps, s.thr.as<RT>(),
-                                                                      s.plan.as<WinEntry>(), dbi, n_dblocks, nkb,
-                                                                      plan.dextra, ctl, bits, mt.len + mt.guard - 64);
+                                                                      s.plan.as<WinEntry>(), Gc, nkb, plan.dextra, ctl,
+                                                                      bits, mt.len + mt.guard - 64);
       PANO_LAUNCH_CHECK();
     }
     replay_walk_bits_kernel<<<grid, RW_THREADS, 0, st>>>(steps, s.plan.as<WinEntry>(), nkb, plan.dextra, ctl, bits,
