@@ -181,6 +181,35 @@ int pano_stitch_fold(pano_ctx* ctx, const uint8_t* const* images, const int* ws,
                      const size_t* strides, int n, int mem, const pano_harris_opts* hopts,
                      const pano_ransac_opts* ropts, pano_pair_result* results);
 
+/* ---- chain mode (multi-image panoramas whose adjacent pairs are independent work items) ----
+ * The reference folds images sequentially and re-detects on the growing panorama, which cannot
+ * be sharded.  Chain mode instead estimates H(i <- i+1) for every adjacent pair
+ * independently (shardable across GPUs), composes them into the frame of image 0 and renders the
+ * canvas, optionally band by band.  For two images it reproduces pano_stitch_pair. */
+
+/* Steps 1-3 of stitchTwoImages only (detect both, match, RANSAC): the homography right -> left.
+ * ref: src/serial/main.cpp:316-332.  No canvas is produced. */
+int pano_pair_homography(pano_ctx* ctx, const uint8_t* left, int wl, int hl, size_t stride_l,
+                         const uint8_t* right, int wr, int hr, size_t stride_r, int mem,
+                         const pano_harris_opts* hopts, const pano_ransac_opts* ropts,
+                         pano_pair_result* res);
+
+/* out = A * B with OpenCV's small-matrix gemm operation order (what `translation * H` does at
+ * ref: src/serial/main.cpp:372); used to compose chain homographies reproducibly. */
+void pano_mul33(const double A[9], const double B[9], double out[9]);
+
+/* Canvas of n images given H[i] (image i -> image 0 frame, H[0] = identity): bounds over image
+ * 0 and all transformed corners exactly as ref :335-369 does for two images.  out->TH receives
+ * the translation T (to be multiplied with each H[i] by pano_mul33). */
+int pano_chain_geometry(int n, const int* ws, const int* hs, const double* Hs, pano_canvas_info* out);
+
+/* Warps src by M (cv::warpPerspective, INTER_LINEAR, BORDER_CONSTANT 0) into rows
+ * [y0, y0 + band_h) of a canvas of width canvas_w and overlays it with the reference's rule
+ * (non-black warped pixels overwrite, ref :380-386) on what `band` already holds. */
+int pano_warp_accumulate(pano_ctx* ctx, const uint8_t* src, int w, int h, size_t stride, int mem,
+                         const double M[9], uint8_t* band, int canvas_w, int canvas_h, int y0,
+                         int band_h, size_t band_stride);
+
 /* Throughput mode: n independent pairs (BASELINE config "batch of 4K pairs"), each exactly
  * pano_stitch_pair.  lefts/rights/canvases_out are arrays of n pointers in `mem`; all pairs
  * share the given image geometry.  canvases_out may be NULL (canvases are then produced and

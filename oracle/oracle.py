@@ -221,5 +221,52 @@ class Oracle:
                 pano = r["canvas"]
         return pano, log
 
+    # ---- chain mode (the engine's shardable multi-image mode) ---------------
+    def mul33(self, A, B):
+        A = np.ascontiguousarray(A, np.float64); B = np.ascontiguousarray(B, np.float64)
+        out = np.empty((3, 3), np.float64)
+        self.lib.orc_mul33(_p(A, C.c_double), _p(B, C.c_double), _p(out, C.c_double))
+        return out
+
+    def pair_homography(self, left, right, seed=12345):
+        """steps 1-3 of stitchTwoImages (ref: src/serial/main.cpp:316-332): H right -> left or None"""
+        kl, kr = self.detect(left), self.detect(right)
+        m = self.match(kr, kl, right, left)
+        if len(m) == 0:
+            return None
+        r = self.ransac(kr, kl, m, seed=seed)
+        return r["H"] if r["ok"] else None
+
+    def chain_geometry(self, sizes, Hs):
+        f = np.float32
+        minX, minY, maxX, maxY = f(0), f(0), f(sizes[0][0]), f(sizes[0][1])
+        for (w, h), H in list(zip(sizes, Hs))[1:]:
+            pts = self.perspective_transform(np.float32([[0, 0], [w, 0], [w, h], [0, h]]), H)
+            for x, y in pts:
+                minX, minY, maxX, maxY = min(minX, f(x)), min(minY, f(y)), max(maxX, f(x)), max(maxY, f(y))
+        T = np.array([[1, 0, float(-minX)], [0, 1, float(-minY)], [0, 0, 1.0]])
+        cw, ch = int(np.ceil(f(maxX - minX))), int(np.ceil(f(maxY - minY)))
+        return (cw, ch, int(-minX), int(-minY)), T
+
+    def stitch_chain(self, images, seed=12345):
+        """H(i <- i+1) per adjacent pair, composed into image 0's frame, image 0 placed at its integer
+        offset, every other image warped by T*H and overlaid with the non-black rule."""
+        images = [self._img(i) for i in images]
+        pair_H = [self.pair_homography(images[i], images[i + 1], seed) for i in range(len(images) - 1)]
+        Hs = [np.eye(3)]
+        for H in pair_H:
+            if H is None:
+                break
+            Hs.append(self.mul33(Hs[-1], H))
+        sizes = [(im.shape[1], im.shape[0]) for im in images]
+        (cw, ch, x0, y0), T = self.chain_geometry(sizes, Hs)
+        canvas = np.zeros((ch, cw, 3), np.uint8)
+        canvas[y0:y0 + images[0].shape[0], x0:x0 + images[0].shape[1]] = images[0]
+        for im, H in list(zip(images, Hs))[1:]:
+            w = self.warp_perspective(im, self.mul33(T, H), (cw, ch))
+            nz = w.any(axis=2)
+            canvas[nz] = w[nz]
+        return canvas, pair_H
+
     def num_threads(self):
         return self.lib.orc_num_threads()

@@ -685,6 +685,7 @@ void orc_perspective_transform(const float* pts, int n, const double* H, float* 
 }
 
 int orc_invert33(const double* s, double* d) { return invert33(s, d); }
+void orc_mul33(const double* a, const double* b, double* d) { mul33(a, b, d); }
 
 // out: cw, ch, offx, offy; TH[9]
 int orc_canvas_geometry(int wl, int hl, int wr, int hr, const double* H, int* geom, double* TH) {

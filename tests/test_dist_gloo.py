@@ -57,3 +57,72 @@ def test_two_ranks_gather_all_homographies(tmp_path, n_pairs):
         o = O.stitch_pair(l, r, seed=12345)
         if o["status"] == 1:
             assert np.array_equal(a[p, :9].view(np.uint64), o["H"].reshape(9).view(np.uint64))
+
+
+# ---------------- distributed chain mode on CPU: oracle-backed stand-in for the engine ------------
+class _OracleEngine:
+    """implements the Engine methods stitch_chain_distributed uses, on the CPU oracle (this test is
+    about pair sharding, the record all-gather, identical geometry on all ranks and band tiling)"""
+
+    def __init__(self):
+        from oracle.oracle import Oracle
+        self.O = Oracle()
+
+    def pairHomography(self, left, right):
+        H = self.O.pair_homography(left, right, seed=12345)
+        return {"H": H if H is not None else np.zeros((3, 3)), "status": 0 if H is not None else 5, "best": 0}
+
+    def composeChain(self, pair_H):
+        Hs = [np.eye(3)]
+        for H in pair_H:
+            if H is None:
+                break
+            Hs.append(self.O.mul33(Hs[-1], H))
+        return Hs
+
+    def chainGeometry(self, sizes, Hs):
+        geom, T = self.O.chain_geometry(sizes, Hs)
+        return True, geom, T
+
+    def renderChainBand(self, images, Hs, geom, T, y0, bh):
+        cw, ch, x0, yy0 = geom
+        canvas = np.zeros((ch, cw, 3), np.uint8)
+        canvas[yy0:yy0 + images[0].shape[0], x0:x0 + images[0].shape[1]] = images[0]
+        for im, H in list(zip(images, Hs))[1:]:
+            w = self.O.warp_perspective(im, self.O.mul33(T, H), (cw, ch))
+            nz = w.any(axis=2)
+            canvas[nz] = w[nz]
+        return canvas[y0:y0 + bh]
+
+
+def _chain_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module(PKG + ".dist")
+    synth = importlib.import_module(PKG + ".synth")
+    views = synth.make_strip(n=4, w=320, h=200, seed=21)
+    pano, allr = d.stitch_chain_distributed(_OracleEngine(), views)
+    np.save(os.path.join(out_dir, "pano%d.npy" % rank), pano)
+    dist.destroy_process_group()
+
+
+def test_band_rows_cover_canvas():
+    d = importlib.import_module(PKG + ".dist")
+    for ch, w in ((401, 2), (7, 8), (1000, 3)):
+        rows = [d.band_rows(ch, r, w) for r in range(w)]
+        assert rows[0][0] == 0 and sum(h for _, h in rows) == ch
+        assert all(rows[i][0] + rows[i][1] == rows[i + 1][0] for i in range(w - 1))
+
+
+def test_distributed_chain_two_ranks(tmp_path):
+    port = 31000 + os.getpid() % 2000
+    mp.spawn(_chain_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "pano0.npy"), np.load(tmp_path / "pano1.npy")
+    assert np.array_equal(a, b)
+    from oracle.oracle import Oracle
+    synth = importlib.import_module(PKG + ".synth")
+    ref, _ = Oracle().stitch_chain(synth.make_strip(n=4, w=320, h=200, seed=21), seed=12345)
+    assert a.shape == ref.shape and np.array_equal(a, ref)

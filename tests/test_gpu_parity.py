@@ -256,3 +256,32 @@ def test_full_size_pair_properties(engine, oracle):
     c = oracle.ransac(kr, kl, m, seed=12345)
     assert np.array_equal(bits(r["H"]), bits(c["H"])) and r["best"] == c["best_count"]
     assert np.array_equal(canvas, oracle.compose(left, right, c["H"]))
+
+
+# ---------------- chain mode ---------------------------------------------------
+def test_chain_of_two_equals_pair(engine, oracle, small_pair):
+    left, right, _ = small_pair
+    pano, res = engine.stitchChain([left, right])
+    canvas, r = engine.stitchTwoImages(left, right)
+    assert res[0]["status"] == 0 and np.array_equal(bits(res[0]["H"]), bits(r["H"]))
+    assert np.array_equal(pano, canvas)
+
+
+def test_chain_strip_matches_oracle_and_bands_tile(engine, oracle):
+    views = load_synth().make_strip(n=4, w=640, h=400, seed=9)
+    pano, res = engine.stitchChain(views)
+    opano, oH = oracle.stitch_chain(views, seed=12345)
+    assert [r["status"] == 0 for r in res] == [h is not None for h in oH]
+    for r, h in zip(res, oH):
+        if h is not None:
+            assert np.array_equal(bits(r["H"]), bits(h))
+    assert pano.shape == opano.shape and np.array_equal(pano, opano)
+    # canvas rows rendered band by band (what each GPU does in the distributed mode) tile exactly
+    Hs = engine.composeChain([r["H"] if r["status"] == 0 else None for r in res])
+    ok, geom, T = engine.chainGeometry([(v.shape[1], v.shape[0]) for v in views], Hs)
+    assert ok and (geom[0], geom[1]) == (pano.shape[1], pano.shape[0])
+    bands, y = [], 0
+    for bh in (7, 100, 1, geom[1] - 108):
+        bands.append(engine.renderChainBand(views, Hs, geom, T, y, bh))
+        y += bh
+    assert np.array_equal(np.concatenate(bands, axis=0), pano)

@@ -40,7 +40,8 @@ EXPORTED_SYMBOLS = [
     "pano_last_error", "pano_version", "pano_kernel_launches", "pano_set_matcher", "pano_detect",
     "pano_harris_response", "pano_convolve_f64", "pano_match", "pano_ransac", "pano_canvas_geometry",
     "pano_warp_overlay", "pano_warp_perspective", "pano_stitch_pair", "pano_get_canvas", "pano_canvas_device",
-    "pano_stitch_fold", "pano_stitch_batch", "pano_stream",
+    "pano_stitch_fold", "pano_stitch_batch", "pano_stream", "pano_pair_homography", "pano_mul33",
+    "pano_chain_geometry", "pano_warp_accumulate",
 ]
 
 
@@ -357,6 +358,69 @@ class Engine:
                                                C.c_size_t(R0.stride), L0.mem, C.byref(ho), C.byref(ro), results,
                                                cp, C.c_size_t(cap), C.byref(ms)))
         return [results[i].as_dict() for i in range(n)], ms.value
+
+    # ---- chain mode --------------------------------------------------
+    def pairHomography(self, leftImage, rightImage, harrisOpts=None, ransacOpts=None):
+        """detect + match + RANSAC only: result dict with 'H' (right -> left) and 'status'"""
+        ho, ro = harrisOpts or HarrisCornerOptions(), ransacOpts or RansacOptions()
+        L, R = _Img(leftImage), _Img(rightImage)
+        assert L.mem == R.mem
+        res = PairResult()
+        st = self.lib.pano_pair_homography(self.ctx, L.ptr, L.w, L.h, C.c_size_t(L.stride), R.ptr, R.w, R.h,
+                                           C.c_size_t(R.stride), L.mem, C.byref(ho), C.byref(ro), C.byref(res))
+        self._check(st, allow=(PANO_ERR_NO_MATCHES, PANO_ERR_TOO_FEW_MATCHES, PANO_ERR_NO_HOMOGRAPHY))
+        return res.as_dict()
+
+    def mul33(self, A, B):
+        A = np.ascontiguousarray(A, np.float64); B = np.ascontiguousarray(B, np.float64)
+        out = np.empty((3, 3), np.float64)
+        self.lib.pano_mul33(A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def composeChain(self, pair_H):
+        """pair_H[i] = H(image i <- image i+1) or None for a failed pair.  Returns the list of
+        H(image 0 <- image i) for the longest prefix of the chain that is connected."""
+        Hs = [np.eye(3)]
+        for H in pair_H:
+            if H is None:
+                break
+            Hs.append(self.mul33(Hs[-1], H))
+        return Hs
+
+    def chainGeometry(self, sizes, Hs):
+        """sizes: [(w, h)], Hs: H(0 <- i).  Returns ok, (cw, ch, x0, y0), T"""
+        n = len(Hs)
+        ws = (C.c_int * n)(*[s[0] for s in sizes[:n]]); hs = (C.c_int * n)(*[s[1] for s in sizes[:n]])
+        flat = np.ascontiguousarray(np.stack(Hs), np.float64)
+        info = CanvasInfo()
+        st = self.lib.pano_chain_geometry(n, ws, hs, flat.ctypes.data_as(C.c_void_p), C.byref(info))
+        return st == PANO_OK, (info.canvas_w, info.canvas_h, info.left_x, info.left_y), \
+            np.array(info.TH[:], np.float64).reshape(3, 3)
+
+    def renderChainBand(self, images, Hs, geom, T, y0, band_h):
+        """rows [y0, y0 + band_h) of the chain canvas: image 0 placed at its integer offset, then
+        every image i >= 1 warped by T * H(0 <- i), non-black pixels overwriting (host arrays)."""
+        cw, ch, x0, yy0 = geom
+        band = np.zeros((band_h, cw, 3), np.uint8)
+        for i, H in enumerate(Hs):
+            M = np.array([[1, 0, x0], [0, 1, yy0], [0, 0, 1.0]]) if i == 0 else self.mul33(T, H)
+            im = _Img(images[i])
+            assert im.mem == MEM_HOST
+            M = np.ascontiguousarray(M, np.float64)
+            self._check(self.lib.pano_warp_accumulate(self.ctx, im.ptr, im.w, im.h, C.c_size_t(im.stride), MEM_HOST,
+                                                      M.ctypes.data_as(C.c_void_p), band.ctypes.data_as(C.c_void_p),
+                                                      cw, ch, int(y0), int(band_h), C.c_size_t(band.strides[0])))
+        return band
+
+    def stitchChain(self, images, harrisOpts=None, ransacOpts=None):
+        """single-GPU chain mode: returns (panorama or None, [pair result dicts])"""
+        res = [self.pairHomography(images[i], images[i + 1], harrisOpts, ransacOpts) for i in range(len(images) - 1)]
+        Hs = self.composeChain([r["H"] if r["status"] == 0 else None for r in res])
+        sizes = [(np.asarray(im).shape[1], np.asarray(im).shape[0]) for im in images]
+        ok, geom, T = self.chainGeometry(sizes, Hs)
+        if not ok:
+            return None, res
+        return self.renderChainBand(images, Hs, geom, T, 0, geom[1]), res
 
     def stream_ptr(self):
         self.lib.pano_stream.restype = C.c_void_p

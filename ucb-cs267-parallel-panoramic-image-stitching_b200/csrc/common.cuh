@@ -158,6 +158,8 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
 
 void warp_overlay_device(cudaStream_t st, const DevImage& left, const DevImage& right,
                          const CanvasGeom& g, uint8_t* canvas, size_t canvas_stride);
+void warp_accumulate_device(cudaStream_t st, const DevImage& src, const double* M, uint8_t* band, int canvas_w,
+                            int canvas_h, int y0, int band_h, size_t band_stride);
 void warp_only_device(cudaStream_t st, const DevImage& src, const double* Minv, int bw0, uint8_t* dst,
                       int dw, int dh, size_t dstride);
 

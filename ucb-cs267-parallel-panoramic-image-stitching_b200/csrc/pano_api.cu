@@ -155,7 +155,7 @@ void fill_canvas_info(const CanvasGeom& g, pano_canvas_info* info) {
 // ref: src/serial/main.cpp:311-391.  left/right are device views.  On success the new
 // canvas is in c->canvas[c->cur].
 int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const pano_harris_opts& ho,
-                       const pano_ransac_opts& ro, pano_pair_result* res) {
+                       const pano_ransac_opts& ro, pano_pair_result* res, bool homography_only = false) {
   memset(res, 0, sizeof *res);
   res->best_iteration = -1;
   cudaStream_t st = c->st;
@@ -195,6 +195,11 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
   CanvasGeom g;
   canvas_geometry(L.w, L.h, R.w, R.h, rr.H, &g);
   fill_canvas_info(g, &res->canvas);
+  if (homography_only) {  // chain mode: the canvas is composed later from all homographies
+    finish(PANO_OK);
+    cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
+    return PANO_OK;
+  }
   if (!g.ok) {
     int s = finish(PANO_ERR_ROI);
     cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
@@ -541,6 +546,72 @@ int pano_stitch_fold(pano_ctx* c, const uint8_t* const* images, const int* ws, c
 }
 
 void* pano_stream(pano_ctx* c) { return c ? (void*)c->st : nullptr; }
+
+int pano_pair_homography(pano_ctx* c, const uint8_t* left, int wl, int hl, size_t stride_l, const uint8_t* right,
+                         int wr, int hr, size_t stride_r, int mem, const pano_harris_opts* hopts,
+                         const pano_ransac_opts* ropts, pano_pair_result* res) {
+  API_TRY(c)
+  if (!valid_image(left, wl, hl, stride_l) || !valid_image(right, wr, hr, stride_r) || !hopts || !ropts || !res)
+    return fail(c, PANO_ERR_INVALID, "pano_pair_homography: bad argument");
+  if (int e = check_harris(*hopts)) return fail(c, e, "pano_pair_homography: unsupported option");
+  if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
+  DevImage L = to_device(c, left, wl, hl, stride_l, mem, 0);
+  DevImage R = to_device(c, right, wr, hr, stride_r, mem, 1);
+  return stitch_pair_device(c, L, R, *hopts, *ropts, res, true);
+  API_CATCH(c)
+}
+
+void pano_mul33(const double A[9], const double B[9], double out[9]) { mul33(A, B, out); }
+
+int pano_chain_geometry(int n, const int* ws, const int* hs, const double* Hs, pano_canvas_info* out) {
+  if (n < 1 || !ws || !hs || !Hs || !out) return PANO_ERR_INVALID;
+  // ref: src/serial/main.cpp:351-369 with every image i >= 1 in the role of "right"
+  float minX = 0, minY = 0, maxX = (float)ws[0], maxY = (float)hs[0];
+  for (int i = 1; i < n; i++) {
+    const float cx[4] = {0.f, (float)ws[i], (float)ws[i], 0.f};
+    const float cy[4] = {0.f, 0.f, (float)hs[i], (float)hs[i]};
+    for (int k = 0; k < 4; k++) {
+      float px, py;
+      persp_point(Hs + 9 * (size_t)i, cx[k], cy[k], &px, &py);
+      minX = fminf(minX, px); minY = fminf(minY, py);
+      maxX = fmaxf(maxX, px); maxY = fmaxf(maxY, py);
+    }
+  }
+  const double T[9] = {1, 0, (double)(-minX), 0, 1, (double)(-minY), 0, 0, 1};
+  memcpy(out->TH, T, sizeof T);
+  const float fw = maxX - minX, fh = maxY - minY;
+  out->canvas_w = (int)ceilf(fw);
+  out->canvas_h = (int)ceilf(fh);
+  out->left_x = (int)(-minX);
+  out->left_y = (int)(-minY);
+  if (!(fw == fw) || !(fh == fh) || out->canvas_w <= 0 || out->canvas_h <= 0) return PANO_ERR_ROI;
+  if (out->left_x < 0 || out->left_y < 0 || out->left_x + ws[0] > out->canvas_w || out->left_y + hs[0] > out->canvas_h)
+    return PANO_ERR_ROI;
+  return PANO_OK;
+}
+
+int pano_warp_accumulate(pano_ctx* c, const uint8_t* src, int w, int h, size_t stride, int mem, const double M[9],
+                         uint8_t* band, int canvas_w, int canvas_h, int y0, int band_h, size_t band_stride) {
+  API_TRY(c)
+  if (!valid_image(src, w, h, stride) || !M || !band || canvas_w <= 0 || canvas_h <= 0 || y0 < 0 || band_h <= 0 ||
+      y0 + band_h > canvas_h || band_stride < (size_t)canvas_w * 3)
+    return fail(c, PANO_ERR_INVALID, "pano_warp_accumulate: bad argument");
+  DevImage S = to_device(c, src, w, h, stride, mem, 0);
+  if (mem == PANO_MEM_DEVICE) {
+    warp_accumulate_device(c->st, S, M, band, canvas_w, canvas_h, y0, band_h, band_stride);
+  } else {
+    size_t pitch = align_up((size_t)canvas_w * 3, 256);
+    c->tmp[0].reserve(pitch * (size_t)band_h);
+    PANO_CUDA(cudaMemcpy2DAsync(c->tmp[0].p, pitch, band, band_stride, (size_t)canvas_w * 3, band_h,
+                                cudaMemcpyHostToDevice, c->st));
+    warp_accumulate_device(c->st, S, M, c->tmp[0].as<uint8_t>(), canvas_w, canvas_h, y0, band_h, pitch);
+    PANO_CUDA(cudaMemcpy2DAsync(band, band_stride, c->tmp[0].p, pitch, (size_t)canvas_w * 3, band_h,
+                                cudaMemcpyDeviceToHost, c->st));
+  }
+  PANO_CUDA(cudaStreamSynchronize(c->st));
+  return PANO_OK;
+  API_CATCH(c)
+}
 
 int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uint8_t* const* rights, int wl, int hl,
                       size_t stride_l, int wr, int hr, size_t stride_r, int mem, const pano_harris_opts* hopts,

@@ -23,6 +23,7 @@ struct WarpParams {
   int ws, hs;              // source (right) size
   int bx0, by0, bx1, by1;  // canvas pixels outside this box provably map outside the source
   size_t src_bytes;        // bytes of the source buffer that may be read with word loads
+  int y0;                  // first canvas row of the band being rendered (0 for a whole canvas)
 };
 
 // 6 consecutive bytes starting at p (two adjacent BGR pixels) from aligned 32-bit loads
@@ -64,14 +65,16 @@ __device__ __forceinline__ uint32_t warp_pixel_fast(const uint8_t* __restrict__ 
 }
 
 // Each thread produces 4 horizontally adjacent canvas pixels (12 bytes = three 32-bit stores;
-// the canvas pitch is a multiple of 4).  OVERLAY = false: plain warpPerspective.
-template <bool OVERLAY>
+// the canvas pitch is a multiple of 4).  MODE 0: plain warpPerspective; 1: + left copy (pair);
+// 2: accumulate — non-black warped pixels overwrite what the canvas band already holds.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 warp_overlay_kernel(const uint8_t* __restrict__ left, size_t lstride, const uint8_t* __restrict__ right,
                     size_t rstride, WarpParams P, uint8_t* __restrict__ canvas, size_t cstride) {
   const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x0 >= P.cw || y >= P.ch) return;
+  const int yb = blockIdx.y * blockDim.y + threadIdx.y;   // row inside the band
+  const int y = yb + P.y0;                                // row of the whole canvas
+  if (x0 >= P.cw || yb >= P.ch) return;
   uint32_t px[4] = {0u, 0u, 0u, 0u};
   if (!(x0 + 3 < P.bx0 || x0 > P.bx1 || y < P.by0 || y > P.by1)) {
     // the four pixels share OpenCV's row-origin numerators when they lie in one bw0-block
@@ -89,7 +92,7 @@ warp_overlay_kernel(const uint8_t* __restrict__ left, size_t lstride, const uint
       }
     }
   }
-  if (OVERLAY) {
+  if (MODE == 1) {
     const int ly = y - P.offy;
     if (ly >= 0 && ly < P.hl) {
 #pragma unroll
@@ -102,7 +105,18 @@ warp_overlay_kernel(const uint8_t* __restrict__ left, size_t lstride, const uint
       }
     }
   }
-  uint8_t* row = canvas + (size_t)y * cstride + 3 * (size_t)x0;
+  uint8_t* row = canvas + (size_t)yb * cstride + 3 * (size_t)x0;
+  if (MODE == 2) {
+    if ((px[0] | px[1] | px[2] | px[3]) == 0u) return;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (px[i] != 0u && x0 + i < P.cw) {
+        row[3 * i] = (uint8_t)px[i];
+        row[3 * i + 1] = (uint8_t)(px[i] >> 8);
+        row[3 * i + 2] = (uint8_t)(px[i] >> 16);
+      }
+    return;
+  }
   if (x0 + 3 < P.cw && (reinterpret_cast<uintptr_t>(row) & 3) == 0) {
     uint32_t* o = reinterpret_cast<uint32_t*>(row);  // 3*x0 is a multiple of 12
     o[0] = px[0] | (px[1] << 24);
@@ -157,10 +171,11 @@ void warp_overlay_device(cudaStream_t st, const DevImage& left, const DevImage& 
   P.cw = g.cw; P.ch = g.ch;
   P.offx = g.offx; P.offy = g.offy; P.wl = left.w; P.hl = left.h;
   P.ws = right.w; P.hs = right.h;
+  P.y0 = 0;
   P.src_bytes = (size_t)(right.h - 1) * right.stride + (size_t)right.w * 3;
   footprint_box(g.TH, g.Minv, right.w, right.h, g.cw, g.ch, P);
   dim3 block(32, 8), grid(((g.cw + 3) / 4 + 31) / 32, (g.ch + 7) / 8);
-  warp_overlay_kernel<true><<<grid, block, 0, st>>>(left.p, left.stride, right.p, right.stride, P, canvas,
+  warp_overlay_kernel<1><<<grid, block, 0, st>>>(left.p, left.stride, right.p, right.stride, P, canvas,
                                                    canvas_stride);
   PANO_LAUNCH_CHECK();
 }
@@ -173,6 +188,7 @@ void warp_only_device(cudaStream_t st, const DevImage& src, const double* Minv, 
   P.cw = dw; P.ch = dh;
   P.offx = P.offy = 0; P.wl = P.hl = 0;
   P.ws = src.w; P.hs = src.h;
+  P.y0 = 0;
   P.src_bytes = (size_t)(src.h - 1) * src.stride + (size_t)src.w * 3;
   {
     double fwd[9];
@@ -180,7 +196,28 @@ void warp_only_device(cudaStream_t st, const DevImage& src, const double* Minv, 
     else { P.bx0 = 0; P.by0 = 0; P.bx1 = dw - 1; P.by1 = dh - 1; }
   }
   dim3 block(32, 8), grid(((dw + 3) / 4 + 31) / 32, (dh + 7) / 8);
-  warp_overlay_kernel<false><<<grid, block, 0, st>>>(nullptr, 0, src.p, src.stride, P, dst, dstride);
+  warp_overlay_kernel<0><<<grid, block, 0, st>>>(nullptr, 0, src.p, src.stride, P, dst, dstride);
+  PANO_LAUNCH_CHECK();
+}
+
+void warp_accumulate_device(cudaStream_t st, const DevImage& src, const double* M, uint8_t* band, int canvas_w,
+                            int canvas_h, int y0, int band_h, size_t band_stride) {
+  WarpParams P;
+  double Minv[9];
+  invert33(M, Minv);
+  memcpy(P.M, Minv, sizeof P.M);
+  int bh0 = canvas_h < 16 ? canvas_h : 16;          // OpenCV's block shape depends on the WHOLE canvas
+  int bw0 = 1024 / (bh0 < 1 ? 1 : bh0);
+  if (bw0 > canvas_w) bw0 = canvas_w;
+  P.bw0 = bw0 < 1 ? 1 : bw0;
+  P.cw = canvas_w; P.ch = band_h;
+  P.offx = P.offy = 0; P.wl = P.hl = 0;
+  P.ws = src.w; P.hs = src.h;
+  P.y0 = y0;
+  P.src_bytes = (size_t)(src.h - 1) * src.stride + (size_t)src.w * 3;
+  footprint_box(M, Minv, src.w, src.h, canvas_w, canvas_h, P);   // box in whole-canvas coordinates
+  dim3 block(32, 8), grid(((canvas_w + 3) / 4 + 31) / 32, (band_h + 7) / 8);
+  warp_overlay_kernel<2><<<grid, block, 0, st>>>(nullptr, 0, src.p, src.stride, P, band, band_stride);
   PANO_LAUNCH_CHECK();
 }
 

@@ -48,3 +48,47 @@ def all_gather_results(local, n_pairs, device=None, group=None):
         out[int(row[11])] = row
     assert (out[:, 11] >= 0).all(), "a pair was not reported by any rank"
     return out
+
+
+def band_rows(canvas_h, rank, world):
+    """rows of the canvas rendered by `rank`: contiguous bands, remainder to the first ranks"""
+    base, rem = divmod(canvas_h, world)
+    y0 = rank * base + min(rank, rem)
+    return y0, base + (1 if rank < rem else 0)
+
+
+def stitch_chain_distributed(engine, images, device=None, group=None):
+    """Chain-mode panorama over all ranks of the process group (SURVEY 8e2 + 8e3): adjacent pair
+    (i, i+1) is estimated on rank i mod W, the 96-byte records are all-gathered, every rank composes
+    the same H(0 <- i) and canvas geometry, renders its own band of canvas rows, and the bands are
+    gathered.  Every rank holds all input images (they come from the host).  Returns the panorama
+    (on every rank) or None, plus the gathered per-pair records."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n_pairs = len(images) - 1
+    mine = shard_pairs(n_pairs, rank, world)
+    res = [engine.pairHomography(images[i], images[i + 1]) for i in mine]
+    allr = all_gather_results(pack_results(mine, res), n_pairs, device=device, group=group)
+    pair_H = [allr[i, :9].reshape(3, 3).copy() if int(allr[i, 9]) == 0 else None for i in range(n_pairs)]
+    Hs = engine.composeChain(pair_H)
+    sizes = [(np.asarray(im).shape[1], np.asarray(im).shape[0]) for im in images]
+    ok, geom, T = engine.chainGeometry(sizes, Hs)
+    if not ok:
+        return None, allr
+    cw, ch = geom[0], geom[1]
+    y0, bh = band_rows(ch, rank, world)
+    band = engine.renderChainBand(images, Hs, geom, T, y0, bh) if bh > 0 else np.zeros((0, cw, 3), np.uint8)
+    # gather the bands (padded to the tallest band)
+    maxh = (ch + world - 1) // world
+    buf = torch.zeros((maxh, cw, 3), dtype=torch.uint8)
+    buf[:bh] = torch.from_numpy(band)
+    if device is not None:
+        buf = buf.to(device)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    rows = []
+    for r in range(world):
+        _, h_r = band_rows(ch, r, world)
+        rows.append(parts[r][:h_r].cpu().numpy())
+    return np.concatenate(rows, axis=0), allr

@@ -90,8 +90,12 @@ def make_pair(w=3840, h=2160, seed=267, overlap=0.5, rot_deg=0.3, persp=1e-6, no
     return left, np.ascontiguousarray(right), H_true / H_true[2, 2]
 
 
-def make_strip(n=8, w=2000, h=1500, seed=267, stride_frac=0.75, rot_deg=0.2, noise=2):
-    """n overlapping views cut left-to-right from one world (config: 8-image strip panorama)."""
+def make_strip(n=8, w=2000, h=1500, seed=267, stride_frac=0.6, rot_deg=0.2, noise=2):
+    """n overlapping views cut left-to-right from one world (config: 8-image strip panorama).
+    Adjacent views overlap by 1 - stride_frac = 40 %: with the 25 % overlap SURVEY 8d suggests, the
+    reference algorithm itself (1-NN raw-patch SSD, no ratio test, 1000 RANSAC iterations) finds
+    only ~0.7 % inliers and returns a garbage homography (checked with the oracle), so the
+    configuration is kept inside the range where the reference works."""
     stride = int(w * stride_frac)
     margin = max(16, h // 15)
     world = make_world(h + 2 * margin, stride * (n - 1) + w + 2 * margin, seed)
