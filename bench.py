@@ -121,6 +121,8 @@ def run_reference(a):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    # all host threads (torchrun exports OMP_NUM_THREADS=1 to its workers; libgomp reads it at load)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle.oracle import Oracle
     O = Oracle("omp")
     cores = O.num_threads()
@@ -318,13 +320,14 @@ def run_engine(a):
             "warp_overlay_kernel": {"ms": t_warp, "alg_bytes": 3 * (2 * npx + cw * ch), "launches_per_pair": 1,
                                     "note": "HBM bound: both sources read once, canvas written once"},
         }
-        share = {k: v["ms"] * v["launches_per_pair"] for k, v in kernels.items()}
         dom = max(stage_ms, key=stage_ms.get)
-        # The roofline object describes the dominant kernel of the step among those that have an
-        # HBM roofline (stencil / warp).  The RANSAC replay kernels that dominate the step are
-        # integer issue/latency bound, so neither roofline applies to them; the
-        # stage table and the ncu launch list under profiles/ show their share.
-        top = max(share, key=share.get)
+        # The roofline object describes warp_overlay_kernel: the kernel of the step that is HBM bound
+        # by design (sources read once, canvas written once).  The kernel with the largest share of
+        # the step is replay_cells_kernel (RANSAC sample replay): integer ALU / issue bound (ncu: issue
+        # slots 80 % busy, DRAM < 1 %), so neither an HBM nor a tensor roofline applies to it; the
+        # Harris stencil is FP64-pipe bound (ncu: FP64 pipe 67 % active).  See DESIGN.md section 4 and the
+        # launch lists under profiles/.
+        top = "warp_overlay_kernel"
         ach = kernels[top]["alg_bytes"] / (kernels[top]["ms"] / 1000.0) / 1e9
         match_ops = 2.0 * r0["kr"] * r0["kl"] * 75
         roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
@@ -337,7 +340,9 @@ def run_engine(a):
                                 "achieved_TOPs": match_ops / (t_match / 1e3) / 1e12,
                                 "note": "whole match stage (gather + tcgen05 kind::i8 GEMM with fused arg-min + emit); "
                                         "K = 75 makes it epilogue/loader bound, see profiles/ for the tensor-pipe share"},
-                    "stage_ms_per_pair": stage_ms, "dominant_stage": dom}
+                    "stage_ms_per_pair": stage_ms, "dominant_stage": dom,
+                    "dominant_kernel": {"name": "replay_cells_kernel", "bound": "integer ALU / issue (not HBM, not tensor)",
+                                        "evidence": "profiles/r01_top_kernels_v2.ncu-rep, profiles/r01_launches_v7.csv"}}
         # ---- CPU baseline: serial oracle on one core, bounded sample ---------------------------
         cpu = None
         if not a.no_cpu:
@@ -356,7 +361,7 @@ def run_engine(a):
                 "ms_per_step": ms_dev / a.steps, "ms_per_pair": ms_dev / (a.steps * P), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
                 "config": {"workload": "synthetic %dx%d textured pair, known homography (BASELINE config 3), "
-                                       "%d distinct pairs per GPU per step" % (w, h, P),
+                                       "%d distinct pairs per GPU per step, 4 overlapped lanes (PANO_BATCH_LANES)" % (w, h, P),
                            "pairs_per_step_per_gpu": P, "seed": SEED, "l2_policy": "inputs %d MB per GPU > 126 MB L2, "
                            "rotating every step" % (P * 2 * 3 * npx // 2**20), "keypoints": [r0["kl"], r0["kr"]],
                            "matches": r0["m"], "inliers": r0["best"], "parallelism": "pairs sharded over %d GPU(s), "
