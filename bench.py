@@ -74,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
@@ -127,7 +127,7 @@ def run_reference(a):
     O = Oracle("omp")
     cores = O.num_threads()
     w, h = a.w, a.h
-    pairs = [cached_pair(w, h, 1000 + i) for i in range(max(1, min(a.pairs, 2)))]
+    pairs = [cached_pair(w, h, 1000 + i) for i in range(2)]
     times = []
     for s in range(a.warmup + a.steps):
         l, r = pairs[s % len(pairs)]
@@ -181,15 +181,22 @@ def run_engine(a):
         os.environ["NCCL_DEBUG"] = os.environ.get("PANO_NCCL_DEBUG", "WARN")   # stdout must be one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    # overlapped lanes per GPU: each has a (spin-waiting) host thread, so share the cores between ranks
+    lanes = int(os.environ.get("PANO_BATCH_LANES", max(2, min(8, (os.cpu_count() or 8) // max(world, 1)))))
+    os.environ["PANO_BATCH_LANES"] = str(lanes)
     eng = pkg.Engine(device=local, seed=SEED)
     w, h, P = a.w, a.h, a.pairs
-    host = [cached_pair(w, h, 1000 + rank * P + i) for i in range(P)]
-    Ld = [torch.from_numpy(l).cuda() for l, _ in host]
-    Rd = [torch.from_numpy(r).cuda() for _, r in host]
-    Lh = [torch.from_numpy(l).pin_memory() for l, _ in host]
-    Rh = [torch.from_numpy(r).pin_memory() for _, r in host]
+    D = min(a.distinct, P)                       # distinct pairs; a step cycles over them
+    host = [cached_pair(w, h, 1000 + rank * D + i) for i in range(D)]
+    Ld0 = [torch.from_numpy(l).cuda() for l, _ in host]
+    Rd0 = [torch.from_numpy(r).cuda() for _, r in host]
+    Lh0 = [torch.from_numpy(l).pin_memory() for l, _ in host]
+    Rh0 = [torch.from_numpy(r).pin_memory() for _, r in host]
     cap = 3 * (2 * w + 64) * (h + 256)
-    Ch = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(P)]
+    Ch0 = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(D)]
+    Ld, Rd = [Ld0[i % D] for i in range(P)], [Rd0[i % D] for i in range(P)]
+    Lh, Rh = [Lh0[i % D] for i in range(P)], [Rh0[i % D] for i in range(P)]
+    Ch = [Ch0[i % D] for i in range(P)]
 
     def barrier():
         if world > 1:
@@ -353,7 +360,13 @@ def run_engine(a):
             o = O.stitch_pair(l, r, seed=SEED)
             dt = time.perf_counter() - t0
             ok = (o["status"] == 1 and np.array_equal(o["H"].view(np.uint64), res[0]["H"].view(np.uint64)))
-            cpu = {"value": 2 * npx / 1e6 / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            o0 = None
+            if a.cpu_o0:   # what the reference's CMake actually builds (no build type => -O0); slow
+                O0 = Oracle("O0")
+                t0 = time.perf_counter()
+                O0.stitch_pair(l, r, seed=SEED)
+                o0 = 2 * npx / 1e6 / (time.perf_counter() - t0)
+            cpu = {"value": 2 * npx / 1e6 / dt, "unit": UNIT, "cores": 1, "kind": "port", "value_O0_build": o0,
                    "sample": "1 pair of the same workload, serial oracle (-O2), %.2f s; "
                              "H bit-identical to the engine's: %s" % (dt, ok),
                    "stage_ms": o["times_ms"]}
@@ -361,9 +374,9 @@ def run_engine(a):
                 "ms_per_step": ms_dev / a.steps, "ms_per_pair": ms_dev / (a.steps * P), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
                 "config": {"workload": "synthetic %dx%d textured pair, known homography (BASELINE config 3), "
-                                       "%d distinct pairs per GPU per step, 4 overlapped lanes (PANO_BATCH_LANES)" % (w, h, P),
+                                       "%d pairs per GPU per step cycling over %d distinct ones, %d overlapped lanes per GPU (PANO_BATCH_LANES)" % (w, h, P, D, lanes),
                            "pairs_per_step_per_gpu": P, "seed": SEED, "l2_policy": "inputs %d MB per GPU > 126 MB L2, "
-                           "rotating every step" % (P * 2 * 3 * npx // 2**20), "keypoints": [r0["kl"], r0["kr"]],
+                           "rotating within every step" % (D * 2 * 3 * npx // 2**20), "keypoints": [r0["kl"], r0["kr"]],
                            "matches": r0["m"], "inliers": r0["best"], "parallelism": "pairs sharded over %d GPU(s), "
                            "no data-path collective" % world},
                 "clocks": clocks, "gpu_launches": launches,
@@ -382,9 +395,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--pairs", type=int, default=4, help="distinct 4K pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=16, help="4K pairs per GPU per step")
+    ap.add_argument("--distinct", type=int, default=4, help="distinct pairs the step cycles over (4 = 189 MB > L2)")
     ap.add_argument("--size", default="3840x2160")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-o0", action="store_true", help="also time the -O0 build of the oracle (the reference's default flags)")
     a = ap.parse_args()
     a.w, a.h = [int(v) for v in a.size.split("x")]
     if a.impl == "reference":

@@ -225,6 +225,9 @@ int pano_stitch_batch(pano_ctx* ctx, int n, const uint8_t* const* lefts, const u
 /* The context's CUDA stream (a cudaStream_t), so callers can bracket calls with their own
  * events or order their own work against the engine's. */
 void* pano_stream(pano_ctx* ctx);
+/* Makes the context enqueue all its work on the caller's stream (a cudaStream_t on the context's
+ * device; NULL = back to a private stream).  Calls still return after their results are valid. */
+int pano_set_stream(pano_ctx* ctx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "pano_harris_response", "pano_convolve_f64", "pano_match", "pano_ransac", "pano_canvas_geometry",
     "pano_warp_overlay", "pano_warp_perspective", "pano_stitch_pair", "pano_get_canvas", "pano_canvas_device",
     "pano_stitch_fold", "pano_stitch_batch", "pano_stream", "pano_pair_homography", "pano_mul33",
-    "pano_chain_geometry", "pano_warp_accumulate",
+    "pano_chain_geometry", "pano_warp_accumulate", "pano_set_stream",
 ]
 
 
@@ -421,6 +421,10 @@ class Engine:
         if not ok:
             return None, res
         return self.renderChainBand(images, Hs, geom, T, 0, geom[1]), res
+
+    def set_stream(self, stream_ptr):
+        """enqueue on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None resets"""
+        self._check(self.lib.pano_set_stream(self.ctx, C.c_void_p(stream_ptr) if stream_ptr else None))
 
     def stream_ptr(self):
         self.lib.pano_stream.restype = C.c_void_p

@@ -22,6 +22,7 @@ struct pano_ctx {
   int matcher = 0;  // 0 tensor-core, 1 SIMT
   double replay_target = 0;  // candidate walks per replay chunk (0 = default)
   cudaStream_t st = nullptr;
+  bool owns_stream = true;
   std::string err;
   PinnedBuf pin;
   DevBuf up[2];  // staging for host images
@@ -288,7 +289,7 @@ void pano_destroy(pano_ctx* c) {
   c->pin.release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
-  if (c->st) cudaStreamDestroy(c->st);
+  if (c->st && c->owns_stream) cudaStreamDestroy(c->st);
   delete c;
 }
 
@@ -547,6 +548,21 @@ int pano_stitch_fold(pano_ctx* c, const uint8_t* const* images, const int* ws, c
 
 void* pano_stream(pano_ctx* c) { return c ? (void*)c->st : nullptr; }
 
+int pano_set_stream(pano_ctx* c, void* stream) {
+  if (!c) return PANO_ERR_INVALID;
+  cudaSetDevice(c->device);
+  if (c->st) cudaStreamSynchronize(c->st);
+  if (c->owns_stream && c->st) cudaStreamDestroy(c->st);
+  if (stream) {
+    c->st = (cudaStream_t)stream;
+    c->owns_stream = false;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) return PANO_ERR_CUDA;
+    c->owns_stream = true;
+  }
+  return PANO_OK;
+}
+
 int pano_pair_homography(pano_ctx* c, const uint8_t* left, int wl, int hl, size_t stride_l, const uint8_t* right,
                          int wr, int hr, size_t stride_r, int mem, const pano_harris_opts* hopts,
                          const pano_ransac_opts* ropts, pano_pair_result* res) {
@@ -627,8 +643,13 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
   if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
   // Pairs are independent: run them on several lanes (child contexts, each with its own stream,
   // scratch and host thread) so that one pair's host synchronisations, copies and low-occupancy
-  // kernels overlap with another pair's work.  PANO_BATCH_LANES (default 4, 1 = sequential).
-  int n_lanes = 4;
+  // kernels overlap with another pair's work.  PANO_BATCH_LANES (default 6, 1 = sequential).
+  int n_lanes = 6;
+  {
+    // each lane has a host thread that spin-waits in stream synchronisation: stay within the cores
+    unsigned hc = std::thread::hardware_concurrency();
+    if (hc > 0 && (int)hc < n_lanes) n_lanes = (int)hc;
+  }
   if (const char* e = getenv("PANO_BATCH_LANES")) n_lanes = atoi(e);
   if (n_lanes < 1) n_lanes = 1;
   if (n_lanes > 8) n_lanes = 8;

@@ -448,40 +448,36 @@ PANO_HD uint32_t ctz32(uint32_t w) {
 // Segment-boundary offsets are recorded as in walk_offsets.
 PANO_HD uint32_t walk_bits(const uint32_t* bits, uint32_t D, uint32_t nkb, uint32_t d0, uint32_t steps,
                            uint32_t pos0, uint32_t* seg_off, size_t seg_stride) {
+  constexpr uint32_t AHEAD = 16;                       // words in flight on the current diagonal
+  constexpr uint32_t SEGW = PANO_SEG_STEPS / 32u;      // words per pass-2 segment
   uint32_t d = d0, kb = 0, mask = ~0u;
   while (kb < nkb) {
-    // 8 words ahead on the current diagonal (independent loads); a hop discards the rest
-    uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
+    // independent loads; a hop to the next diagonal discards the rest
+    uint32_t w[AHEAD];
     const uint32_t* p = bits + (size_t)kb * D + d;
     const uint32_t left = nkb - kb;
-    w0 = p[0] & mask;
-    w1 = left > 1 ? p[(size_t)D] : 0u;
-    w2 = left > 2 ? p[(size_t)2 * D] : 0u;
-    w3 = left > 3 ? p[(size_t)3 * D] : 0u;
-    w4 = left > 4 ? p[(size_t)4 * D] : 0u;
-    w5 = left > 5 ? p[(size_t)5 * D] : 0u;
-    w6 = left > 6 ? p[(size_t)6 * D] : 0u;
-    w7 = left > 7 ? p[(size_t)7 * D] : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t i = 0; i < AHEAD; i++) w[i] = i < left ? p[(size_t)i * D] : 0u;
+    w[0] &= mask;
     mask = ~0u;
-    uint32_t adv, w;  // words without a rejection before the first one that has one
-    if (w0) { adv = 0; w = w0; }
-    else if (w1) { adv = 1; w = w1; }
-    else if (w2) { adv = 2; w = w2; }
-    else if (w3) { adv = 3; w = w3; }
-    else if (w4) { adv = 4; w = w4; }
-    else if (w5) { adv = 5; w = w5; }
-    else if (w6) { adv = 6; w = w6; }
-    else if (w7) { adv = 7; w = w7; }
-    else { adv = left < 8u ? left : 8u; w = 0; }
-    // at most one segment boundary (multiple of PANO_SEG_STEPS / 32 = 8 words) lies in (kb, kb + adv]
-    const uint32_t nb = (kb + adv) & ~(PANO_SEG_STEPS / 32u - 1u);
-    if (nb > kb && nb < nkb && seg_off)
-      seg_off[(size_t)(nb / (PANO_SEG_STEPS / 32u) - 1u) * seg_stride] = pos0 + d + nb * 32u;
+    uint32_t adv = left < AHEAD ? left : AHEAD, hit = 0;  // words without a rejection, first word with one
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = (int)AHEAD - 1; i >= 0; i--)
+      if (w[i]) { adv = (uint32_t)i; hit = w[i]; }
+    // segment boundaries (multiples of SEGW words) in (kb, kb + adv]: at most AHEAD / SEGW of them
+    if (seg_off) {
+      for (uint32_t nb = (kb / SEGW + 1u) * SEGW; nb <= kb + adv && nb < nkb; nb += SEGW)
+        seg_off[(size_t)(nb / SEGW - 1u) * seg_stride] = pos0 + d + nb * 32u;
+    }
     kb += adv;
-    if (w) {
+    if (hit) {
       d++;
       if (d >= D) return 0xffffffffu;
-      mask = ~0u << ctz32(w);
+      mask = ~0u << ctz32(hit);
     }
   }
   return pos0 + d + steps;

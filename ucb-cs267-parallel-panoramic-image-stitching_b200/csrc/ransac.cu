@@ -698,7 +698,19 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
     return (v >= 64.0 && v <= 51000.0) ? v : 0.0;
   }();
   const double target_cand = env_target > 0 ? env_target : (replay_target > 0 ? replay_target : 50000.0);
-  ReplayPlan plan = plan_replay(n, iters, window_scale, target_cand);
+  // plans depend only on (M, iterations, window scale, chunk target): keep the most recent ones
+  struct PlanKey { uint32_t n; int iters, scale; double target; };
+  thread_local std::vector<std::pair<PlanKey, ReplayPlan>> plan_cache;
+  const ReplayPlan* plan_ptr = nullptr;
+  for (auto& e : plan_cache)
+    if (e.first.n == n && e.first.iters == iters && e.first.scale == window_scale && e.first.target == target_cand)
+      plan_ptr = &e.second;
+  if (!plan_ptr) {
+    if (plan_cache.size() >= 8) plan_cache.erase(plan_cache.begin());
+    plan_cache.emplace_back(PlanKey{n, iters, window_scale, target_cand}, plan_replay(n, iters, window_scale, target_cand));
+    plan_ptr = &plan_cache.back().second;
+  }
+  const ReplayPlan& plan = *plan_ptr;
   const std::vector<WinEntry>& win = plan.win;
   const int G = plan.G;
   const uint32_t n_cand = plan.n_cand, max_w = plan.max_w;
