@@ -298,7 +298,12 @@ def run_engine(a):
                                                  Hm.ctypes.data_as(C.c_void_p), C.c_void_p(canvas.data_ptr()),
                                                  C.c_size_t(canvas.stride(0)), C.c_size_t(canvas.numel()),
                                                  C.byref(info)))
-        t_warp = time_kernel(eng, torch, k_warp)
+        t_warp_api = time_kernel(eng, torch, k_warp)          # through the stage entry point (launch + sync)
+        # the kernel itself: CUDA events recorded on the engine's stream right around the launch
+        # inside the fused pair call (pano_pair_result.ms_warp), median of 7 single-pair runs
+        os.environ["PANO_BATCH_LANES"] = "1"
+        t_warp = statistics.median([eng.stitchTwoImages(Ld[0], Rd[0], fetch=False)[1]["ms"]["warp"] for _ in range(7)])
+        os.environ["PANO_BATCH_LANES"] = str(lanes)
         # matcher stage (descriptor gather + tcgen05 distance GEMM + emit) on resident inputs
         kl_t = torch.zeros((max(r0["kl"], 1), 2), dtype=torch.int32, device="cuda")
         kr_t = torch.zeros((max(r0["kr"], 1), 2), dtype=torch.int32, device="cuda")
@@ -339,7 +344,7 @@ def run_engine(a):
         match_ops = 2.0 * r0["kr"] * r0["kl"] * 75
         roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                     "traffic": traffic.get(top), "peak_source": how + " copy bandwidth (MEASURED_PEAKS.json)",
-                    "kernel_ms": kernels[top]["ms"], "note": kernels[top]["note"],
+                    "kernel_ms": kernels[top]["ms"], "stage_call_ms": t_warp_api, "note": kernels[top]["note"],
                     "other_kernels": {k: {"ms": v["ms"], "achieved_GBs": v["alg_bytes"] / (v["ms"] / 1e3) / 1e9,
                                           "frac": v["alg_bytes"] / (v["ms"] / 1e3) / 1e9 / hbm,
                                           "traffic": traffic.get(k)} for k, v in kernels.items()},

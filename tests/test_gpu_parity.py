@@ -285,3 +285,23 @@ def test_chain_strip_matches_oracle_and_bands_tile(engine, oracle):
         bands.append(engine.renderChainBand(views, Hs, geom, T, y, bh))
         y += bh
     assert np.array_equal(np.concatenate(bands, axis=0), pano)
+
+
+# ---------------- replay regimes at large match counts (synthetic matches, no images needed) -------
+@pytest.mark.parametrize("m,iters", [(40001, 60), (65535, 24), (65536, 24), (70000, 30)])
+def test_ransac_large_match_counts(engine, oracle, m, iters):
+    """paired draws with heavy Lemire rejection (ranges near 2^32) and, above 65535 elements,
+    libstdc++'s one-draw-per-element branch; samples and counts must still be bit-exact"""
+    rng = np.random.default_rng(m)
+    kp1 = rng.integers(0, 4000, (m, 2)).astype(np.int32)
+    kp2 = (kp1 + np.array([900, 3]) + rng.integers(-40, 41, (m, 2))).astype(np.int32)
+    good = rng.random(m) < 0.5
+    kp2[good] = kp1[good] + np.array([900, 3])
+    mt = np.zeros(m, load_pkg().MATCH_DTYPE)
+    mt["queryIdx"] = np.arange(m); mt["trainIdx"] = np.arange(m)
+    o = load_pkg().RansacOptions(numIterations_=iters)
+    g = engine.computeHomography(kp1, kp2, mt, o, details=True)
+    c = oracle.ransac(kp1, kp2, mt, iters=iters, seed=12345)
+    assert np.array_equal(g["samples"], c["samples"][:iters])
+    assert np.array_equal(g["counts"], c["counts"][:iters])
+    assert g["ok"] == c["ok"] and (not c["ok"] or np.array_equal(bits(g["H"]), bits(c["H"])))
