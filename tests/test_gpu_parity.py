@@ -305,3 +305,28 @@ def test_ransac_large_match_counts(engine, oracle, m, iters):
     assert np.array_equal(g["samples"], c["samples"][:iters])
     assert np.array_equal(g["counts"], c["counts"][:iters])
     assert g["ok"] == c["ok"] and (not c["ok"] or np.array_equal(bits(g["H"]), bits(c["H"])))
+
+
+def test_replay_window_miss_is_detected_and_rerun(oracle, small_pair):
+    """with absurdly narrow speculation windows (0.3 sigma) the true start falls outside its window
+    all the time; the engine must notice, widen and still return the exact samples"""
+    import subprocess
+    import sys
+    import textwrap
+    import os
+    from conftest import ROOT, PKG
+    code = textwrap.dedent('''
+        import sys, importlib, numpy as np
+        sys.path.insert(0, %r)
+        pkg = importlib.import_module(%r); synth = importlib.import_module(%r + ".synth")
+        from oracle.oracle import Oracle
+        O = Oracle(); eng = pkg.Engine(0, 12345)
+        left, right, _ = synth.make_pair(960, 540, seed=267)
+        kl, kr = O.detect(left), O.detect(right); m = O.match(kr, kl, right, left)
+        g = eng.computeHomography(kr, kl, m, details=True); c = O.ransac(kr, kl, m, seed=12345)
+        assert np.array_equal(g["samples"], c["samples"]) and np.array_equal(g["counts"], c["counts"])
+        print("OK", len(m))
+    ''') % (ROOT, PKG, PKG)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       env=dict(os.environ, PANO_REPLAY_Z="0.3"))
+    assert p.returncode == 0 and "OK" in p.stdout, p.stderr[-800:]

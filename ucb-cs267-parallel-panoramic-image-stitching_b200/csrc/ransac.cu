@@ -698,16 +698,21 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
     return (v >= 64.0 && v <= 51000.0) ? v : 0.0;
   }();
   const double target_cand = env_target > 0 ? env_target : (replay_target > 0 ? replay_target : 50000.0);
+  static const double z_sigma = [] {   // window half-width in sigmas (test hook: small values force re-runs)
+    const char* e = getenv("PANO_REPLAY_Z");
+    double v = e ? atof(e) : 0.0;
+    return (v > 0.0 && v < 20.0) ? v : 4.2;
+  }();
   // plans depend only on (M, iterations, window scale, chunk target): keep the most recent ones
   struct PlanKey { uint32_t n; int iters, scale; double target; };
   thread_local std::vector<std::pair<PlanKey, ReplayPlan>> plan_cache;
   const ReplayPlan* plan_ptr = nullptr;
   for (auto& e : plan_cache)
-    if (e.first.n == n && e.first.iters == iters && e.first.scale == window_scale && e.first.target == target_cand)
+    if (e.first.n == n && e.first.iters == iters && e.first.scale == window_scale && e.first.target == target_cand)  // (z_sigma is process-constant)
       plan_ptr = &e.second;
   if (!plan_ptr) {
     if (plan_cache.size() >= 8) plan_cache.erase(plan_cache.begin());
-    plan_cache.emplace_back(PlanKey{n, iters, window_scale, target_cand}, plan_replay(n, iters, window_scale, target_cand));
+    plan_cache.emplace_back(PlanKey{n, iters, window_scale, target_cand}, plan_replay(n, iters, window_scale, target_cand, z_sigma));
     plan_ptr = &plan_cache.back().second;
   }
   const ReplayPlan& plan = *plan_ptr;

@@ -32,7 +32,8 @@ struct ReplayPlan {
 
 // n = number of shuffled elements (matches), iters = RANSAC iterations,
 // window_scale = 1, 2, 4, ... (doubled by the caller after a detected window miss).
-inline ReplayPlan plan_replay(uint32_t n, int iters, int window_scale, double target_cand = 50000.0) {
+inline ReplayPlan plan_replay(uint32_t n, int iters, int window_scale, double target_cand = 50000.0,
+                              double z_sigma = 4.2) {
   ReplayPlan P;
   const bool pairs = shuffle_uses_pairs(n);
   const uint32_t steps = shuffle_steps(n);
@@ -56,9 +57,11 @@ inline ReplayPlan plan_replay(uint32_t n, int iters, int window_scale, double ta
   }
   P.mu = mu;
   P.sigma = std::sqrt(var);
-  // windows of +-(5 sigma sqrt(g) + 3) * scale around g * mu (a miss is detected and re-run
-  // wider, never guessed); chunk length chosen so a chunk has about `target` candidate walks
-  const double zs = 5.0 * window_scale, pad = 3.0 * window_scale;
+  // windows of +-(4.2 sigma sqrt(g) + 2) * scale around g * mu.  A true start outside its window
+  // is detected and the replay re-run with doubled windows, never guessed, so the width only trades
+  // speculative work against the (rare: ~2e-5 per iteration) cost of a re-run.  The chunk length is
+  // chosen so that a chunk has about `target` candidate walks.
+  const double zs = z_sigma * window_scale, pad = 2.0 * window_scale;
   int G = 8;
   for (int cand = 8; cand <= 1024; cand *= 2) {
     double tot = 0;
@@ -82,9 +85,9 @@ inline ReplayPlan plan_replay(uint32_t n, int iters, int window_scale, double ta
     P.max_w = std::max(P.max_w, P.win[g].width);
     max_hi = std::max(max_hi, hi);
   }
-  // a walk moves up one diagonal per rejection: mu + 8 sigma (+ margin) extra diagonals; a walk
+  // a walk moves up one diagonal per rejection: mu + 6 sigma (+ margin) extra diagonals; a walk
   // that would leave them is flagged and the caller re-plans wider, like a window miss
-  P.dextra = (uint32_t)std::ceil(mu + (8.0 * window_scale) * P.sigma + 8.0 * window_scale);
+  P.dextra = (uint32_t)std::ceil(mu + (6.0 * window_scale) * P.sigma + 4.0 * window_scale);
   for (int g = 0; g < G; g++) {
     P.win[g].dfirst = P.n_diag;
     uint32_t D = (P.win[g].width + P.dextra + 31u) / 32u * 32u;
