@@ -10,15 +10,20 @@
 // tiles are visited in train order with a strict '<', and CTAs that split the train range merge
 // through atomicMin on (ssd << 32 | j).
 //
-// Structure (one persistent CTA per SM, 288 threads):
-//   warps 0-3  epilogue: TMEM -> registers (tcgen05.ld 32x32b.x32), key/min, atomicMin
-//   warps 4-7  loaders : descriptor rows (global, row-major [rows][128 B]) -> shared memory in the
-//                        128-byte-swizzled K-major layout the UMMA descriptors expect
-//   warp  8    one lane issues tcgen05.mma (4 K-steps of 32 bytes per 128x256 tile) and commits
-// Pipelines (mbarriers): B stages full/empty (3 deep), A buffer full/empty (2 deep),
-// TMEM accumulators full/empty (2 x 256 columns).
+// Structure (one persistent CTA per SM, 320 threads):
+//   warps 0-3  epilogue warpgroup 0: drains TMEM accumulator 0 (even tiles)
+//   warps 4-7  epilogue warpgroup 1: drains TMEM accumulator 1 (odd tiles)
+//              (tcgen05.ld 32x32b.x32 -> registers, key/min, atomicMin)
+//   warp  8    producer: one lane issues TMA loads (cp.async.bulk.tensor.2d, 128B swizzle) of the
+//              descriptor tiles straight into the K-major layout the UMMA descriptors expect; the
+//              warp also writes the per-tile column constants
+//   warp  9    one lane issues tcgen05.mma (4 K-steps of 32 bytes per 128x256 tile) and commits
+// Pipelines (mbarriers): B stages full/empty (3 deep, TMA complete_tx), A buffer full/empty
+// (2 deep), TMEM accumulators full/empty (2 x 256 columns).
 // Every wait is bounded: a bring-up bug raises an error flag instead of hanging the device.
 #include "common.cuh"
+
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 
 namespace pano {
 
@@ -28,9 +33,10 @@ constexpr int TM = 128;            // query rows per tile (UMMA M)
 constexpr int TN = 256;            // train rows per tile (UMMA N)
 constexpr int KB = PANO_DESC_STRIDE;  // 128 bytes of K per row = one 128B swizzle atom
 constexpr int NSTAGE = 3;
+constexpr int K_STEPS = 3;         // 3 x 32 = 96 >= 75 descriptor bytes; bytes 96..127 of a row are zero padding
 constexpr int A_BYTES = TM * KB;   // 16 KB
 constexpr int B_BYTES = TN * KB;   // 32 KB
-constexpr int TC_THREADS = 288;
+constexpr int TC_THREADS = 320;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 // instruction descriptor, kind::i8: D = S32 (2 << 4), A = B = UINT8 (0), both K-major,
@@ -77,6 +83,18 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t pari
   return false;
 }
 
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 2-D TMA tile load: box (128 bytes of K) x (rows) starting at row `row0`, completes on `bar`
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int row0,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(row0), "r"(smem_u32(bar))
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -116,33 +134,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// rows [row0, row0 + rows) of a row-major [.][128 B] descriptor matrix -> swizzled K-major tile.
-// 128 threads, 8 independent 16-byte loads in flight per thread before the stores.
-__device__ __forceinline__ void load_tile(uint8_t* dst, const uint8_t* __restrict__ src, int row0, int rows, int tid,
-                                          int nthreads) {
-  const uint4* g = reinterpret_cast<const uint4*>(src + (size_t)row0 * KB);
-  const int total = rows * 8;
-  for (int e0 = tid; e0 < total; e0 += nthreads * 8) {
-    uint4 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int e = e0 + u * nthreads;
-      v[u] = e < total ? g[e] : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int e = e0 + u * nthreads;
-      if (e < total) {
-        const int r = e >> 3, q = e & 7;
-        *reinterpret_cast<uint4*>(dst + r * KB + ((q ^ (r & 7)) << 4)) = v[u];
-      }
-    }
-  }
-}
-
 __global__ void __launch_bounds__(TC_THREADS, 1)
-match_tc_kernel(const uint8_t* __restrict__ qd, const uint32_t* __restrict__ qn, int nq,
-                const uint8_t* __restrict__ td, const uint32_t* __restrict__ tn, int nt, int n_qtiles,
+match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
+                const uint32_t* __restrict__ qn, int nq, const uint32_t* __restrict__ tn, int nt, int n_qtiles,
                 int n_ttiles, int tiles_per_item, int n_items, unsigned long long* __restrict__ best,
                 int* __restrict__ err) {
   extern __shared__ uint8_t smem_raw[];
@@ -151,15 +145,15 @@ match_tc_kernel(const uint8_t* __restrict__ qd, const uint32_t* __restrict__ qn,
   volatile int* abort_flag = &S.abort_flag;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; i++) { mbar_init(&S.b_full[i], 128); mbar_init(&S.b_empty[i], 1); }
+    for (int i = 0; i < NSTAGE; i++) { mbar_init(&S.b_full[i], 33); mbar_init(&S.b_empty[i], 1); }  // 32 cvec lanes + TMA
     for (int i = 0; i < 2; i++) {
-      mbar_init(&S.a_full[i], 128); mbar_init(&S.a_empty[i], 1);
+      mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1);
       mbar_init(&S.t_full[i], 1);   mbar_init(&S.t_empty[i], 128);
     }
     S.abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {  // TMEM: all 512 columns (two 128 x 256 s32 accumulators)
+  if (warp == 9) {  // TMEM: all 512 columns (two 128 x 256 s32 accumulators)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
                  "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -171,24 +165,26 @@ match_tc_kernel(const uint8_t* __restrict__ qd, const uint32_t* __restrict__ qn,
 
   const int per_q = (n_ttiles + tiles_per_item - 1) / tiles_per_item;  // items per query tile
 
-  if (warp < 4) {
-    // ================= epilogue =================
+  if (warp < 8) {
+    // ================= epilogue: warpgroup wg drains TMEM accumulator wg =================
+    const uint32_t wg = (uint32_t)warp >> 2;
     uint32_t tile_ctr = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int qt = item / per_q, c = item - qt * per_q;
       const int t0 = c * tiles_per_item, t1 = min(n_ttiles, t0 + tiles_per_item);
-      const int qrow = qt * TM + (int)threadIdx.x;
+      const int qrow = qt * TM + ((int)threadIdx.x & 127);
       const int myqn = qrow < nq ? (int)qn[qrow] : 0;
       int best_ssd = 0x7fffffff, best_j = -1;
       bool ok = true;
       for (int tt = t0; tt < t1 && ok; tt++, tile_ctr++) {
         const uint32_t tb = tile_ctr & 1u, ph = (tile_ctr >> 1) & 1u;
+        if (tb != wg) continue;   // the other warpgroup's tile
         const uint32_t s = tile_ctr % NSTAGE, sph = (tile_ctr / NSTAGE) & 1u;
-        // b_full: acquires the loaders' cvec[tb] writes; t_full: the accumulator is complete
+        // b_full: acquires the producer's cvec[tb] writes; t_full: the accumulator is complete
         ok = mbar_wait(&S.b_full[s], sph, abort_flag) && mbar_wait(&S.t_full[tb], ph, abort_flag);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + tb * TN;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + tb * TN;
         int kmin = 0x7fffffff;
         uint32_t r[32];
         tmem_ld32(taddr, r);
@@ -219,9 +215,8 @@ match_tc_kernel(const uint8_t* __restrict__ qd, const uint32_t* __restrict__ qn,
       if (ok && qrow < nq && best_j >= 0 && best_j < nt)
         atomicMin(&best[qrow], ((unsigned long long)(uint32_t)best_ssd << 32) | (uint32_t)best_j);
     }
-  } else if (warp < 8) {
-    // ================= loaders =================
-    const int ltid = threadIdx.x - 128;
+  } else if (warp == 8) {
+    // ================= producer: TMA tile loads + per-tile column constants =================
     uint32_t tile_ctr = 0, item_ctr = 0;
     bool ok = true;
     for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, item_ctr++) {
@@ -230,24 +225,27 @@ match_tc_kernel(const uint8_t* __restrict__ qd, const uint32_t* __restrict__ qn,
       const uint32_t ab = item_ctr & 1u, aph = (item_ctr >> 1) & 1u;
       ok = mbar_wait(&S.a_empty[ab], aph ^ 1u, abort_flag);
       if (!ok) break;
-      load_tile(S.A[ab], qd, qt * TM, TM, ltid, 128);
-      fence_async_smem();
-      mbar_arrive(&S.a_full[ab]);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&S.a_full[ab], A_BYTES);
+        tma_load_2d(S.A[ab], &tmap_q, 0, qt * TM, &S.a_full[ab]);
+      }
       for (int tt = t0; tt < t1; tt++, tile_ctr++) {
         const uint32_t s = tile_ctr % NSTAGE, sph = (tile_ctr / NSTAGE) & 1u;
         const uint32_t tb = tile_ctr & 1u, tph = (tile_ctr >> 1) & 1u;
         ok = mbar_wait(&S.b_empty[s], sph ^ 1u, abort_flag) && mbar_wait(&S.t_empty[tb], tph ^ 1u, abort_flag);
         if (!ok) break;
-        load_tile(S.B[s], td, tt * TN, TN, ltid, 128);
-        for (int j = ltid; j < TN; j += 128) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&S.b_full[s], B_BYTES);
+          tma_load_2d(S.B[s], &tmap_t, 0, tt * TN, &S.b_full[s]);
+        }
+        for (int j = lane; j < TN; j += 32) {
           const int col = tt * TN + j;
           S.cvec[tb][j] = col < nt ? (int)(tn[col] * 256u + (uint32_t)j) : 0x7fffffff;
         }
-        fence_async_smem();
-        mbar_arrive(&S.b_full[s]);
+        mbar_arrive(&S.b_full[s]);   // release of this lane's cvec writes
       }
     }
-  } else if (lane == 0) {
+  } else if (warp == 9 && lane == 0) {
     // ================= MMA issuer (one thread) =================
     uint32_t tile_ctr = 0, item_ctr = 0;
     bool ok = true;
@@ -268,7 +266,7 @@ match_tc_kernel(const uint8_t* __restrict__ qd, const uint32_t* __restrict__ qn,
         const uint64_t bdesc = make_desc(smem_u32(S.B[s]));
         const uint32_t d_tmem = tmem_base + tb * TN;
 #pragma unroll
-        for (int ks = 0; ks < KB / 32; ks++)  // 32 bytes of K per MMA: descriptor start advances 32 B
+        for (int ks = 0; ks < K_STEPS; ks++)  // 32 bytes of K per MMA: descriptor start advances 32 B
           mma_i8(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), ks > 0 ? 1u : 0u);
         mma_commit(&S.b_empty[s]);   // smem stage reusable once these MMAs have read it
         mma_commit(&S.t_full[tb]);   // accumulator ready for the epilogue
@@ -280,7 +278,7 @@ match_tc_kernel(const uint8_t* __restrict__ qd, const uint32_t* __restrict__ qn,
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0 && S.abort_flag) atomicExch(err, 1);
-  if (warp == 8) {
+  if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
 }
@@ -290,6 +288,33 @@ std::atomic<int> g_tc_state{0};  // 0 unknown, 1 usable, -1 disabled after a fai
 }  // namespace
 
 bool match_tc_available() { return g_tc_state >= 0; }
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// descriptor matrix [rows][128 B] u8 -> 2-D tensor map, box = 128 bytes x box_rows, 128B swizzle
+void make_tmap(CUtensorMap* map, const void* base, size_t rows, uint32_t box_rows) {
+  static EncodeTiledFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return (EncodeTiledFn)fn;
+  }();
+  if (!encode) throw CudaError{cudaErrorNotSupported, "cuTensorMapEncodeTiled unavailable", __FILE__, __LINE__};
+  const cuuint64_t dims[2] = {(cuuint64_t)KB, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)KB};
+  const cuuint32_t box[2] = {(cuuint32_t)KB, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw CudaError{cudaErrorInvalidValue, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__};
+}
+}  // namespace
 
 void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t, unsigned long long* best,
                      DevBuf& errbuf) {
@@ -312,9 +337,13 @@ void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescript
   const int grid = n_items < sms ? n_items : sms;
   const size_t smem = sizeof(Smem) + 1024;
   PANO_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(q.desc.as<uint8_t>(), q.norm.as<uint32_t>(), q.count,
-                                                  t.desc.as<uint8_t>(), t.norm.as<uint32_t>(), t.count, n_qtiles,
-                                                  n_ttiles, tiles_per_item, n_items, best, errbuf.as<int>());
+  // descriptor buffers are padded to a multiple of 256 rows (build_descriptors_device)
+  CUtensorMap tmap_q, tmap_t;
+  make_tmap(&tmap_q, q.desc.p, ((size_t)q.count + 255) / 256 * 256, TM);
+  make_tmap(&tmap_t, t.desc.p, ((size_t)t.count + 255) / 256 * 256, TN);
+  match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_t, q.norm.as<uint32_t>(), q.count,
+                                                  t.norm.as<uint32_t>(), t.count, n_qtiles, n_ttiles,
+                                                  tiles_per_item, n_items, best, errbuf.as<int>());
   PANO_LAUNCH_CHECK();
   if (g_tc_state == 0) {
     // first use on this process: make sure the pipeline ran to completion
