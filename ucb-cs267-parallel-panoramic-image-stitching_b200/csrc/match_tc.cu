@@ -10,16 +10,22 @@
 // tiles are visited in train order with a strict '<', and CTAs that split the train range merge
 // through atomicMin on (ssd << 32 | j).
 //
+// Work split: the (query tile, train tile) grid is flattened query-major and every CTA takes one
+// contiguous, equally long run of tiles (a run that crosses a query-tile boundary reloads A and
+// flushes its rows' minima), so all SMs finish together.
 // Structure (one persistent CTA per SM, 320 threads):
 //   warps 0-3  epilogue warpgroup 0: drains TMEM accumulator 0 (even tiles)
 //   warps 4-7  epilogue warpgroup 1: drains TMEM accumulator 1 (odd tiles)
 //              (tcgen05.ld 32x32b.x32 -> registers, key/min, atomicMin)
 //   warp  8    producer: one lane issues TMA loads (cp.async.bulk.tensor.2d, 128B swizzle) of the
-//              descriptor tiles straight into the K-major layout the UMMA descriptors expect; the
-//              warp also writes the per-tile column constants
+//              descriptor tiles straight into the K-major layout the UMMA descriptors expect, and
+//              bulk copies (cp.async.bulk) of the tile's 256 precomputed column constants
 //   warp  9    one lane issues tcgen05.mma (4 K-steps of 32 bytes per 128x256 tile) and commits
-// Pipelines (mbarriers): B stages full/empty (3 deep, TMA complete_tx), A buffer full/empty
-// (2 deep), TMEM accumulators full/empty (2 x 256 columns).
+// Pipelines (mbarriers): B stages full/empty (5 deep, TMA complete_tx; the producer runs ahead of
+// the accumulators so the TMA latency is hidden), A buffer full/empty (2 deep), TMEM accumulators
+// full/empty (2 x 256 columns).  The per-tile column constants live in NCV = NSTAGE + 2 slots: the
+// producer reaches tile m only after the MMA of tile m - NSTAGE was issued, which needed the
+// epilogue of tile m - NSTAGE - 2 to have released its accumulator, so slot m % NCV is free.
 // Every wait is bounded: a bring-up bug raises an error flag instead of hanging the device.
 #include "common.cuh"
 
@@ -32,7 +38,8 @@ namespace {
 constexpr int TM = 128;            // query rows per tile (UMMA M)
 constexpr int TN = 256;            // train rows per tile (UMMA N)
 constexpr int KB = PANO_DESC_STRIDE;  // 128 bytes of K per row = one 128B swizzle atom
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 5;
+constexpr int NCV = NSTAGE + 2;      // column-constant slots (see the header comment)
 constexpr int K_STEPS = 3;         // 3 x 32 = 96 >= 75 descriptor bytes; bytes 96..127 of a row are zero padding
 constexpr int A_BYTES = TM * KB;   // 16 KB
 constexpr int B_BYTES = TN * KB;   // 32 KB
@@ -47,10 +54,11 @@ struct Smem {
   // tiles first: 1024-byte aligned (SWIZZLE_128B requirement)
   uint8_t A[2][A_BYTES];
   uint8_t B[NSTAGE][B_BYTES];
-  int cvec[2][TN];                 // per TMEM buffer: |t_j|^2 * 256 + (j mod 256), INT_MAX for padding
+  int cvec[NCV][TN];               // per tile in flight: |t_j|^2 * 256 + (j mod 256), INT_MAX for padding
   unsigned long long b_full[NSTAGE], b_empty[NSTAGE];
   unsigned long long a_full[2], a_empty[2];
   unsigned long long t_full[2], t_empty[2];
+  unsigned long long c_full[2];    // column constants of the tile in accumulator tb are visible (see MMA issuer)
   uint32_t tmem_base;
   int abort_flag;
 };
@@ -95,6 +103,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completes on `bar`
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -134,21 +149,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 32 columns of one accumulator row: key = cvec[j] - 512 * acc[j], four independent min chains
+__device__ __forceinline__ void chunk_min(const int4* __restrict__ cv, const uint32_t (&acc)[32], int& km0, int& km1,
+                                          int& km2, int& km3) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int4 c4 = cv[i];
+    km0 = min(km0, (int)((uint32_t)c4.x - 512u * acc[4 * i]));
+    km1 = min(km1, (int)((uint32_t)c4.y - 512u * acc[4 * i + 1]));
+    km2 = min(km2, (int)((uint32_t)c4.z - 512u * acc[4 * i + 2]));
+    km3 = min(km3, (int)((uint32_t)c4.w - 512u * acc[4 * i + 3]));
+  }
+}
+
+// the CTA's next run of tiles inside one query tile: tiles [tile, tile + n) of the flattened grid
+struct Seg { int qt, t0, t1; };
+__device__ __forceinline__ Seg next_seg(int tile, int hi, int n_ttiles) {
+  Seg g;
+  g.qt = tile / n_ttiles;
+  g.t0 = tile - g.qt * n_ttiles;
+  g.t1 = min(n_ttiles, g.t0 + (hi - tile));
+  return g;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
-                const uint32_t* __restrict__ qn, int nq, const uint32_t* __restrict__ tn, int nt, int n_qtiles,
-                int n_ttiles, int tiles_per_item, int n_items, unsigned long long* __restrict__ best,
-                int* __restrict__ err) {
-  extern __shared__ uint8_t smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+                const uint32_t* __restrict__ qn, int nq, const int* __restrict__ tkey, int nt, int n_ttiles,
+                int n_tiles, unsigned long long* __restrict__ best, int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // keep the pointer in the shared address space (LDS/STS, not generic loads)
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   volatile int* abort_flag = &S.abort_flag;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; i++) { mbar_init(&S.b_full[i], 33); mbar_init(&S.b_empty[i], 1); }  // 32 cvec lanes + TMA
+    for (int i = 0; i < NSTAGE; i++) { mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], 1); }
     for (int i = 0; i < 2; i++) {
       mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1);
       mbar_init(&S.t_full[i], 1);   mbar_init(&S.t_empty[i], 128);
+      mbar_init(&S.c_full[i], 1);
     }
     S.abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -163,51 +202,49 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
 
-  const int per_q = (n_ttiles + tiles_per_item - 1) / tiles_per_item;  // items per query tile
+  // this CTA's run of the flattened tile grid
+  const int lo = (int)((long long)n_tiles * blockIdx.x / gridDim.x);
+  const int hi = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
 
   if (warp < 8) {
     // ================= epilogue: warpgroup wg drains TMEM accumulator wg =================
     const uint32_t wg = (uint32_t)warp >> 2;
     uint32_t tile_ctr = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int qt = item / per_q, c = item - qt * per_q;
-      const int t0 = c * tiles_per_item, t1 = min(n_ttiles, t0 + tiles_per_item);
-      const int qrow = qt * TM + ((int)threadIdx.x & 127);
+    bool ok = true;
+    for (int tile = lo; tile < hi && ok;) {
+      const Seg sg = next_seg(tile, hi, n_ttiles);
+      tile += sg.t1 - sg.t0;
+      const int qrow = sg.qt * TM + ((int)threadIdx.x & 127);
       const int myqn = qrow < nq ? (int)qn[qrow] : 0;
       int best_ssd = 0x7fffffff, best_j = -1;
-      bool ok = true;
-      for (int tt = t0; tt < t1 && ok; tt++, tile_ctr++) {
+      for (int tt = sg.t0; tt < sg.t1 && ok; tt++, tile_ctr++) {
         const uint32_t tb = tile_ctr & 1u, ph = (tile_ctr >> 1) & 1u;
         if (tb != wg) continue;   // the other warpgroup's tile
-        const uint32_t s = tile_ctr % NSTAGE, sph = (tile_ctr / NSTAGE) & 1u;
-        // b_full: acquires the producer's cvec[tb] writes; t_full: the accumulator is complete
-        ok = mbar_wait(&S.b_full[s], sph, abort_flag) && mbar_wait(&S.t_full[tb], ph, abort_flag);
+        const uint32_t cs = tile_ctr % NCV;
+        // c_full: the producer's cvec writes are visible (relayed by the MMA thread, which acquired them
+        // through b_full; both barriers here advance in lockstep with the accumulator, so a waiter can
+        // never fall two phases behind); t_full: the accumulator is complete
+        ok = mbar_wait(&S.c_full[tb], ph, abort_flag) && mbar_wait(&S.t_full[tb], ph, abort_flag);
         if (!ok) break;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + tb * TN;
-        int kmin = 0x7fffffff;
-        uint32_t r[32];
-        tmem_ld32(taddr, r);
+        int km0 = 0x7fffffff, km1 = 0x7fffffff, km2 = 0x7fffffff, km3 = 0x7fffffff;
+        // two register buffers: the tcgen05.ld of chunk c + 1 is in flight while chunk c is reduced
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr, ra);
         tmem_ld_wait();
 #pragma unroll 1
-        for (int cb = 0; cb < TN / 32; cb++) {
-          uint32_t cur[32];
-#pragma unroll
-          for (int i = 0; i < 32; i++) cur[i] = r[i];
-          if (cb + 1 < TN / 32) tmem_ld32(taddr + (cb + 1) * 32, r);  // next chunk in flight
-          const int4* cv = reinterpret_cast<const int4*>(&S.cvec[tb][cb * 32]);
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int4 c4 = cv[i];
-            kmin = min(kmin, (int)((uint32_t)c4.x - 512u * cur[4 * i]));
-            kmin = min(kmin, (int)((uint32_t)c4.y - 512u * cur[4 * i + 1]));
-            kmin = min(kmin, (int)((uint32_t)c4.z - 512u * cur[4 * i + 2]));
-            kmin = min(kmin, (int)((uint32_t)c4.w - 512u * cur[4 * i + 3]));
-          }
+        for (int cb = 0; cb < TN / 32; cb += 2) {
+          tmem_ld32(taddr + (cb + 1) * 32, rb);
+          chunk_min(reinterpret_cast<const int4*>(&S.cvec[cs][cb * 32]), ra, km0, km1, km2, km3);
+          tmem_ld_wait();
+          if (cb + 2 < TN / 32) tmem_ld32(taddr + (cb + 2) * 32, ra);
+          chunk_min(reinterpret_cast<const int4*>(&S.cvec[cs][(cb + 1) * 32]), rb, km0, km1, km2, km3);
           tmem_ld_wait();
         }
         tc_fence_before();
         mbar_arrive(&S.t_empty[tb]);
+        const int kmin = min(min(km0, km1), min(km2, km3));
         const int v = kmin >> 8, jl = kmin & 255;
         const int ssd = v + myqn;
         if (kmin != 0x7fffffff && ssd < best_ssd) { best_ssd = ssd; best_j = tt * TN + jl; }
@@ -216,52 +253,48 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         atomicMin(&best[qrow], ((unsigned long long)(uint32_t)best_ssd << 32) | (uint32_t)best_j);
     }
   } else if (warp == 8) {
-    // ================= producer: TMA tile loads + per-tile column constants =================
-    uint32_t tile_ctr = 0, item_ctr = 0;
+    // ================= producer: TMA tile loads + bulk copies of the column constants =================
+    uint32_t tile_ctr = 0, seg_ctr = 0;
     bool ok = true;
-    for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, item_ctr++) {
-      const int qt = item / per_q, c = item - qt * per_q;
-      const int t0 = c * tiles_per_item, t1 = min(n_ttiles, t0 + tiles_per_item);
-      const uint32_t ab = item_ctr & 1u, aph = (item_ctr >> 1) & 1u;
+    for (int tile = lo; tile < hi && ok; seg_ctr++) {
+      const Seg sg = next_seg(tile, hi, n_ttiles);
+      tile += sg.t1 - sg.t0;
+      const uint32_t ab = seg_ctr & 1u, aph = (seg_ctr >> 1) & 1u;
       ok = mbar_wait(&S.a_empty[ab], aph ^ 1u, abort_flag);
       if (!ok) break;
       if (lane == 0) {
         mbar_arrive_expect_tx(&S.a_full[ab], A_BYTES);
-        tma_load_2d(S.A[ab], &tmap_q, 0, qt * TM, &S.a_full[ab]);
+        tma_load_2d(S.A[ab], &tmap_q, 0, sg.qt * TM, &S.a_full[ab]);
       }
-      for (int tt = t0; tt < t1; tt++, tile_ctr++) {
+      for (int tt = sg.t0; tt < sg.t1; tt++, tile_ctr++) {
         const uint32_t s = tile_ctr % NSTAGE, sph = (tile_ctr / NSTAGE) & 1u;
-        const uint32_t tb = tile_ctr & 1u, tph = (tile_ctr >> 1) & 1u;
-        ok = mbar_wait(&S.b_empty[s], sph ^ 1u, abort_flag) && mbar_wait(&S.t_empty[tb], tph ^ 1u, abort_flag);
+        const uint32_t cs = tile_ctr % NCV;
+        ok = mbar_wait(&S.b_empty[s], sph ^ 1u, abort_flag);
         if (!ok) break;
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&S.b_full[s], B_BYTES);
+        if (lane == 0) {   // descriptor tile (TMA) + the tile's 256 column constants (bulk copy), one barrier
+          mbar_arrive_expect_tx(&S.b_full[s], B_BYTES + TN * (uint32_t)sizeof(int));
           tma_load_2d(S.B[s], &tmap_t, 0, tt * TN, &S.b_full[s]);
+          bulk_load_1d(S.cvec[cs], tkey + (size_t)tt * TN, TN * (uint32_t)sizeof(int), &S.b_full[s]);
         }
-        for (int j = lane; j < TN; j += 32) {
-          const int col = tt * TN + j;
-          S.cvec[tb][j] = col < nt ? (int)(tn[col] * 256u + (uint32_t)j) : 0x7fffffff;
-        }
-        mbar_arrive(&S.b_full[s]);   // release of this lane's cvec writes
       }
     }
   } else if (warp == 9 && lane == 0) {
     // ================= MMA issuer (one thread) =================
-    uint32_t tile_ctr = 0, item_ctr = 0;
+    uint32_t tile_ctr = 0, seg_ctr = 0;
     bool ok = true;
-    for (int item = blockIdx.x; item < n_items && ok; item += gridDim.x, item_ctr++) {
-      const int qt = item / per_q, c = item - qt * per_q;
-      const int t0 = c * tiles_per_item, t1 = min(n_ttiles, t0 + tiles_per_item);
-      (void)qt;
-      const uint32_t ab = item_ctr & 1u, aph = (item_ctr >> 1) & 1u;
+    for (int tile = lo; tile < hi && ok; seg_ctr++) {
+      const Seg sg = next_seg(tile, hi, n_ttiles);
+      tile += sg.t1 - sg.t0;
+      const uint32_t ab = seg_ctr & 1u, aph = (seg_ctr >> 1) & 1u;
       ok = mbar_wait(&S.a_full[ab], aph, abort_flag);
       if (!ok) break;
       const uint64_t adesc = make_desc(smem_u32(S.A[ab]));
-      for (int tt = t0; tt < t1; tt++, tile_ctr++) {
+      for (int tt = sg.t0; tt < sg.t1; tt++, tile_ctr++) {
         const uint32_t s = tile_ctr % NSTAGE, sph = (tile_ctr / NSTAGE) & 1u;
         const uint32_t tb = tile_ctr & 1u, tph = (tile_ctr >> 1) & 1u;
         ok = mbar_wait(&S.b_full[s], sph, abort_flag) && mbar_wait(&S.t_empty[tb], tph ^ 1u, abort_flag);
         if (!ok) break;
+        mbar_arrive(&S.c_full[tb]);  // release: passes the acquired cvec writes on to the epilogue
         tc_fence_after();
         const uint64_t bdesc = make_desc(smem_u32(S.B[s]));
         const uint32_t d_tmem = tmem_base + tb * TN;
@@ -271,7 +304,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mma_commit(&S.b_empty[s]);   // smem stage reusable once these MMAs have read it
         mma_commit(&S.t_full[tb]);   // accumulator ready for the epilogue
       }
-      mma_commit(&S.a_empty[ab]);    // A buffer reusable after the item's last MMA
+      mma_commit(&S.a_empty[ab]);    // A buffer reusable after the segment's last MMA
     }
   }
 
@@ -281,6 +314,12 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
+}
+
+// column constants of the train side: |t_j|^2 * 256 + (j mod 256); INT_MAX for the padding columns
+__global__ void tkey_kernel(const uint32_t* __restrict__ tn, int nt, int n_pad, int* __restrict__ tkey) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_pad) tkey[j] = j < nt ? (int)(tn[j] * 256u + (uint32_t)(j & (TN - 1))) : 0x7fffffff;
 }
 
 std::atomic<int> g_tc_state{0};  // 0 unknown, 1 usable, -1 disabled after a failure
@@ -320,21 +359,20 @@ void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescript
                      DevBuf& errbuf) {
   PANO_CUDA(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * (size_t)q.count, st));
   if (q.count == 0 || t.count == 0) return;
-  errbuf.reserve(sizeof(int));
-  PANO_CUDA(cudaMemsetAsync(errbuf.p, 0, sizeof(int), st));
   const int n_qtiles = (q.count + TM - 1) / TM;
   const int n_ttiles = (t.count + TN - 1) / TN;
+  // errbuf: [0] pipeline error flag, [256 B ...] the train side's column constants
+  errbuf.reserve(256 + sizeof(int) * (size_t)n_ttiles * TN);
+  PANO_CUDA(cudaMemsetAsync(errbuf.p, 0, sizeof(int), st));
+  int* tkey = reinterpret_cast<int*>(errbuf.as<uint8_t>() + 256);
+  tkey_kernel<<<(n_ttiles * TN + 255) / 256, 256, 0, st>>>(t.norm.as<uint32_t>(), t.count, n_ttiles * TN, tkey);
+  PANO_LAUNCH_CHECK();
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // work items = (query tile, run of train tiles); aim at ~4 items per SM for balance
-  int per_q = (4 * sms + n_qtiles - 1) / n_qtiles;
-  if (per_q > n_ttiles) per_q = n_ttiles;
-  if (per_q < 1) per_q = 1;
-  int tiles_per_item = (n_ttiles + per_q - 1) / per_q;
-  per_q = (n_ttiles + tiles_per_item - 1) / tiles_per_item;
-  const int n_items = n_qtiles * per_q;
-  const int grid = n_items < sms ? n_items : sms;
+  // flattened (query tile, train tile) grid split into equal contiguous runs, one per SM
+  const int n_tiles = n_qtiles * n_ttiles;
+  const int grid = n_tiles < sms ? n_tiles : sms;
   const size_t smem = sizeof(Smem) + 1024;
   PANO_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // descriptor buffers are padded to a multiple of 256 rows (build_descriptors_device)
@@ -342,8 +380,8 @@ void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescript
   make_tmap(&tmap_q, q.desc.p, ((size_t)q.count + 255) / 256 * 256, TM);
   make_tmap(&tmap_t, t.desc.p, ((size_t)t.count + 255) / 256 * 256, TN);
   match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_t, q.norm.as<uint32_t>(), q.count,
-                                                  t.norm.as<uint32_t>(), t.count, n_qtiles, n_ttiles,
-                                                  tiles_per_item, n_items, best, errbuf.as<int>());
+                                                  tkey, t.count, n_ttiles, n_tiles, best,
+                                                  errbuf.as<int>());
   PANO_LAUNCH_CHECK();
   if (g_tc_state == 0) {
     // first use on this process: make sure the pipeline ran to completion
