@@ -104,6 +104,10 @@ const char* pano_version(void);
 uint64_t pano_kernel_launches(const pano_ctx* ctx);
 /* 0 = tensor-core matcher (default), 1 = SIMT cross-check kernel (debug / tests) */
 int pano_set_matcher(pano_ctx* ctx, int which);
+/* shuffle replay of pano_ransac / pano_stitch_*: 0 = chunked speculative replay over the whole GPU (lowest
+ * single-pair latency, default), 1 = resident replay (one CTA walks the iterations in order from exact
+ * offsets: ~20x less work, used by pano_stitch_batch's lanes).  Both are bit-exact; results are identical. */
+int pano_set_replay_mode(pano_ctx* ctx, int mode);
 
 /* ---- stage entry points -------------------------------------------------------------- */
 

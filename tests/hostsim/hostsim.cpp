@@ -138,4 +138,84 @@ int hs_replay(uint32_t seed, uint32_t n, int iters, int window_scale, int32_t* s
   return 0;
 }
 
+// emulates replay_resident_kernel phase by phase (cells -> segment walks -> chain -> tracking).
+// returns 0 ok, 1 band miss, 2 stream too short, 32 plan does not fit.  stats: nwords, dmax, nseg, n_entries, smem
+int hs_replay_resident(uint32_t seed, uint32_t n, int iters, int window_scale, double z_sigma, int32_t* samples,
+                       uint64_t* end_offset, double* stats) {
+  ReplayPlan P = plan_replay(n, iters, window_scale);
+  ResidentPlan R = plan_resident(P, n, window_scale, z_sigma > 0 ? z_sigma : 4.5);
+  if (stats) { stats[0] = R.nwords; stats[1] = R.dmax; stats[2] = R.nseg; stats[3] = R.n_entries; stats[4] = (double)R.smem_bytes; }
+  if (!R.ok) return 32;
+  const uint32_t steps = R.steps, odd = n & 1u;
+  const uint64_t x_limit = P.stream_need + steps + 4096;
+  std::vector<uint32_t> X(x_limit, 0xffffffffu);
+  {
+    std::mt19937 e(seed);
+    for (uint64_t i = 0; i < P.stream_need; i++) X[i] = e();
+  }
+  std::vector<uint32_t> bits(R.nwords);
+  std::vector<uint8_t> dtab((size_t)R.n_entries * (R.segb + 1));
+  std::vector<uint32_t> seg_entry(R.nseg);
+  uint64_t s = 0;
+  for (int t = 0; t < iters; t++) {
+    if (s + R.xcap + steps > x_limit) return 2;
+    const uint32_t* Xs = X.data() + s;   // (the kernel's shared-memory window, rel = 0)
+    // phase 1: cells
+    for (uint32_t b = 0; b < R.nkb; b++) {
+      const ResBlock B = R.blk[b];
+      for (uint32_t j = 0; j < B.w; j++) {
+        uint32_t word = 0;
+        for (uint32_t lane = 0; lane < 32; lane++) {
+          const uint32_t k = b * 32u + lane;
+          const RT q = k < steps ? P.rt[k] : RT{2u, 0u};
+          if (Xs[k + B.dlo + j] * q.r < q.T) word |= 1u << lane;
+        }
+        bits[B.woff + j] = word;
+      }
+    }
+    // phase 2: one walk per (segment, entry diagonal)
+    for (uint32_t sgm = 0; sgm < R.nseg; sgm++) {
+      const uint32_t b0 = sgm * R.segb, b1 = std::min(R.nkb, b0 + R.segb);
+      for (uint32_t e = 0; e < R.blk[b0].w; e++) {
+        uint8_t* out = dtab.data() + (size_t)(R.seg_eoff[sgm] + e) * (R.segb + 1);
+        out[R.segb] = (uint8_t)res_walk_segment(bits.data(), R.blk.data(), b0, b1, R.blk[b0].dlo + e, out);
+      }
+    }
+    // chain
+    uint32_t d = 0;
+    for (uint32_t sgm = 0; sgm < R.nseg; sgm++) {
+      const ResBlock B0 = R.blk[sgm * R.segb];
+      const uint32_t e = d - B0.dlo;
+      if (e >= B0.w) return 1;
+      seg_entry[sgm] = R.seg_eoff[sgm] + e;
+      d = dtab[(size_t)seg_entry[sgm] * (R.segb + 1) + R.segb];
+      if (d == RES_MISS) return 1;
+    }
+    // tracking: exact first steps, then "largest element written to position p wins"
+    int a[4] = {0, 1, 2, 3};
+    {
+      uint32_t o = 0, k = 0;
+      while (k < steps && 2u * k + odd < 4u) { track_step<true>(Xs, o, k, n, P.rt.data(), a); k++; }
+    }
+    int slot[4] = {-1, -1, -1, -1};
+    for (uint32_t k = 0; k < steps; k++) {
+      const uint32_t idx = 2u * k + odd;
+      if (idx < 4u) continue;
+      const uint32_t b = k >> 5, sgm = b / R.segb;
+      const uint32_t d0 = dtab[(size_t)seg_entry[sgm] * (R.segb + 1) + (b - sgm * R.segb)];
+      const uint32_t dk = res_diag_at(bits.data(), R.blk[b], d0, k & 31u);
+      const uint32_t x = Xs[k + dk];
+      const unsigned long long u = (unsigned long long)x * (idx + 1u);
+      const unsigned long long v = (unsigned long long)(uint32_t)u * (idx + 2u);
+      const uint32_t p1 = (uint32_t)(u >> 32), p2 = (uint32_t)(v >> 32);
+      if (p1 < 4u) slot[p1] = std::max(slot[p1], (int)idx);
+      if (p2 < 4u) slot[p2] = std::max(slot[p2], (int)idx + 1);
+    }
+    for (int p = 0; p < 4; p++) samples[(size_t)t * 4 + p] = slot[p] >= 0 ? slot[p] : a[p];
+    s += steps + d;
+  }
+  if (end_offset) *end_offset = s;
+  return 0;
+}
+
 }  // extern "C"

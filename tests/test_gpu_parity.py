@@ -330,3 +330,53 @@ def test_replay_window_miss_is_detected_and_rerun(oracle, small_pair):
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
                        env=dict(os.environ, PANO_REPLAY_Z="0.3"))
     assert p.returncode == 0 and "OK" in p.stdout, p.stderr[-800:]
+
+
+# ---------------- resident replay (one CTA, iterations in order; pano_stitch_batch's lanes) --------
+@pytest.mark.parametrize("m,iters", [(4, 50), (5, 50), (9, 100), (257, 300), (3000, 1000), (10774, 1000),
+                                     (10837, 1000), (20001, 100), (40001, 30)])
+def test_ransac_resident_replay(engine, oracle, m, iters):
+    """pano_set_replay_mode(1): samples, counts and H identical to the oracle (and so to the chunked
+    replay); m = 40001 exceeds the resident plan's band limit and must fall back to the chunked path"""
+    rng = np.random.default_rng(m)
+    kp1 = rng.integers(0, 4000, (m, 2)).astype(np.int32)
+    kp2 = (kp1 + np.array([900, 3]) + rng.integers(-40, 41, (m, 2))).astype(np.int32)
+    good = rng.random(m) < 0.5
+    kp2[good] = kp1[good] + np.array([900, 3])
+    mt = np.zeros(m, load_pkg().MATCH_DTYPE)
+    mt["queryIdx"] = np.arange(m); mt["trainIdx"] = np.arange(m)
+    o = load_pkg().RansacOptions(numIterations_=iters)
+    engine.set_replay_mode(1)
+    try:
+        g = engine.computeHomography(kp1, kp2, mt, o, details=True)
+    finally:
+        engine.set_replay_mode(0)
+    c = oracle.ransac(kp1, kp2, mt, iters=iters, seed=12345)
+    assert np.array_equal(g["samples"], c["samples"][:iters])
+    assert np.array_equal(g["counts"], c["counts"][:iters])
+    assert g["ok"] == c["ok"] and (not c["ok"] or np.array_equal(bits(g["H"]), bits(c["H"])))
+
+
+def test_resident_band_miss_is_detected_and_rerun(oracle):
+    """narrow bands (PANO_REPLAY_Z=0.3 -> 0.6 sigma) make paths leave their band; the kernel must report
+    it and the engine re-plan wider, never return guessed samples"""
+    import subprocess
+    import sys
+    import textwrap
+    import os
+    from conftest import ROOT, PKG
+    code = textwrap.dedent('''
+        import sys, importlib, numpy as np
+        sys.path.insert(0, %r)
+        pkg = importlib.import_module(%r); synth = importlib.import_module(%r + ".synth")
+        from oracle.oracle import Oracle
+        O = Oracle(); eng = pkg.Engine(0, 12345); eng.set_replay_mode(1)
+        left, right, _ = synth.make_pair(960, 540, seed=267)
+        kl, kr = O.detect(left), O.detect(right); m = O.match(kr, kl, right, left)
+        g = eng.computeHomography(kr, kl, m, details=True); c = O.ransac(kr, kl, m, seed=12345)
+        assert np.array_equal(g["samples"], c["samples"]) and np.array_equal(g["counts"], c["counts"])
+        print("OK", len(m))
+    ''') % (ROOT, PKG, PKG)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       env=dict(os.environ, PANO_REPLAY_Z="0.3"))
+    assert p.returncode == 0 and "OK" in p.stdout, p.stderr[-800:]

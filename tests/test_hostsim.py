@@ -80,3 +80,45 @@ def test_replay_total_draws_match_oracle_ransac(hostsim, oracle, small_pair):
     st = hostsim.hs_replay(C.c_uint32(12345), C.c_uint32(len(m)), 1000, 1, p(samples, C.c_int32), C.byref(end), None)
     assert st == 0 and end.value == r["draws"]
     assert np.array_equal(samples, r["samples"])
+
+
+@pytest.mark.parametrize("n,iters", [(4, 64), (5, 64), (6, 64), (7, 64), (8, 64), (9, 33), (10, 100), (33, 100),
+                                     (256, 300), (257, 300), (1000, 1000), (2500, 1000), (4097, 600),
+                                     (10774, 300), (10837, 200), (20001, 40)])
+def test_resident_replay_matches_std_shuffle(hostsim, oracle, n, iters):
+    """replay_resident_kernel's formulation (banded rejection cells from the exact start of every
+    iteration, segment walks, chain, max-element tracking) == real std::shuffle."""
+    ref = oracle.shuffle_iota(12345, n, reps=iters)
+    samples = np.zeros((iters, 4), np.int32)
+    end = C.c_uint64(0)
+    end2 = C.c_uint64(0)
+    stats = np.zeros(8)
+    st = hostsim.hs_replay_resident(C.c_uint32(12345), C.c_uint32(n), iters, 1, C.c_double(0.0), p(samples, C.c_int32),
+                                    C.byref(end), p(stats, C.c_double))
+    assert st == 0, (st, stats)
+    assert np.array_equal(samples, ref)
+    # same total number of engine outputs as the chunked formulation
+    s2 = np.zeros((iters, 4), np.int32)
+    assert hostsim.hs_replay(C.c_uint32(12345), C.c_uint32(n), iters, 1, p(s2, C.c_int32), C.byref(end2), None) == 0
+    assert end.value == end2.value and np.array_equal(s2, samples)
+
+
+def test_resident_replay_band_miss_is_detected(hostsim, oracle):
+    """a band that is too narrow must be reported (status 1), never silently produce samples;
+    doubling the margins (window_scale) recovers the exact result."""
+    n, iters = 9000, 400
+    samples = np.zeros((iters, 4), np.int32)
+    st = hostsim.hs_replay_resident(C.c_uint32(7), C.c_uint32(n), iters, 1, C.c_double(0.6), p(samples, C.c_int32), None, None)
+    assert st == 1
+    for scale in (2, 4, 8, 16):
+        st = hostsim.hs_replay_resident(C.c_uint32(7), C.c_uint32(n), iters, scale, C.c_double(0.6), p(samples, C.c_int32), None, None)
+        if st == 0:
+            break
+    assert st == 0
+    assert np.array_equal(samples, oracle.shuffle_iota(7, n, reps=iters))
+
+
+def test_resident_plan_limits(hostsim):
+    """the single-draw regime (n > 65535) and bands wider than a byte of diagonals stay on the chunked path"""
+    samples = np.zeros((4, 4), np.int32)
+    assert hostsim.hs_replay_resident(C.c_uint32(1), C.c_uint32(70000), 4, 1, C.c_double(0.0), p(samples, C.c_int32), None, None) == 32

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=267)
     ap.add_argument("--matcher", type=int, default=0)
+    ap.add_argument("--replay", type=int, default=0, help="0 chunked, 1 resident")
     a = ap.parse_args()
     w, h = [int(v) for v in a.size.split("x")]
     import torch
@@ -41,6 +42,7 @@ def main():
     L, R = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
     eng = pkg.Engine(0, 12345)
     eng.set_matcher(a.matcher)
+    eng.set_replay_mode(a.replay)
     for i in range(a.reps):
         n0 = eng.kernel_launches()
         _, r = eng.stitchTwoImages(L, R, fetch=False)

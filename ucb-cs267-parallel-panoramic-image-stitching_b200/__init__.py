@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "pano_harris_response", "pano_convolve_f64", "pano_match", "pano_ransac", "pano_canvas_geometry",
     "pano_warp_overlay", "pano_warp_perspective", "pano_stitch_pair", "pano_get_canvas", "pano_canvas_device",
     "pano_stitch_fold", "pano_stitch_batch", "pano_stream", "pano_pair_homography", "pano_mul33",
-    "pano_chain_geometry", "pano_warp_accumulate", "pano_set_stream",
+    "pano_chain_geometry", "pano_warp_accumulate", "pano_set_stream", "pano_set_replay_mode",
 ]
 
 
@@ -168,6 +168,10 @@ class Engine:
     def set_matcher(self, which):
         """0 = tensor-core matcher (product), 1 = SIMT cross-check kernel"""
         self._check(self.lib.pano_set_matcher(self.ctx, int(which)))
+
+    def set_replay_mode(self, mode):
+        """0 = chunked speculative shuffle replay (lowest latency), 1 = resident one-CTA replay (least work)"""
+        self._check(self.lib.pano_set_replay_mode(self.ctx, int(mode)))
 
     def kernel_launches(self):
         return int(self.lib.pano_kernel_launches(self.ctx))

@@ -154,7 +154,8 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
                            const pano_dmatch* matches_dev, int m, const pano_ransac_opts& o,
                            uint32_t seed, MtStream& mt, RansacScratch& s, PinnedBuf& pin,
                            int32_t* samples_out_host, int32_t* counts_out_host,
-                           uint8_t* mask_out_host, int window_scale, double replay_target);
+                           uint8_t* mask_out_host, int window_scale, double replay_target,
+                           int replay_mode);
 
 void warp_overlay_device(cudaStream_t st, const DevImage& left, const DevImage& right,
                          const CanvasGeom& g, uint8_t* canvas, size_t canvas_stride);

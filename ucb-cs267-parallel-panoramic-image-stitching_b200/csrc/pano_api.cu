@@ -21,6 +21,7 @@ struct pano_ctx {
   uint32_t seed = 0;
   int matcher = 0;  // 0 tensor-core, 1 SIMT
   double replay_target = 0;  // candidate walks per replay chunk (0 = default)
+  int replay_mode = 0;       // 0: chunked speculative replay (lowest latency), 1: resident one-CTA replay (least work)
   cudaStream_t st = nullptr;
   bool owns_stream = true;
   std::string err;
@@ -134,7 +135,7 @@ RansacResult ransac_retry(pano_ctx* c, const int32_t* kp1, const int32_t* kp2, c
   int scale = 1;
   for (;;) {
     r = ransac_device(c->st, kp1, kp2, m, n, o, c->seed, c->mt, c->rs, c->pin, samples, counts, mask, scale,
-                      c->replay_target);
+                      c->replay_target, c->replay_mode);
     if (r.status >= 0 || scale >= 16) break;
     scale *= 2;  // a speculation window was missed: re-run wider (exactness is never traded)
   }
@@ -302,6 +303,12 @@ int pano_set_seed(pano_ctx* c, uint32_t seed) {
 int pano_set_matcher(pano_ctx* c, int which) {
   if (!c || (which != 0 && which != 1)) return PANO_ERR_INVALID;
   c->matcher = which;
+  return PANO_OK;
+}
+
+int pano_set_replay_mode(pano_ctx* c, int mode) {
+  if (!c || (mode != 0 && mode != 1)) return PANO_ERR_INVALID;
+  c->replay_mode = mode;
   return PANO_OK;
 }
 
@@ -671,6 +678,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
     l->seed = c->seed;
     l->matcher = c->matcher;
     l->replay_target = n_lanes > 1 ? 16000.0 : 0.0;
+    l->replay_mode = n_lanes > 1 ? 1 : c->replay_mode;   // overlapped pairs: the one-CTA replay leaves the GPU to the other lanes
     try {
       PANO_CUDA(cudaSetDevice(l->device));
       for (int i = li; i < n; i += n_lanes) {

@@ -307,6 +307,204 @@ __global__ void combine_samples_kernel(const int4* __restrict__ seg_w, int iters
 }
 
 // ---------------------------------------------------------------------------------------
+// K5, resident formulation: ONE CTA replays all iterations strictly in order.  Every iteration
+// starts from its exact stream offset, so the only unknown is the number of rejections so far
+// inside the iteration; the cells of a narrow band of diagonals around its expectation are
+// evaluated (about 20x fewer than the chunked replay's windows over start offsets), at the price
+// of ~num_iterations sequential phases inside the CTA.  It occupies one SM, which is what makes
+// it the throughput-mode replay: independent pairs on other lanes fill the rest of the GPU.
+//   phase 1  lane = step, loop over the band's diagonals: ballot packs 32 steps of one diagonal
+//            into a word (same bit layout as the chunked cell grid)
+//   phase 2  one thread per (walk segment, entry diagonal): exit diagonal + diagonal at every block
+//   phase 3  thread 0 chains the segments from diagonal 0 (exact; leaving the band is detected)
+//   phase 4  thread per step: accepted draw -> swap targets; position p ends up holding the LARGEST
+//            element index written to it (writes happen in increasing element order), the swaps
+//            among the first four elements are replayed exactly by one thread
+// The stream window of the next iteration is prefetched with cp.async while the current one runs.
+// ---------------------------------------------------------------------------------------
+constexpr int RES_THREADS = 1024;
+
+struct ResParams {
+  const uint32_t* X;
+  unsigned long long x_limit;   // readable stream words (generated + guard)
+  const RT* rt;
+  const ResBlock* blk;
+  const uint32_t* seg_eoff;
+  uint32_t n, steps, nkb, nwords, dmax, segb, nseg, n_entries, xcap;
+  int iters;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(RES_THREADS, 1)
+replay_resident_kernel(ResParams P, ReplayCtl* ctl, int4* __restrict__ samples) {
+  extern __shared__ __align__(16) uint8_t res_smem[];
+  uint32_t* Xs0 = reinterpret_cast<uint32_t*>(res_smem);
+  uint32_t* Xs1 = Xs0 + P.xcap;
+  uint32_t* bits = Xs1 + P.xcap;
+  ResBlock* sblk = reinterpret_cast<ResBlock*>(bits + P.nwords + (P.nwords & 1u));
+  int2* s_segc = reinterpret_cast<int2*>(sblk + P.nkb);           // per segment: (entry base - dlo, dlo | w << 16)
+  uint32_t* s_entry = reinterpret_cast<uint32_t*>(s_segc + P.nseg + 1);
+  uint8_t* dtab = reinterpret_cast<uint8_t*>(s_entry + P.nseg + 1);
+  __shared__ int s_slot[4], s_init[4];
+  __shared__ RT s_rt4[4];
+  __shared__ uint32_t s_rej;
+  __shared__ int s_flag;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t steps = P.steps, odd = P.n & 1u, stride = P.segb + 1u;
+  for (uint32_t i = tid; i < P.nkb; i += RES_THREADS) sblk[i] = P.blk[i];
+  for (uint32_t i = tid; i < P.nseg; i += RES_THREADS) {
+    const ResBlock B0 = P.blk[i * P.segb];
+    s_segc[i] = make_int2((int)P.seg_eoff[i] - (int)B0.dlo, (int)((uint32_t)B0.dlo | ((uint32_t)B0.w << 16)));
+  }
+  if (tid < 4) { s_slot[tid] = -1; s_rt4[tid] = P.rt[tid]; }   // (rt is padded by 8 entries)
+  if (tid == 0) s_flag = 0;
+  // this thread's (segment, entry diagonal) of phase 2: the plan is the same for every iteration
+  int my_seg = -1;
+  uint32_t my_d = 0;
+  if ((uint32_t)tid < P.n_entries) {
+    uint32_t sgm = 0;
+    while (P.seg_eoff[sgm + 1] <= (uint32_t)tid) sgm++;
+    my_seg = (int)sgm;
+    my_d = P.blk[sgm * P.segb].dlo + ((uint32_t)tid - P.seg_eoff[sgm]);
+  }
+  // this lane's steps of phase 1 (blocks warp, warp + 32, ...): range / threshold stay in registers
+  RT q[RES_MAXB];
+#pragma unroll
+  for (uint32_t i = 0; i < RES_MAXB; i++) {
+    const uint32_t k = (warp + 32u * i) * 32u + lane;
+    q[i].r = 2u; q[i].T = 0u;                // steps past the end never reject
+    if (k < steps) q[i] = P.rt[k];
+  }
+
+  unsigned long long s = ctl->base;          // exact stream offset of the current iteration
+  unsigned long long xb = s & ~3ull;         // stream offset of word 0 of the current window
+  uint32_t* Xc = Xs0;
+  uint32_t* Xn = Xs1;
+  if (xb + P.xcap > P.x_limit) {
+    if (tid == 0) atomicOr(&ctl->status, 2);
+    return;
+  }
+  for (uint32_t c = tid; c < P.xcap / 4u; c += RES_THREADS) cp_async16(Xc + 4u * c, P.X + xb + 4u * c);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  for (int t = 0; t < P.iters; t++) {
+    const uint32_t rel = (uint32_t)(s - xb);
+    // ---- prefetch: the next iteration starts in [s + steps, s + steps + dmax)
+    const unsigned long long nb = (s + steps) & ~3ull;
+    if (t + 1 < P.iters) {
+      if (nb + P.xcap > P.x_limit) {
+        if (tid == 0) { atomicOr(&ctl->status, 2); s_flag = 1; }
+      } else {
+        for (uint32_t c = tid; c < P.xcap / 4u; c += RES_THREADS) cp_async16(Xn + 4u * c, P.X + nb + 4u * c);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // ---- phase 1: rejection cells of the band (lane = step, one ballot word per diagonal)
+#pragma unroll
+    for (uint32_t i = 0; i < RES_MAXB; i++) {
+      const uint32_t b = warp + 32u * i;
+      if (b < P.nkb) {
+        const ResBlock B = sblk[b];
+        const uint32_t* px = Xc + rel + b * 32u + lane + B.dlo;
+        uint32_t* out = bits + B.woff;
+        const uint32_t r = q[i].r, T = q[i].T, w = B.w;
+        uint32_t j = 0;
+        for (; j + 4u <= w; j += 4u) {
+          const uint32_t x0 = px[j], x1 = px[j + 1], x2 = px[j + 2], x3 = px[j + 3];
+          const uint32_t w0 = __ballot_sync(0xffffffffu, x0 * r < T);
+          const uint32_t w1 = __ballot_sync(0xffffffffu, x1 * r < T);
+          const uint32_t w2 = __ballot_sync(0xffffffffu, x2 * r < T);
+          const uint32_t w3 = __ballot_sync(0xffffffffu, x3 * r < T);
+          if (lane == 0) { out[j] = w0; out[j + 1] = w1; out[j + 2] = w2; out[j + 3] = w3; }
+        }
+        for (; j < w; j++) {
+          const uint32_t w0 = __ballot_sync(0xffffffffu, px[j] * r < T);
+          if (lane == 0) out[j] = w0;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: segment walks for every entry diagonal
+    if (my_seg >= 0) {
+      const uint32_t b0 = (uint32_t)my_seg * P.segb, b1 = min(P.nkb, b0 + P.segb);
+      uint8_t* out = dtab + (size_t)tid * stride;
+      out[P.segb] = (uint8_t)res_walk_segment(bits, sblk, b0, b1, my_d, out);
+    }
+    __syncthreads();
+
+    // ---- phase 3: chain from diagonal 0 (thread 0); exact swaps among the first four elements (thread 32)
+    if (tid == 0) {
+      uint32_t d = 0;
+      bool bad = false;
+      for (uint32_t sgm = 0; sgm < P.nseg; sgm++) {
+        const int2 c = s_segc[sgm];
+        const uint32_t dlo = (uint32_t)c.y & 0xffffu, w = (uint32_t)c.y >> 16;
+        if (d - dlo >= w) { bad = true; break; }
+        const uint32_t ent = (uint32_t)(c.x + (int)d);
+        s_entry[sgm] = ent;
+        d = dtab[(size_t)ent * stride + P.segb];
+        if (d == RES_MISS) { bad = true; break; }
+      }
+      s_rej = d;
+      if (bad) { atomicOr(&ctl->status, 1); s_flag = 1; }
+    } else if (tid == 32) {
+      int a0 = 0, a1 = 1, a2 = 2, a3 = 3;
+      uint32_t o = rel;
+      for (uint32_t k = 0; k < steps && 2u * k + odd < 4u; k++) {
+        int a[4] = {a0, a1, a2, a3};
+        track_step<true>(Xc, o, k, P.n, s_rt4, a);
+        a0 = a[0]; a1 = a[1]; a2 = a[2]; a3 = a[3];
+      }
+      s_init[0] = a0; s_init[1] = a1; s_init[2] = a2; s_init[3] = a3;
+    }
+    __syncthreads();
+    if (s_flag) break;
+
+    // ---- phase 4: swap targets of every step's accepted draw (a warp works on one block at a time)
+#pragma unroll 2
+    for (uint32_t b = warp; b < P.nkb; b += RES_THREADS / 32) {
+      const uint32_t k = b * 32u + lane;
+      const uint32_t idx = 2u * k + odd;
+      if (k >= steps || idx < 4u) continue;
+      const ResBlock B = sblk[b];
+      const uint32_t d0 = dtab[(size_t)s_entry[B.seg] * stride + B.boff];
+      const uint32_t dk = res_diag_at(bits, B, d0, lane);
+      const uint32_t x = Xc[rel + k + dk];
+      const unsigned long long u = (unsigned long long)x * (idx + 1u);
+      const unsigned long long v = (unsigned long long)(uint32_t)u * (idx + 2u);
+      const uint32_t p1 = (uint32_t)(u >> 32), p2 = (uint32_t)(v >> 32);
+      if (p1 < 4u) atomicMax(&s_slot[p1], (int)idx);
+      if (p2 < 4u) atomicMax(&s_slot[p2], (int)idx + 1);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      int4 r;
+      r.x = s_slot[0] >= 0 ? s_slot[0] : s_init[0];
+      r.y = s_slot[1] >= 0 ? s_slot[1] : s_init[1];
+      r.z = s_slot[2] >= 0 ? s_slot[2] : s_init[2];
+      r.w = s_slot[3] >= 0 ? s_slot[3] : s_init[3];
+      samples[t] = r;
+      s_slot[0] = s_slot[1] = s_slot[2] = s_slot[3] = -1;
+    }
+    s += (unsigned long long)steps + s_rej;
+    xb = nb;
+    uint32_t* tmp = Xc; Xc = Xn; Xn = tmp;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (tid == 0 && !s_flag) ctl->base = s;
+}
+
+// ---------------------------------------------------------------------------------------
 // K6 / K7
 // ---------------------------------------------------------------------------------------
 __global__ void build_points_kernel(const int32_t* __restrict__ kp1, const int32_t* __restrict__ kp2,
@@ -675,7 +873,8 @@ void mt_ensure(cudaStream_t st, MtStream& mt, uint32_t seed, uint64_t need, uint
 RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_t* kp2_dev,
                            const pano_dmatch* matches_dev, int m, const pano_ransac_opts& o, uint32_t seed,
                            MtStream& mt, RansacScratch& s, PinnedBuf& pin, int32_t* samples_out_host,
-                           int32_t* counts_out_host, uint8_t* mask_out_host, int window_scale, double replay_target) {
+                           int32_t* counts_out_host, uint8_t* mask_out_host, int window_scale, double replay_target,
+                           int replay_mode) {
   RansacResult res;
   memset(&res, 0, sizeof res);
   res.best_iter = -1;
@@ -705,17 +904,27 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   }();
   // plans depend only on (M, iterations, window scale, chunk target): keep the most recent ones
   struct PlanKey { uint32_t n; int iters, scale; double target; };
-  thread_local std::vector<std::pair<PlanKey, ReplayPlan>> plan_cache;
-  const ReplayPlan* plan_ptr = nullptr;
+  struct Plans { ReplayPlan chunked; ResidentPlan resident; };
+  thread_local std::vector<std::pair<PlanKey, Plans>> plan_cache;
+  const Plans* plan_ptr = nullptr;
   for (auto& e : plan_cache)
     if (e.first.n == n && e.first.iters == iters && e.first.scale == window_scale && e.first.target == target_cand)  // (z_sigma is process-constant)
       plan_ptr = &e.second;
   if (!plan_ptr) {
     if (plan_cache.size() >= 8) plan_cache.erase(plan_cache.begin());
-    plan_cache.emplace_back(PlanKey{n, iters, window_scale, target_cand}, plan_replay(n, iters, window_scale, target_cand, z_sigma));
+    Plans np;
+    np.chunked = plan_replay(n, iters, window_scale, target_cand, z_sigma);
+    np.resident = plan_resident(np.chunked, n, window_scale, z_sigma + 0.3);
+    plan_cache.emplace_back(PlanKey{n, iters, window_scale, target_cand}, std::move(np));
     plan_ptr = &plan_cache.back().second;
   }
-  const ReplayPlan& plan = *plan_ptr;
+  const ReplayPlan& plan = plan_ptr->chunked;
+  const ResidentPlan& rplan = plan_ptr->resident;
+  static const int env_mode = [] {   // PANO_REPLAY_MODE: 0 chunked, 1 resident (overrides the context's choice)
+    const char* e = getenv("PANO_REPLAY_MODE");
+    return e ? atoi(e) : -1;
+  }();
+  const bool resident = ((env_mode >= 0 ? env_mode : replay_mode) == 1) && rplan.ok;
   const std::vector<WinEntry>& win = plan.win;
   const int G = plan.G;
   const uint32_t n_cand = plan.n_cand, max_w = plan.max_w;
@@ -728,14 +937,15 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   // ---- buffers ---------------------------------------------------------------------------
   const int nseg = (int)((steps + PANO_SEG_STEPS - 1) / PANO_SEG_STEPS);
   s.thr.reserve(sizeof(RT) * plan.rt.size());
-  s.plan.reserve(sizeof(WinEntry) * win.size());
+  s.plan.reserve(std::max(sizeof(WinEntry) * win.size(),
+                          sizeof(ResBlock) * (size_t)rplan.nkb + sizeof(uint32_t) * ((size_t)rplan.nseg + 2)));
   s.cand_off.reserve(sizeof(uint32_t) * (size_t)n_cand * (size_t)std::max(nseg, 1));  // end + (nseg-1) boundaries
   s.cand_samp.reserve(sizeof(unsigned long long) * ((size_t)n_chunks * G * nseg + 1));  // segment start table
   s.base.reserve(sizeof(ReplayCtl));
   const uint32_t nkb = (steps + 31u) / 32u;
   const int n_dblocks = (int)plan.diag_block_iter.size();
   s.pts_bits.reserve(sizeof(uint32_t) * (size_t)plan.n_diag * nkb + sizeof(int) * (size_t)n_dblocks + 256);
-  s.samples.reserve(sizeof(int4) * ((size_t)n_chunks * G * (nseg + 1)));
+  s.samples.reserve(sizeof(int4) * std::max((size_t)n_chunks * G * (nseg + 1), (size_t)iters));
   s.pts.reserve(sizeof(float4) * (size_t)m);
   s.Hs.reserve(sizeof(double) * 9 * (size_t)iters);
   s.valid.reserve(sizeof(int) * (size_t)iters);
@@ -745,11 +955,13 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   pin.reserve(sizeof(SelectOut) + 64);
 
   PANO_CUDA(cudaMemcpyAsync(s.thr.p, plan.rt.data(), sizeof(RT) * plan.rt.size(), cudaMemcpyHostToDevice, st));
-  PANO_CUDA(cudaMemcpyAsync(s.plan.p, win.data(), sizeof(WinEntry) * win.size(), cudaMemcpyHostToDevice, st));
+  if (!resident)
+    PANO_CUDA(cudaMemcpyAsync(s.plan.p, win.data(), sizeof(WinEntry) * win.size(), cudaMemcpyHostToDevice, st));
   PANO_CUDA(cudaMemsetAsync(s.base.p, 0, sizeof(ReplayCtl), st));
   uint32_t* bits = s.pts_bits.as<uint32_t>();
   int* dbi = reinterpret_cast<int*>(bits + (size_t)plan.n_diag * nkb);
-  PANO_CUDA(cudaMemcpyAsync(dbi, plan.diag_block_iter.data(), sizeof(int) * (size_t)n_dblocks, cudaMemcpyHostToDevice, st));
+  if (!resident)
+    PANO_CUDA(cudaMemcpyAsync(dbi, plan.diag_block_iter.data(), sizeof(int) * (size_t)n_dblocks, cudaMemcpyHostToDevice, st));
   ReplayCtl* ctl = s.base.as<ReplayCtl>();
   int* status_ptr = &ctl->status;
   uint32_t* cand_end = s.cand_off.as<uint32_t>();
@@ -761,36 +973,57 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   build_points_kernel<<<(m + 255) / 256, 256, 0, st>>>(kp1_dev, kp2_dev, matches_dev, m, s.pts.as<float4>());
   PANO_LAUNCH_CHECK();
 
-  size_t chain_smem = (size_t)n_cand * sizeof(uint32_t) <= CHAIN_SMEM_MAX ? (size_t)n_cand * sizeof(uint32_t) : 0;
-  PANO_CUDA(cudaFuncSetAttribute(replay_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
-  for (int c = 0; c < n_chunks; c++) {
-    int Gc = std::min(G, iters - c * G);
-    dim3 grid((max_w + RW_THREADS - 1) / RW_THREADS, Gc);
-    {
-      long long warps = (long long)Gc * nkb;
-      replay_cells_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(mt.x.as<uint32_t>(), steps, s.thr.as<RT>(),
-                                                                      s.plan.as<WinEntry>(), Gc, nkb, plan.dextra, ctl,
-                                                                      bits, mt.len + mt.guard - 64);
+  if (resident) {
+    // one CTA, iterations in order from exact offsets (throughput mode: leaves the other SMs to other pairs)
+    ResBlock* blk_dev = s.plan.as<ResBlock>();
+    uint32_t* eoff_dev = reinterpret_cast<uint32_t*>(blk_dev + rplan.nkb);
+    PANO_CUDA(cudaMemcpyAsync(blk_dev, rplan.blk.data(), sizeof(ResBlock) * rplan.nkb, cudaMemcpyHostToDevice, st));
+    PANO_CUDA(cudaMemcpyAsync(eoff_dev, rplan.seg_eoff.data(), sizeof(uint32_t) * (rplan.nseg + 1), cudaMemcpyHostToDevice, st));
+    ResParams rp;
+    rp.X = mt.x.as<uint32_t>();
+    rp.x_limit = mt.len + mt.guard;
+    rp.rt = s.thr.as<RT>();
+    rp.blk = blk_dev;
+    rp.seg_eoff = eoff_dev;
+    rp.n = n; rp.steps = steps; rp.nkb = rplan.nkb; rp.nwords = rplan.nwords; rp.dmax = rplan.dmax;
+    rp.segb = rplan.segb; rp.nseg = rplan.nseg; rp.n_entries = rplan.n_entries; rp.xcap = rplan.xcap;
+    rp.iters = iters;
+    PANO_CUDA(cudaFuncSetAttribute(replay_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)RES_SMEM_BUDGET));
+    replay_resident_kernel<<<1, RES_THREADS, rplan.smem_bytes, st>>>(rp, ctl, samples_dev);
+    PANO_LAUNCH_CHECK();
+  } else {
+    size_t chain_smem = (size_t)n_cand * sizeof(uint32_t) <= CHAIN_SMEM_MAX ? (size_t)n_cand * sizeof(uint32_t) : 0;
+    PANO_CUDA(cudaFuncSetAttribute(replay_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHAIN_SMEM_MAX));
+    for (int c = 0; c < n_chunks; c++) {
+      int Gc = std::min(G, iters - c * G);
+      dim3 grid((max_w + RW_THREADS - 1) / RW_THREADS, Gc);
+      {
+        long long warps = (long long)Gc * nkb;
+        replay_cells_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(mt.x.as<uint32_t>(), steps, s.thr.as<RT>(),
+                                                                        s.plan.as<WinEntry>(), Gc, nkb, plan.dextra, ctl,
+                                                                        bits, mt.len + mt.guard - 64);
+        PANO_LAUNCH_CHECK();
+      }
+      replay_walk_bits_kernel<<<grid, RW_THREADS, 0, st>>>(steps, s.plan.as<WinEntry>(), nkb, plan.dextra, ctl, bits,
+                                                           cand_end, seg_off, (int)n_cand, mt.len);
+      PANO_LAUNCH_CHECK();
+      replay_chain_kernel<<<1, 1024, chain_smem, st>>>(s.plan.as<WinEntry>(), Gc, steps, cand_end, seg_off, (int)n_cand,
+                                                      nseg, ctl, seg_tab + (size_t)c * G * nseg);
       PANO_LAUNCH_CHECK();
     }
-    replay_walk_bits_kernel<<<grid, RW_THREADS, 0, st>>>(steps, s.plan.as<WinEntry>(), nkb, plan.dextra, ctl, bits,
-                                                         cand_end, seg_off, (int)n_cand, mt.len);
-    PANO_LAUNCH_CHECK();
-    replay_chain_kernel<<<1, 1024, chain_smem, st>>>(s.plan.as<WinEntry>(), Gc, steps, cand_end, seg_off, (int)n_cand,
-                                                    nseg, ctl, seg_tab + (size_t)c * G * nseg);
-    PANO_LAUNCH_CHECK();
-  }
-  {
-    int nthr = iters * nseg;
-    if (pairs)
-      replay_segments_kernel<true><<<(nthr + 63) / 64, 64, 0, st>>>(mt.x.as<uint32_t>(), n, steps, s.thr.as<RT>(), seg_tab,
-                                                                    iters, nseg, ctl, seg_w);
-    else
-      replay_segments_kernel<false><<<(nthr + 63) / 64, 64, 0, st>>>(mt.x.as<uint32_t>(), n, steps, s.thr.as<RT>(), seg_tab,
-                                                                     iters, nseg, ctl, seg_w);
-    PANO_LAUNCH_CHECK();
-    combine_samples_kernel<<<(iters + 127) / 128, 128, 0, st>>>(seg_w, iters, nseg, samples_dev);
-    PANO_LAUNCH_CHECK();
+    {
+      int nthr = iters * nseg;
+      if (pairs)
+        replay_segments_kernel<true><<<(nthr + 63) / 64, 64, 0, st>>>(mt.x.as<uint32_t>(), n, steps, s.thr.as<RT>(), seg_tab,
+                                                                      iters, nseg, ctl, seg_w);
+      else
+        replay_segments_kernel<false><<<(nthr + 63) / 64, 64, 0, st>>>(mt.x.as<uint32_t>(), n, steps, s.thr.as<RT>(), seg_tab,
+                                                                       iters, nseg, ctl, seg_w);
+      PANO_LAUNCH_CHECK();
+      combine_samples_kernel<<<(iters + 127) / 128, 128, 0, st>>>(seg_w, iters, nseg, samples_dev);
+      PANO_LAUNCH_CHECK();
+    }
   }
 
   dlt_kernel<<<(iters + DLT_WARPS - 1) / DLT_WARPS, DLT_WARPS * 32, 0, st>>>(s.pts.as<float4>(), s.samples.as<int4>(), iters,

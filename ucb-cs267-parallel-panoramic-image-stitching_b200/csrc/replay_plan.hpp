@@ -99,4 +99,137 @@ inline ReplayPlan plan_replay(uint32_t n, int iters, int window_scale, double ta
   return P;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Resident replay (replay_resident_kernel): one CTA replays the iterations strictly in order,
+// so every iteration starts from its EXACT stream offset and the only speculation left is on
+// the number of rejections so far inside the iteration ("diagonal" d = rejections before the
+// current step).  Per 32-step block b only the diagonals [dlo, dlo + w) around the expected
+// count are evaluated (mean -+ z sigma of the rejections before / through the block, from the
+// exact per-step probabilities); a path that leaves its band is DETECTED (status bit 0) and the
+// caller re-plans with doubled margins, exactly like a window miss of the chunked replay.
+// ---------------------------------------------------------------------------------------
+struct alignas(8) ResBlock {
+  uint16_t dlo;   // first diagonal evaluated for this block
+  uint16_t w;     // number of diagonals
+  uint16_t woff;  // index of (diagonal dlo) in the iteration's word array: word(b, d) = bits[woff + d - dlo]
+  uint8_t seg;    // walk segment of this block
+  uint8_t boff;   // index of the block inside its segment
+};
+
+struct ResidentPlan {
+  bool ok = false;                // fits the kernel's shared-memory budget
+  uint32_t steps = 0, nkb = 0;    // Lemire steps per shuffle, 32-step blocks
+  uint32_t nwords = 0;            // bitmap words per iteration
+  uint32_t dmax = 0;              // diagonals are < dmax (max rejections per iteration the band admits + 1)
+  uint32_t segb = 0, nseg = 0;    // blocks per walk segment, segments
+  uint32_t n_entries = 0;         // sum over segments of the entry-band widths
+  uint32_t xcap = 0;              // stream words per shared-memory window
+  std::vector<ResBlock> blk;      // nkb entries
+  std::vector<uint32_t> seg_eoff; // nseg + 1: first entry index of each segment
+  size_t smem_bytes = 0;
+};
+
+constexpr uint32_t RES_MAX_DIAG = 250;        // diagonals are stored in bytes (255 = miss)
+constexpr uint32_t RES_MAXB = 12;             // 32-step blocks per warp of the kernel (32 warps): steps <= 12288
+constexpr size_t RES_SMEM_BUDGET = 200 * 1024;
+
+
+constexpr uint32_t RES_MISS = 255u;
+
+// Walk of blocks [b0, b1) over the evaluated rejection bits, entered on diagonal d: along a diagonal until
+// the next set bit (a rejection at that step), then the same step again on the next diagonal.  dout[i] =
+// diagonal on entering block b0 + i.  Returns the exit diagonal, or RES_MISS if the path leaves the band.
+PANO_HD uint32_t res_walk_segment(const uint32_t* bits, const ResBlock* blk, uint32_t b0, uint32_t b1, uint32_t d,
+                                  uint8_t* dout) {
+  for (uint32_t b = b0; b < b1; b++) {
+    const ResBlock B = blk[b];
+    if (d - (uint32_t)B.dlo >= (uint32_t)B.w) return RES_MISS;
+    dout[b - b0] = (uint8_t)d;
+    uint32_t mask = ~0u;
+    for (;;) {
+      const uint32_t w = bits[B.woff + d - B.dlo] & mask;
+      if (!w) break;
+      d++;
+      if (d - (uint32_t)B.dlo >= (uint32_t)B.w) return RES_MISS;
+      mask = ~0u << ctz32(w);
+    }
+  }
+  return d;
+}
+
+// Rejections at steps <= (block start + kbit) for a path that entered the block on diagonal d (a path the
+// segment walk has already validated): the accepted draw of that step is word (start + step + result).
+PANO_HD uint32_t res_diag_at(const uint32_t* bits, const ResBlock B, uint32_t d, uint32_t kbit) {
+  const uint32_t upto = kbit == 31u ? ~0u : ((2u << kbit) - 1u);
+  uint32_t mask = upto;
+  for (;;) {
+    const uint32_t w = bits[B.woff + d - B.dlo] & mask;
+    if (!w) break;
+    d++;
+    mask = (~0u << ctz32(w)) & upto;
+  }
+  return d;
+}
+
+inline size_t resident_smem_bytes(const ResidentPlan& R) {
+  size_t b = 0;
+  b += sizeof(uint32_t) * 2 * (size_t)R.xcap;                 // stream windows (double buffered)
+  b += sizeof(uint32_t) * (size_t)R.nwords;                   // rejection bitmap
+  b += sizeof(ResBlock) * (size_t)R.nkb;                      // band table
+  b += (size_t)R.n_entries * (R.segb + 1);                    // per entry: diagonal at each block + exit
+  b += sizeof(uint32_t) * 4 * (size_t)(R.nseg + 1);           // per segment: entry base, band, chosen entry
+  return b + 256;
+}
+
+inline ResidentPlan plan_resident(const ReplayPlan& P, uint32_t n, int window_scale, double z_sigma = 4.5) {
+  ResidentPlan R;
+  const uint32_t steps = shuffle_steps(n);
+  R.steps = steps;
+  if (!shuffle_uses_pairs(n) || steps == 0) return R;   // the single-draw regime (n > 65535) stays on the chunked path
+  const uint32_t nkb = (steps + 31u) / 32u;
+  R.nkb = nkb;
+  // cumulative mean / variance of the rejections before step k
+  std::vector<double> cm((size_t)steps + 1, 0.0), cv((size_t)steps + 1, 0.0);
+  for (uint32_t k = 0; k < steps; k++) {
+    const double p = (double)P.rt[k].T / 4294967296.0;
+    cm[k + 1] = cm[k] + p / (1.0 - p);
+    cv[k + 1] = cv[k] + p / ((1.0 - p) * (1.0 - p));
+  }
+  const double z = z_sigma * window_scale, pad = 1.0 * window_scale;
+  R.blk.resize(nkb);
+  uint32_t prev_lo = 0, prev_hi = 0, woff = 0;
+  for (uint32_t b = 0; b < nkb; b++) {
+    const uint32_t k0 = b * 32u, k1 = std::min(steps, k0 + 32u);
+    double lo = std::floor(cm[k0] - z * std::sqrt(cv[k0]) - pad);
+    double hi = std::ceil(cm[k1] + z * std::sqrt(cv[k1]) + pad);
+    if (lo < 0) lo = 0;
+    uint32_t ulo = std::max(prev_lo, (uint32_t)lo), uhi = std::max(prev_hi, (uint32_t)hi);
+    if (b == 0) ulo = 0;
+    if (uhi >= RES_MAX_DIAG) return R;
+    R.blk[b].dlo = (uint16_t)ulo;
+    R.blk[b].w = (uint16_t)(uhi - ulo + 1u);
+    if (woff > 0xffffu) return R;
+    R.blk[b].woff = (uint16_t)woff;
+    woff += R.blk[b].w;
+    prev_lo = ulo; prev_hi = uhi;
+  }
+  R.nwords = woff;
+  R.dmax = prev_hi + 1u;
+  // walk segments: about 16 per iteration (the chain over segments is sequential, the walks of a
+  // segment's entries are parallel)
+  R.segb = std::max(1u, (nkb + 15u) / 16u);
+  R.nseg = (nkb + R.segb - 1u) / R.segb;
+  for (uint32_t b = 0; b < nkb; b++) { R.blk[b].seg = (uint8_t)(b / R.segb); R.blk[b].boff = (uint8_t)(b % R.segb); }
+  R.seg_eoff.assign((size_t)R.nseg + 1, 0u);
+  for (uint32_t sgm = 0; sgm < R.nseg; sgm++) R.seg_eoff[sgm + 1] = R.seg_eoff[sgm] + R.blk[sgm * R.segb].w;
+  R.n_entries = R.seg_eoff[R.nseg];
+  // window of iteration t+1 is prefetched before iteration t's rejections are known:
+  // [s + steps, s + steps + dmax) are its possible starts, each needs steps + dmax + 32 words
+  R.xcap = (steps + 2u * R.dmax + 64u + 3u) / 4u * 4u + 8u;
+  R.smem_bytes = resident_smem_bytes(R);
+  R.ok = R.smem_bytes <= RES_SMEM_BUDGET && R.n_entries <= 1024u && nkb <= 32u * RES_MAXB && R.segb <= 255u;
+  return R;
+}
+
 }  // namespace pano
