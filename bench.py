@@ -17,6 +17,8 @@ BASELINE.json; P pairs = P*50 MB of input, larger than the 126 MB L2, rotating e
            itself needs OpenCV C++ and cannot be built here) on a bounded sample, rank 0 only.
 """
 import argparse
+import os as _os
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per batch lane (before CUDA starts)
 import importlib
 import json
 import os
@@ -182,7 +184,7 @@ def run_engine(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     # overlapped lanes per GPU: each has a (spin-waiting) host thread, so share the cores between ranks
-    lanes = int(os.environ.get("PANO_BATCH_LANES", max(2, min(8, (os.cpu_count() or 8) // max(world, 1)))))
+    lanes = int(os.environ.get("PANO_BATCH_LANES", max(2, min(16, (os.cpu_count() or 8) // max(world, 1)))))
     os.environ["PANO_BATCH_LANES"] = str(lanes)
     eng = pkg.Engine(device=local, seed=SEED)
     w, h, P = a.w, a.h, a.pairs

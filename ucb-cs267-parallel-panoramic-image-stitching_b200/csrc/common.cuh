@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -25,6 +27,18 @@ struct CudaError {
     cudaError_t e__ = (expr);                                            \
     if (e__ != cudaSuccess) throw ::pano::CudaError{e__, #expr, __FILE__, __LINE__}; \
   } while (0)
+
+// Host-side wait for a stream.  With more batch lanes than host cores (g_yield_wait > 0) the lanes must not
+// spin inside the driver: poll and sleep instead, so a lane costs a core only while it has host work to do.
+extern std::atomic<int> g_yield_wait;
+inline cudaError_t stream_wait(cudaStream_t st) {
+  if (g_yield_wait.load(std::memory_order_relaxed) <= 0) return cudaStreamSynchronize(st);
+  for (;;) {
+    const cudaError_t e = cudaStreamQuery(st);
+    if (e != cudaErrorNotReady) return e;
+    std::this_thread::sleep_for(std::chrono::microseconds(20));
+  }
+}
 
 // every engine kernel launch goes through this: counts it and surfaces launch errors
 extern std::atomic<uint64_t> g_kernel_launches;

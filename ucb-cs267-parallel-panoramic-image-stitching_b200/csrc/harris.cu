@@ -316,7 +316,7 @@ int harris_detect_device(cudaStream_t st, const DevImage& img, const pano_harris
   }
   exclusive_scan_u32(st, s.rowcnt.as<uint32_t>(), s.rowoff.as<uint32_t>(), h, s.total.as<uint32_t>());
   PANO_CUDA(cudaMemcpyAsync(pin.p, s.total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  PANO_CUDA(cudaStreamSynchronize(st));
+  PANO_CUDA(stream_wait(st));
   int n = (int)*pin.as<uint32_t>();
   kp.count = n;
   kp.xy.reserve(sizeof(int32_t) * 2 * (size_t)(n > 0 ? n : 1));

@@ -138,7 +138,7 @@ int build_descriptors_device(cudaStream_t st, const DevImage& img, const int32_t
   PANO_LAUNCH_CHECK();
   compact_flagged(st, s.flags.as<uint8_t>(), n, d.orig.as<int32_t>(), s.cnt.as<uint32_t>(), s.tmp);
   PANO_CUDA(cudaMemcpyAsync(pin.p, s.cnt.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  PANO_CUDA(cudaStreamSynchronize(st));
+  PANO_CUDA(stream_wait(st));
   int n_in = (int)*pin.as<uint32_t>();
   d.count = n_in;
   if (n_in == 0) return 0;
@@ -198,7 +198,7 @@ int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescr
   PANO_LAUNCH_CHECK();
   compact_flagged(st, s.mflags.as<uint8_t>(), nq, s.midx.as<int32_t>(), s.cnt.as<uint32_t>(), s.tmp);
   PANO_CUDA(cudaMemcpyAsync(pin.p, s.cnt.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  PANO_CUDA(cudaStreamSynchronize(st));
+  PANO_CUDA(stream_wait(st));
   int m = (int)*pin.as<uint32_t>();
   if (m > 0) {
     gather_matches_kernel<<<(m + 255) / 256, 256, 0, st>>>(s.mtmp.as<pano_dmatch>(), s.midx.as<int32_t>(), m, out_dev);

@@ -387,7 +387,7 @@ void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescript
     // first use on this process: make sure the pipeline ran to completion
     int e = 0;
     PANO_CUDA(cudaMemcpyAsync(&e, errbuf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    PANO_CUDA(cudaStreamSynchronize(st));
+    PANO_CUDA(stream_wait(st));
     if (e != 0) {
       g_tc_state = -1;
       throw CudaError{cudaErrorLaunchFailure, "tensor-core matcher pipeline timed out", __FILE__, __LINE__};

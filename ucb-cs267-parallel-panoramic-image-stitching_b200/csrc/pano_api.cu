@@ -11,6 +11,15 @@
 #include <thread>
 
 namespace pano {
+std::atomic<int> g_yield_wait{0};
+
+// Batch lanes are independent streams; with the default of 8 hardware work queues, streams alias onto the same
+// queue and a lane's kernels wait behind another lane's.  Has to be in the environment before the CUDA context
+// exists, so it is set when the library is loaded (an explicit setting wins).
+static const int g_env_init = [] {
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+  return 0;
+}();
 std::atomic<uint64_t> g_kernel_launches{0};
 }
 
@@ -329,7 +338,7 @@ int pano_detect(pano_ctx* c, const uint8_t* bgr, int w, int h, size_t stride, in
     PANO_CUDA(cudaMemcpyAsync(xy_out, c->kpL.xy.p, sizeof(int32_t) * 2 * (size_t)ncopy,
                               mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
   }
-  PANO_CUDA(cudaStreamSynchronize(c->st));
+  PANO_CUDA(stream_wait(c->st));
   return (xy_out && n > cap) ? PANO_ERR_CAPACITY : PANO_OK;
   API_CATCH(c)
 }
@@ -347,7 +356,7 @@ int pano_harris_response(pano_ctx* c, const uint8_t* bgr, int w, int h, size_t s
   }
   harris_response_device(c->st, img, k, dst);
   if (mem == PANO_MEM_HOST) PANO_CUDA(cudaMemcpyAsync(resp_out, dst, bytes, cudaMemcpyDeviceToHost, c->st));
-  PANO_CUDA(cudaStreamSynchronize(c->st));
+  PANO_CUDA(stream_wait(c->st));
   return PANO_OK;
   API_CATCH(c)
 }
@@ -367,7 +376,7 @@ int pano_convolve_f64(pano_ctx* c, const double* in, int w, int h, const double*
   }
   convolve_f64_device(c->st, din, w, h, dk, ksize, dout);
   if (mem == PANO_MEM_HOST) PANO_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, c->st));
-  PANO_CUDA(cudaStreamSynchronize(c->st));
+  PANO_CUDA(stream_wait(c->st));
   return PANO_OK;
   API_CATCH(c)
 }
@@ -391,7 +400,7 @@ int pano_match(pano_ctx* c, const int32_t* kp_query, int n_query, const int32_t*
   if (out && ncopy > 0)
     PANO_CUDA(cudaMemcpyAsync(out, c->matches.p, sizeof(pano_dmatch) * (size_t)ncopy,
                               mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
-  PANO_CUDA(cudaStreamSynchronize(c->st));
+  PANO_CUDA(stream_wait(c->st));
   return (out && m > cap) ? PANO_ERR_CAPACITY : PANO_OK;
   API_CATCH(c)
 }
@@ -448,7 +457,7 @@ int pano_warp_overlay(pano_ctx* c, const uint8_t* left, int wl, int hl, size_t s
     PANO_CUDA(cudaMemcpy2DAsync(canvas_out, canvas_stride, c->tmp[0].p, pitch, (size_t)g.cw * 3, g.ch,
                                 cudaMemcpyDeviceToHost, c->st));
   }
-  PANO_CUDA(cudaStreamSynchronize(c->st));
+  PANO_CUDA(stream_wait(c->st));
   return PANO_OK;
   API_CATCH(c)
 }
@@ -471,7 +480,7 @@ int pano_warp_perspective(pano_ctx* c, const uint8_t* src, int w, int h, size_t 
     warp_only_device(c->st, S, Minv, bw0, c->tmp[0].as<uint8_t>(), dw, dh, pitch);
     PANO_CUDA(cudaMemcpy2DAsync(dst, dstride, c->tmp[0].p, pitch, (size_t)dw * 3, dh, cudaMemcpyDeviceToHost, c->st));
   }
-  PANO_CUDA(cudaStreamSynchronize(c->st));
+  PANO_CUDA(stream_wait(c->st));
   return PANO_OK;
   API_CATCH(c)
 }
@@ -509,7 +518,7 @@ int pano_get_canvas(pano_ctx* c, uint8_t* out, size_t out_stride, size_t cap_byt
     return PANO_ERR_CAPACITY;
   PANO_CUDA(cudaMemcpy2DAsync(out, out_stride, c->canvas[c->cur].p, c->cstride, (size_t)c->cw * 3, c->ch,
                               mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
-  PANO_CUDA(cudaStreamSynchronize(c->st));
+  PANO_CUDA(stream_wait(c->st));
   return PANO_OK;
   API_CATCH(c)
 }
@@ -548,7 +557,7 @@ int pano_stitch_fold(pano_ctx* c, const uint8_t* const* images, const int* ws, c
     if (s == PANO_ERR_CUDA) return s;
     // any other failure: the reference logs and keeps the previous panorama (ref :404-407)
   }
-  PANO_CUDA(cudaStreamSynchronize(c->st));
+  PANO_CUDA(stream_wait(c->st));
   return PANO_OK;
   API_CATCH(c)
 }
@@ -631,7 +640,7 @@ int pano_warp_accumulate(pano_ctx* c, const uint8_t* src, int w, int h, size_t s
     PANO_CUDA(cudaMemcpy2DAsync(band, band_stride, c->tmp[0].p, pitch, (size_t)canvas_w * 3, band_h,
                                 cudaMemcpyDeviceToHost, c->st));
   }
-  PANO_CUDA(cudaStreamSynchronize(c->st));
+  PANO_CUDA(stream_wait(c->st));
   return PANO_OK;
   API_CATCH(c)
 }
@@ -659,8 +668,15 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
   }
   if (const char* e = getenv("PANO_BATCH_LANES")) n_lanes = atoi(e);
   if (n_lanes < 1) n_lanes = 1;
-  if (n_lanes > 8) n_lanes = 8;
+  if (n_lanes > 32) n_lanes = 32;
   if (n_lanes > n) n_lanes = n > 0 ? n : 1;
+  // lanes beyond the host cores (or PANO_YIELD_WAIT=1): waits poll and sleep instead of spinning in the driver
+  {
+    const unsigned hc = std::thread::hardware_concurrency();
+    const char* e = getenv("PANO_YIELD_WAIT");
+    const bool yield_wait = e ? atoi(e) != 0 : (hc > 0 && n_lanes + 1 > (int)hc);
+    g_yield_wait = yield_wait ? 1 : 0;
+  }
   while ((int)c->lanes.size() < n_lanes) {
     pano_ctx* l = nullptr;
     int s = pano_create(c->device, c->seed, &l);
@@ -670,7 +686,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
   cudaEvent_t e0, e1;
   PANO_CUDA(cudaEventCreate(&e0));
   PANO_CUDA(cudaEventCreate(&e1));
-  PANO_CUDA(cudaStreamSynchronize(c->st));
+  PANO_CUDA(stream_wait(c->st));
   PANO_CUDA(cudaEventRecord(e0, c->st));
   std::vector<int> lane_rc((size_t)n_lanes, PANO_OK);
   auto work = [&](int li) {
@@ -678,7 +694,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
     l->seed = c->seed;
     l->matcher = c->matcher;
     l->replay_target = n_lanes > 1 ? 16000.0 : 0.0;
-    l->replay_mode = n_lanes > 1 ? 1 : c->replay_mode;   // overlapped pairs: the one-CTA replay leaves the GPU to the other lanes
+    l->replay_mode = c->replay_mode;   // (resident = 1 pays off from ~32 lanes on: it trades latency for GPU time)
     try {
       PANO_CUDA(cudaSetDevice(l->device));
       for (int i = li; i < n; i += n_lanes) {
@@ -697,7 +713,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
           }
         }
       }
-      PANO_CUDA(cudaStreamSynchronize(l->st));
+      PANO_CUDA(stream_wait(l->st));
     } catch (const CudaError& e) {
       char buf[512];
       snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e.e, cudaGetErrorString(e.e), e.file, e.line,

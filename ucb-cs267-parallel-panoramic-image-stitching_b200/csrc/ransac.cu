@@ -346,7 +346,8 @@ replay_resident_kernel(ResParams P, ReplayCtl* ctl, int4* __restrict__ samples) 
   uint32_t* Xs1 = Xs0 + P.xcap;
   uint32_t* bits = Xs1 + P.xcap;
   ResBlock* sblk = reinterpret_cast<ResBlock*>(bits + P.nwords + (P.nwords & 1u));
-  int2* s_segc = reinterpret_cast<int2*>(sblk + P.nkb);           // per segment: (entry base - dlo, dlo | w << 16)
+  uint4* s_p1 = reinterpret_cast<uint4*>(sblk + P.nkb + (P.nkb & 1u));   // phase-1 view: (x offset, word offset, w / 4, -)
+  int2* s_segc = reinterpret_cast<int2*>(s_p1 + P.nkb);          // per segment: (entry base - dlo, dlo | w << 16)
   uint32_t* s_entry = reinterpret_cast<uint32_t*>(s_segc + P.nseg + 1);
   uint8_t* dtab = reinterpret_cast<uint8_t*>(s_entry + P.nseg + 1);
   __shared__ int s_slot[4], s_init[4];
@@ -356,7 +357,11 @@ replay_resident_kernel(ResParams P, ReplayCtl* ctl, int4* __restrict__ samples) 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t steps = P.steps, odd = P.n & 1u, stride = P.segb + 1u;
-  for (uint32_t i = tid; i < P.nkb; i += RES_THREADS) sblk[i] = P.blk[i];
+  for (uint32_t i = tid; i < P.nkb; i += RES_THREADS) {
+    const ResBlock B = P.blk[i];
+    sblk[i] = B;
+    s_p1[i] = make_uint4(i * 32u + B.dlo, B.woff, B.w >> 2, 0u);
+  }
   for (uint32_t i = tid; i < P.nseg; i += RES_THREADS) {
     const ResBlock B0 = P.blk[i * P.segb];
     s_segc[i] = make_int2((int)P.seg_eoff[i] - (int)B0.dlo, (int)((uint32_t)B0.dlo | ((uint32_t)B0.w << 16)));
@@ -407,27 +412,26 @@ replay_resident_kernel(ResParams P, ReplayCtl* ctl, int4* __restrict__ samples) 
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 
-    // ---- phase 1: rejection cells of the band (lane = step, one ballot word per diagonal)
+    // ---- phase 1: rejection cells of the band (lane = step, one ballot word per diagonal, 4 per trip)
+    {
+      const uint32_t* xl = Xc + rel + lane;
+      const bool lead = lane == 0;
 #pragma unroll
-    for (uint32_t i = 0; i < RES_MAXB; i++) {
-      const uint32_t b = warp + 32u * i;
-      if (b < P.nkb) {
-        const ResBlock B = sblk[b];
-        const uint32_t* px = Xc + rel + b * 32u + lane + B.dlo;
-        uint32_t* out = bits + B.woff;
-        const uint32_t r = q[i].r, T = q[i].T, w = B.w;
-        uint32_t j = 0;
-        for (; j + 4u <= w; j += 4u) {
-          const uint32_t x0 = px[j], x1 = px[j + 1], x2 = px[j + 2], x3 = px[j + 3];
-          const uint32_t w0 = __ballot_sync(0xffffffffu, x0 * r < T);
-          const uint32_t w1 = __ballot_sync(0xffffffffu, x1 * r < T);
-          const uint32_t w2 = __ballot_sync(0xffffffffu, x2 * r < T);
-          const uint32_t w3 = __ballot_sync(0xffffffffu, x3 * r < T);
-          if (lane == 0) { out[j] = w0; out[j + 1] = w1; out[j + 2] = w2; out[j + 3] = w3; }
-        }
-        for (; j < w; j++) {
-          const uint32_t w0 = __ballot_sync(0xffffffffu, px[j] * r < T);
-          if (lane == 0) out[j] = w0;
+      for (uint32_t i = 0; i < RES_MAXB; i++) {
+        const uint32_t b = warp + 32u * i;
+        if (b < P.nkb) {
+          const uint4 B = s_p1[b];
+          const uint32_t* px = xl + B.x;
+          uint32_t* out = bits + B.y;
+          const uint32_t r = q[i].r, T = q[i].T;
+          for (uint32_t j4 = B.z; j4 != 0; j4--, px += 4, out += 4) {
+            const uint32_t x0 = px[0], x1 = px[1], x2 = px[2], x3 = px[3];
+            const uint32_t w0 = __ballot_sync(0xffffffffu, x0 * r < T);
+            const uint32_t w1 = __ballot_sync(0xffffffffu, x1 * r < T);
+            const uint32_t w2 = __ballot_sync(0xffffffffu, x2 * r < T);
+            const uint32_t w3 = __ballot_sync(0xffffffffu, x3 * r < T);
+            if (lead) { out[0] = w0; out[1] = w1; out[2] = w2; out[3] = w3; }
+          }
         }
       }
     }
@@ -470,20 +474,27 @@ replay_resident_kernel(ResParams P, ReplayCtl* ctl, int4* __restrict__ samples) 
     if (s_flag) break;
 
     // ---- phase 4: swap targets of every step's accepted draw (a warp works on one block at a time)
+    {
+      const uint32_t* xl = Xc + rel + lane;
+      const uint32_t upto = lane == 31 ? ~0u : ((2u << lane) - 1u);
 #pragma unroll 2
-    for (uint32_t b = warp; b < P.nkb; b += RES_THREADS / 32) {
-      const uint32_t k = b * 32u + lane;
-      const uint32_t idx = 2u * k + odd;
-      if (k >= steps || idx < 4u) continue;
-      const ResBlock B = sblk[b];
-      const uint32_t d0 = dtab[(size_t)s_entry[B.seg] * stride + B.boff];
-      const uint32_t dk = res_diag_at(bits, B, d0, lane);
-      const uint32_t x = Xc[rel + k + dk];
-      const unsigned long long u = (unsigned long long)x * (idx + 1u);
-      const unsigned long long v = (unsigned long long)(uint32_t)u * (idx + 2u);
-      const uint32_t p1 = (uint32_t)(u >> 32), p2 = (uint32_t)(v >> 32);
-      if (p1 < 4u) atomicMax(&s_slot[p1], (int)idx);
-      if (p2 < 4u) atomicMax(&s_slot[p2], (int)idx + 1);
+      for (uint32_t b = warp; b < P.nkb; b += RES_THREADS / 32) {
+        const ResBlock B = sblk[b];
+        uint32_t d = dtab[s_entry[B.seg] * stride + B.boff];      // diagonal on entering the block (warp-uniform)
+        const uint32_t* wp = bits + B.woff - B.dlo;
+        uint32_t m = wp[d] & upto;
+        while (m) {                                               // rejections at steps <= mine: rare
+          d++;
+          m = wp[d] & upto & (~0u << (__ffs((int)m) - 1));
+        }
+        const uint32_t k = b * 32u + lane, idx = 2u * k + odd;
+        const uint32_t x = xl[b * 32u + d];
+        const uint32_t p1 = __umulhi(x, idx + 1u), p2 = __umulhi(x * (idx + 1u), idx + 2u);
+        if (min(p1, p2) < 4u && k < steps && idx >= 4u) {
+          if (p1 < 4u) atomicMax(&s_slot[p1], (int)idx);
+          if (p2 < 4u) atomicMax(&s_slot[p2], (int)idx + 1);
+        }
+      }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -849,7 +860,7 @@ void mt_ensure(cudaStream_t st, MtStream& mt, uint32_t seed, uint64_t need, uint
     DevBuf bigger;
     bigger.reserve(sizeof(uint32_t) * (std::max<uint64_t>(new_len, 2 * mt.len) + guard));
     PANO_CUDA(cudaMemcpyAsync(bigger.p, mt.x.p, sizeof(uint32_t) * mt.len, cudaMemcpyDeviceToDevice, st));
-    PANO_CUDA(cudaStreamSynchronize(st));
+    PANO_CUDA(stream_wait(st));
     mt.x.release();
     mt.x = bigger;
   }
@@ -1042,7 +1053,7 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   char* pp = pin.as<char>();
   PANO_CUDA(cudaMemcpyAsync(pp, s.result.p, sizeof(SelectOut), cudaMemcpyDeviceToHost, st));
   PANO_CUDA(cudaMemcpyAsync(pp + sizeof(SelectOut), status_ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
-  PANO_CUDA(cudaStreamSynchronize(st));
+  PANO_CUDA(stream_wait(st));
   SelectOut so;
   memcpy(&so, pp, sizeof so);
   int replay_status;
@@ -1063,7 +1074,7 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
     PANO_CUDA(cudaMemcpyAsync(counts_out_host, s.counts.p, sizeof(int) * (size_t)iters, cudaMemcpyDeviceToHost, st));
   if (mask_out_host)
     PANO_CUDA(cudaMemcpyAsync(mask_out_host, s.mask.p, (size_t)m, cudaMemcpyDeviceToHost, st));
-  if (samples_out_host || counts_out_host || mask_out_host) PANO_CUDA(cudaStreamSynchronize(st));
+  if (samples_out_host || counts_out_host || mask_out_host) PANO_CUDA(stream_wait(st));
   return res;
 }
 

@@ -140,20 +140,60 @@ constexpr uint32_t RES_MISS = 255u;
 // Walk of blocks [b0, b1) over the evaluated rejection bits, entered on diagonal d: along a diagonal until
 // the next set bit (a rejection at that step), then the same step again on the next diagonal.  dout[i] =
 // diagonal on entering block b0 + i.  Returns the exit diagonal, or RES_MISS if the path leaves the band.
+// The words of RES_LOOK consecutive blocks on the current diagonal are fetched together (most blocks hold no
+// rejection on a given diagonal), so the dependent-load chain is per batch, not per block.
+constexpr int RES_LOOK = 4;
 PANO_HD uint32_t res_walk_segment(const uint32_t* bits, const ResBlock* blk, uint32_t b0, uint32_t b1, uint32_t d,
                                   uint8_t* dout) {
-  for (uint32_t b = b0; b < b1; b++) {
-    const ResBlock B = blk[b];
-    if (d - (uint32_t)B.dlo >= (uint32_t)B.w) return RES_MISS;
-    dout[b - b0] = (uint8_t)d;
-    uint32_t mask = ~0u;
-    for (;;) {
-      const uint32_t w = bits[B.woff + d - B.dlo] & mask;
-      if (!w) break;
-      d++;
-      if (d - (uint32_t)B.dlo >= (uint32_t)B.w) return RES_MISS;
-      mask = ~0u << ctz32(w);
+  uint32_t b = b0, mask = ~0u;
+  bool fresh = true;   // block b has not been entered yet (its dout is still to be written)
+  while (b < b1) {
+    uint32_t wv[RES_LOOK];
+    bool inb[RES_LOOK];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < RES_LOOK; i++) {
+      const uint32_t bb = b + (uint32_t)i < b1 ? b + (uint32_t)i : b1 - 1u;
+      const ResBlock B = blk[bb];
+      const uint32_t r = d - (uint32_t)B.dlo;
+      inb[i] = r < (uint32_t)B.w;
+      wv[i] = inb[i] ? bits[B.woff + r] : 0u;
     }
+    wv[0] &= mask;
+    int stop = RES_LOOK;   // first block of the batch that ends the straight run along diagonal d
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = RES_LOOK - 1; i >= 0; i--)
+      if (b + (uint32_t)i < b1 && (!inb[i] || wv[i] != 0u)) stop = i;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < RES_LOOK; i++)
+      if (i <= stop && b + (uint32_t)i < b1 && (i > 0 || fresh)) dout[b + (uint32_t)i - b0] = (uint8_t)d;
+    if (stop == RES_LOOK) {
+      b += RES_LOOK;
+      fresh = true;
+      mask = ~0u;
+      continue;
+    }
+    uint32_t hit = 0u;
+    bool in_band = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < RES_LOOK; i++)
+      if (i == stop) { hit = wv[i]; in_band = inb[i]; }
+    if (!in_band) return RES_MISS;
+    b += (uint32_t)stop;
+    fresh = false;
+    d++;
+    {
+      const ResBlock B = blk[b];
+      if (d - (uint32_t)B.dlo >= (uint32_t)B.w) return RES_MISS;
+    }
+    mask = ~0u << ctz32(hit);
   }
   return d;
 }
@@ -176,7 +216,7 @@ inline size_t resident_smem_bytes(const ResidentPlan& R) {
   size_t b = 0;
   b += sizeof(uint32_t) * 2 * (size_t)R.xcap;                 // stream windows (double buffered)
   b += sizeof(uint32_t) * (size_t)R.nwords;                   // rejection bitmap
-  b += sizeof(ResBlock) * (size_t)R.nkb;                      // band table
+  b += (sizeof(ResBlock) + 16) * (size_t)R.nkb;               // band table + phase-1 view of it
   b += (size_t)R.n_entries * (R.segb + 1);                    // per entry: diagonal at each block + exit
   b += sizeof(uint32_t) * 4 * (size_t)(R.nseg + 1);           // per segment: entry base, band, chosen entry
   return b + 256;
@@ -206,6 +246,7 @@ inline ResidentPlan plan_resident(const ReplayPlan& P, uint32_t n, int window_sc
     if (lo < 0) lo = 0;
     uint32_t ulo = std::max(prev_lo, (uint32_t)lo), uhi = std::max(prev_hi, (uint32_t)hi);
     if (b == 0) ulo = 0;
+    uhi = ulo + ((uhi - ulo + 1u + 3u) & ~3u) - 1u;   // width a multiple of 4: phase 1 evaluates 4 diagonals per trip
     if (uhi >= RES_MAX_DIAG) return R;
     R.blk[b].dlo = (uint16_t)ulo;
     R.blk[b].w = (uint16_t)(uhi - ulo + 1u);
