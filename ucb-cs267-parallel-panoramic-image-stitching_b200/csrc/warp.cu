@@ -133,32 +133,227 @@ warp_overlay_kernel(const uint8_t* __restrict__ left, size_t lstride, const uint
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast path (the common case: a proper projective map with a positive denominator on the whole
+// canvas, 64-px coordinate blocks).  Same results, about a third of the instructions:
+//   * lane = pixel (3-byte stride), so a warp's tap loads touch one or two cache lines; a warp
+//     renders 256 px of one row, a block 8 adjacent rows (L1 reuse of the source rows);
+//   * OpenCV's  X = rint((X0 + M0 x1) * (32 / W))  is evaluated with a checked Newton reciprocal
+//     (MUFU.RCP64H seed, two steps, the second step's residual bounds the error) and a magic-number
+//     rounding at 2^-20; whenever the approximation could round differently from the exact
+//     expression (fraction within 2^-16 of .5, residual too large) the pixel takes the exact path
+//     (IEEE division, pano_core.cuh warp_coord), so the fast path never changes a result;
+//   * the factor 32 is folded into the numerator rows (a power of two commutes with rounding);
+//   * separable fixed-point bilinear: h = (32-fx) p0 + fx p1 per row with DP4A on the raw BGRBGR
+//     bytes, then ((32-fy) h0 + fy h1 + 512) >> 10, algebraically identical to OpenCV's
+//     (sum w_i p_i + 2^14) >> 15 with w = 32 (32-fx)(32-fy) ... (no intermediate rounding);
+//   * groups of 32 px outside the source footprint are straight copies of the left image.
+// ---------------------------------------------------------------------------------------
+struct FastParams {
+  double Mx[3], My[3], Mw[3];  // 32 * M[0..2], 32 * M[3..5], M[6..8]  (M = inverse of T*H)
+  WarpParams W;                // everything the exact path needs
+  int copy_words;              // canvas base and pitch are 4-byte aligned: left-only groups are copied as words
+};
+
+__device__ __forceinline__ double rcp_seed(double w) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+  return r;
+}
+
+// fixed-point bilinear, all four taps inside the source (sx in [0, ws-2], sy in [0, hs-3])
+__device__ __forceinline__ uint32_t bilinear_dp4a(const uint8_t* __restrict__ src, uint32_t sstride, int sx, int sy,
+                                                  int fx, int fy) {
+  const uint32_t off = (uint32_t)sy * sstride + 3u * (uint32_t)sx;    // sources are < 4 GB
+  const uint32_t a = off & 3u, sh = 8u * a;                           // base and pitch are multiples of 4
+  const uint32_t* q0 = reinterpret_cast<const uint32_t*>(src + (off - a));
+  const uint32_t* q1 = reinterpret_cast<const uint32_t*>(src + (off - a + sstride));
+  const uint32_t u0 = q0[0], u1 = q0[1], u2 = q0[2];
+  const uint32_t v0 = q1[0], v1 = q1[1], v2 = q1[2];
+  const uint32_t alo = __funnelshift_r(u0, u1, sh), ahi = __funnelshift_r(u1, u2, sh);   // B0 G0 R0 B1 | G1 R1 . .
+  const uint32_t blo = __funnelshift_r(v0, v1, sh), bhi = __funnelshift_r(v1, v2, sh);
+  const uint32_t wx = (uint32_t)(32 - fx) | ((uint32_t)fx << 24);                        // bytes 0 and 3
+  const int gy = 32 - fy;
+  uint32_t out = 0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const uint32_t ta = c == 0 ? alo : __funnelshift_r(alo, ahi, 8 * c);   // p0[c] . . p1[c]
+    const uint32_t tb = c == 0 ? blo : __funnelshift_r(blo, bhi, 8 * c);
+    const int h0 = (int)__dp4a(ta, wx, 0u), h1 = (int)__dp4a(tb, wx, 0u);
+    const int sv = gy * h0 + fy * h1 + 512;
+    out |= (uint32_t)(sv >> 10) << (8 * c);
+  }
+  return out;
+}
+
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+warp_fast_kernel(const uint8_t* __restrict__ left, size_t lstride, const uint8_t* __restrict__ right, size_t rstride,
+                 const FastParams F, uint8_t* __restrict__ canvas, size_t cstride) {
+  const WarpParams& P = F.W;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int yb = blockIdx.y * 8 + wrp;            // row inside the band
+  if (yb >= P.ch) return;
+  const int y = yb + P.y0;
+  const int xc = blockIdx.x * 256;
+  uint8_t* crow = canvas + (size_t)yb * cstride;
+  const double yd = (double)y;
+  const double cX = __dmul_rn(F.Mx[1], yd), cY = __dmul_rn(F.My[1], yd), cW = __dmul_rn(F.Mw[1], yd);
+  const bool row_in = y >= P.by0 && y <= P.by1;
+  const int ly = y - P.offy;
+  const bool lrow = MODE == 1 && ly >= 0 && ly < P.hl;
+  const uint8_t* lrowp = left + (size_t)(lrow ? ly : 0) * lstride;
+  const uint32_t rs = (uint32_t)rstride;
+#pragma unroll 1
+  for (int blk = 0; blk < 4; blk++) {
+    const int xb = xc + blk * 64;
+    if (xb >= P.cw) break;
+    const double xbd = (double)xb;
+    // row-origin numerators of this 64-px block (ref arithmetic of warp_row_origin, X and Y scaled by 32)
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(F.Mx[0], xbd), cX), F.Mx[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(F.My[0], xbd), cY), F.My[2]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(F.Mw[0], xbd), cW), F.Mw[2]);
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      const int x0 = xb + 32 * g, x = x0 + lane;
+      if (x0 >= P.cw) break;
+      uint32_t px = 0u;
+      const bool grp_in = row_in && !(x0 + 31 < P.bx0 || x0 > P.bx1);   // warp-uniform
+      if (MODE == 1 && F.copy_words && !grp_in && lrow && x0 >= P.offx && x0 + 32 <= P.offx + P.wl && x0 + 32 <= P.cw &&
+          ly + 1 < P.hl) {
+        // 32 px of the left image, nothing of the right one: 24 aligned words (the canvas row and x0 * 3 are
+        // 4-byte aligned; the source words are realigned with a funnel shift; the row below keeps the last
+        // word's over-read inside the image)
+        if (lane < 24) {
+          const uint8_t* sp = lrowp + 3u * (uint32_t)(x0 - P.offx) + 4u * (uint32_t)lane;
+          const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 3u);
+          const uint32_t* q = reinterpret_cast<const uint32_t*>(sp - a);
+          const uint32_t w0 = q[0], w1 = q[1];
+          reinterpret_cast<uint32_t*>(crow + 3u * (uint32_t)x0)[lane] = __funnelshift_r(w0, w1, 8u * a);
+        }
+        continue;
+      }
+      if (grp_in) {
+        const double x1d = (double)(32 * g + lane);
+        const double Wd = __dadd_rn(W0, __dmul_rn(F.Mw[0], x1d));
+        const double Xn = __dadd_rn(X0, __dmul_rn(F.Mx[0], x1d));
+        const double Yn = __dadd_rn(Y0, __dmul_rn(F.My[0], x1d));
+        const double r0 = rcp_seed(Wd);
+        const double e0 = __fma_rn(-Wd, r0, 1.0);
+        const double r1 = __fma_rn(r0, e0, r0);
+        const double e1 = __fma_rn(-Wd, r1, 1.0);
+        const double r2 = __fma_rn(r1, e1, r1);
+        // magic rounding: the mantissa of (v + 1.5 * 2^32) is 2^51 + round(v * 2^20)
+        const double mx = __dadd_rn(__dmul_rn(Xn, r2), 6442450944.0);
+        const double my = __dadd_rn(__dmul_rn(Yn, r2), 6442450944.0);
+        const uint32_t xl = (uint32_t)__double2loint(mx), xh = (uint32_t)__double2hiint(mx);
+        const uint32_t yl = (uint32_t)__double2loint(my), yh = (uint32_t)__double2hiint(my);
+        // fraction within 16 * 2^-20 of one half?  ((frac + 2^19 + 16) mod 2^20 <= 32)
+        const uint32_t tx = (xl + 0x80010u) & 0xFFFFFu, ty = (yl + 0x80010u) & 0xFFFFFu;
+        const bool exact_needed = min(tx, ty) <= 32u || !(fabs(e1) < 2.384185791015625e-07);   // |e1| < 2^-22
+        int X, Y;
+        {
+          const uint32_t xl2 = xl + 0x80000u, yl2 = yl + 0x80000u;
+          const uint32_t xh2 = xh + (xl2 < xl ? 1u : 0u), yh2 = yh + (yl2 < yl ? 1u : 0u);
+          X = (int)(__funnelshift_r(xl2, xh2, 20) ^ 0x80000000u);
+          Y = (int)(__funnelshift_r(yl2, yh2, 20) ^ 0x80000000u);
+        }
+        if (x < P.cw) {
+          if (exact_needed) warp_coord(P.M, x, y, P.bw0, &X, &Y);
+          const int sx = X >> 5, sy = Y >> 5;
+          if ((unsigned)sx < (unsigned)(P.ws - 1) && (unsigned)sy < (unsigned)(P.hs - 2))
+            px = bilinear_dp4a(right, rs, sx, sy, X & 31, Y & 31);
+          else
+            px = warp_pixel(right, rstride, P.ws, P.hs, X, Y);   // border ring / outside: general path
+        }
+      }
+      if (x < P.cw) {
+        if (MODE == 1 && px == 0u && lrow) {
+          const int lx = x - P.offx;
+          if (lx >= 0 && lx < P.wl) {
+            const uint8_t* lp = lrowp + 3u * (uint32_t)lx;
+            px = (uint32_t)lp[0] | ((uint32_t)lp[1] << 8) | ((uint32_t)lp[2] << 16);
+          }
+        }
+        if (MODE != 2 || px != 0u) {
+          uint8_t* o = crow + 3u * (uint32_t)x;
+          o[0] = (uint8_t)px;
+          o[1] = (uint8_t)(px >> 8);
+          o[2] = (uint8_t)(px >> 16);
+        }
+      }
+    }
+  }
+}
+
+// PANO_WARP_FAST=0 forces the general kernel (tests compare the two)
+bool warp_fast_enabled() {
+  const char* e = getenv("PANO_WARP_FAST");
+  return !(e && atoi(e) == 0);
+}
+
+// Can the fast kernel be used?  Needs the footprint box (positive denominators), OpenCV's 64-px coordinate
+// blocks, |coordinates| * 32 < 2^22 inside the canvas (magic rounding range) and a 4-byte aligned source.
+bool fast_path_ok(const WarpParams& P, const uint8_t* src, size_t sstride, bool box_valid) {
+  if (!box_valid || P.bw0 != 64 || P.ws < 4 || P.hs < 4) return false;
+  if ((reinterpret_cast<uintptr_t>(src) & 3u) != 0 || (sstride & 3u) != 0) return false;
+  const double cx[4] = {0.0, (double)P.cw, (double)P.cw, 0.0};
+  const double cy[4] = {(double)P.y0, (double)P.y0, (double)(P.y0 + P.ch), (double)(P.y0 + P.ch)};
+  double wmin = 1e300, nmax = 0;
+  for (int i = 0; i < 4; i++) {
+    const double w = P.M[6] * cx[i] + P.M[7] * cy[i] + P.M[8];
+    wmin = fmin(wmin, w);
+    nmax = fmax(nmax, fabs(P.M[0] * cx[i] + P.M[1] * cy[i] + P.M[2]));
+    nmax = fmax(nmax, fabs(P.M[3] * cx[i] + P.M[4] * cy[i] + P.M[5]));
+  }
+  if (!(wmin > 1e-9) || !(nmax == nmax)) return false;
+  return 32.0 * nmax / wmin < 4000000.0;   // < 2^22 with margin
+}
+
+template <int MODE>
+void launch_fast(cudaStream_t st, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
+                 const WarpParams& P, uint8_t* canvas, size_t cstride) {
+  FastParams F;
+  for (int i = 0; i < 3; i++) { F.Mx[i] = 32.0 * P.M[i]; F.My[i] = 32.0 * P.M[3 + i]; F.Mw[i] = P.M[6 + i]; }
+  F.W = P;
+  F.copy_words = ((reinterpret_cast<uintptr_t>(canvas) & 3u) == 0 && (cstride & 3u) == 0) ? 1 : 0;
+  dim3 block(256), grid((P.cw + 255) / 256, (P.ch + 7) / 8);
+  static const int minb = [] { const char* e = getenv("PANO_WARP_MINB"); return e ? atoi(e) : 5; }();
+  if (minb >= 6)
+    warp_fast_kernel<MODE, 6><<<grid, block, 0, st>>>(left, lstride, right, rstride, F, canvas, cstride);
+  else if (minb == 5)
+    warp_fast_kernel<MODE, 5><<<grid, block, 0, st>>>(left, lstride, right, rstride, F, canvas, cstride);
+  else
+    warp_fast_kernel<MODE, 4><<<grid, block, 0, st>>>(left, lstride, right, rstride, F, canvas, cstride);
+}
+
 // Canvas box outside which no pixel can receive a source tap: forward image (by `fwd`, the matrix
 // whose inverse is iterated) of the source rectangle grown by 2 px, grown again by 2 px.  Only
 // valid when the inverse map's denominator is positive on the whole canvas (then it is a proper
 // projective bijection there and the image of the rectangle is the convex quad of its corners);
 // otherwise the box is the whole canvas and every pixel is evaluated.
-void footprint_box(const double* fwd, const double* Minv, int ws, int hs, int cw, int ch, WarpParams& P) {
+bool footprint_box(const double* fwd, const double* Minv, int ws, int hs, int cw, int ch, WarpParams& P) {
   P.bx0 = 0; P.by0 = 0; P.bx1 = cw - 1; P.by1 = ch - 1;
   const double cx[4] = {0.0, (double)cw, (double)cw, 0.0}, cy[4] = {0.0, 0.0, (double)ch, (double)ch};
   for (int i = 0; i < 4; i++) {
     double wd = Minv[6] * cx[i] + Minv[7] * cy[i] + Minv[8];
-    if (!(wd > 1e-12)) return;
+    if (!(wd > 1e-12)) return false;
   }
   const double sx[4] = {-2.0, ws + 1.0, ws + 1.0, -2.0}, sy[4] = {-2.0, -2.0, hs + 1.0, hs + 1.0};
   double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
   for (int i = 0; i < 4; i++) {
     double wd = fwd[6] * sx[i] + fwd[7] * sy[i] + fwd[8];
-    if (!(wd > 1e-12)) return;
+    if (!(wd > 1e-12)) return false;
     double X = (fwd[0] * sx[i] + fwd[1] * sy[i] + fwd[2]) / wd, Y = (fwd[3] * sx[i] + fwd[4] * sy[i] + fwd[5]) / wd;
     x0 = fmin(x0, X); x1 = fmax(x1, X); y0 = fmin(y0, Y); y1 = fmax(y1, Y);
   }
-  if (!(x0 == x0) || !(x1 == x1) || !(y0 == y0) || !(y1 == y1)) return;
+  if (!(x0 == x0) || !(x1 == x1) || !(y0 == y0) || !(y1 == y1)) return false;
   auto clampi = [](double v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : (int)v); };
   P.bx0 = clampi(floor(x0) - 2, 0, cw - 1);
   P.by0 = clampi(floor(y0) - 2, 0, ch - 1);
   P.bx1 = clampi(ceil(x1) + 2, 0, cw - 1);
   P.by1 = clampi(ceil(y1) + 2, 0, ch - 1);
+  return true;
 }
 
 }  // namespace
@@ -173,10 +368,14 @@ void warp_overlay_device(cudaStream_t st, const DevImage& left, const DevImage& 
   P.ws = right.w; P.hs = right.h;
   P.y0 = 0;
   P.src_bytes = (size_t)(right.h - 1) * right.stride + (size_t)right.w * 3;
-  footprint_box(g.TH, g.Minv, right.w, right.h, g.cw, g.ch, P);
-  dim3 block(32, 8), grid(((g.cw + 3) / 4 + 31) / 32, (g.ch + 7) / 8);
-  warp_overlay_kernel<1><<<grid, block, 0, st>>>(left.p, left.stride, right.p, right.stride, P, canvas,
-                                                   canvas_stride);
+  const bool box = footprint_box(g.TH, g.Minv, right.w, right.h, g.cw, g.ch, P);
+  if (fast_path_ok(P, right.p, right.stride, box) && warp_fast_enabled()) {
+    launch_fast<1>(st, left.p, left.stride, right.p, right.stride, P, canvas, canvas_stride);
+  } else {
+    dim3 block(32, 8), grid(((g.cw + 3) / 4 + 31) / 32, (g.ch + 7) / 8);
+    warp_overlay_kernel<1><<<grid, block, 0, st>>>(left.p, left.stride, right.p, right.stride, P, canvas,
+                                                     canvas_stride);
+  }
   PANO_LAUNCH_CHECK();
 }
 
@@ -190,13 +389,18 @@ void warp_only_device(cudaStream_t st, const DevImage& src, const double* Minv, 
   P.ws = src.w; P.hs = src.h;
   P.y0 = 0;
   P.src_bytes = (size_t)(src.h - 1) * src.stride + (size_t)src.w * 3;
+  bool box = false;
   {
     double fwd[9];
-    if (invert33(Minv, fwd)) footprint_box(fwd, Minv, src.w, src.h, dw, dh, P);
+    if (invert33(Minv, fwd)) box = footprint_box(fwd, Minv, src.w, src.h, dw, dh, P);
     else { P.bx0 = 0; P.by0 = 0; P.bx1 = dw - 1; P.by1 = dh - 1; }
   }
-  dim3 block(32, 8), grid(((dw + 3) / 4 + 31) / 32, (dh + 7) / 8);
-  warp_overlay_kernel<0><<<grid, block, 0, st>>>(nullptr, 0, src.p, src.stride, P, dst, dstride);
+  if (fast_path_ok(P, src.p, src.stride, box) && warp_fast_enabled()) {
+    launch_fast<0>(st, nullptr, 0, src.p, src.stride, P, dst, dstride);
+  } else {
+    dim3 block(32, 8), grid(((dw + 3) / 4 + 31) / 32, (dh + 7) / 8);
+    warp_overlay_kernel<0><<<grid, block, 0, st>>>(nullptr, 0, src.p, src.stride, P, dst, dstride);
+  }
   PANO_LAUNCH_CHECK();
 }
 
@@ -215,9 +419,13 @@ void warp_accumulate_device(cudaStream_t st, const DevImage& src, const double* 
   P.ws = src.w; P.hs = src.h;
   P.y0 = y0;
   P.src_bytes = (size_t)(src.h - 1) * src.stride + (size_t)src.w * 3;
-  footprint_box(M, Minv, src.w, src.h, canvas_w, canvas_h, P);   // box in whole-canvas coordinates
-  dim3 block(32, 8), grid(((canvas_w + 3) / 4 + 31) / 32, (band_h + 7) / 8);
-  warp_overlay_kernel<2><<<grid, block, 0, st>>>(nullptr, 0, src.p, src.stride, P, band, band_stride);
+  const bool box = footprint_box(M, Minv, src.w, src.h, canvas_w, canvas_h, P);   // box in whole-canvas coordinates
+  if (fast_path_ok(P, src.p, src.stride, box) && warp_fast_enabled()) {
+    launch_fast<2>(st, nullptr, 0, src.p, src.stride, P, band, band_stride);
+  } else {
+    dim3 block(32, 8), grid(((canvas_w + 3) / 4 + 31) / 32, (band_h + 7) / 8);
+    warp_overlay_kernel<2><<<grid, block, 0, st>>>(nullptr, 0, src.p, src.stride, P, band, band_stride);
+  }
   PANO_LAUNCH_CHECK();
 }
 
