@@ -121,24 +121,27 @@ struct ReplayCtl {
 constexpr int RW_THREADS = 128;
 constexpr size_t CHAIN_SMEM_MAX = 200 * 1024;  // + 20 KB static: under the 227 KB per-block limit
 
-// Pass 1a: rejection cells of a whole chunk.  One warp = one (iteration g, 32-step block kb)
-// task; it keeps the block's 32 (range, threshold) pairs in registers and sweeps all diagonal
-// blocks of the iteration.  Lane = diagonal: for step k it reads stream word pos + lane + k from
-// a 64-word shared-memory window (conflict free) and shifts the test bit into its own word with
-// an add-with-carry pair: ~lo = x*(-r) - 1 (one IMAD), and T + ~lo carries out of 32 bits exactly
-// when lo32(x*r) < T, so "add.cc; addc w, w, w" is w = 2w + rejected.  Steps are visited from 31
-// down to 0 so that bit k is step k.  3 ALU + 1 LDS instructions per 32 cells; the 32 words of a
-// diagonal block are one 128-byte row.
+// Pass 1a: rejection cells of a whole chunk.  One warp = one (iteration g, 32-step block kb) task; it keeps the
+// block's 32 (range, threshold) pairs in registers and sweeps the iteration's diagonals in tiles of 128.
+// Lane l owns the four diagonals 4l .. 4l+3 of a tile: the cell (diagonal d, step i) reads stream word
+// pos + d + i, so ONE aligned 16-byte shared-memory load (words 4l + 4q .. 4l + 4q + 3) feeds 16 cells - four
+// steps of each of the lane's four diagonals - and the kernel is bound by its three ALU instructions per cell,
+// not by shared-memory loads (the earlier lane = diagonal mapping spent one LDS per cell and was LSU bound).
+// The test bit is shifted into the diagonal's word with an add-with-carry pair: ~lo = x*(-r) - 1 (one IMAD), and
+// T + ~lo carries out of 32 bits exactly when lo32(x*r) < T, so "add.cc; addc w, w, w" is w = 2w + rejected.
+// Steps are visited from 31 down to 0 so that bit k is step k; a lane's four words are one 16-byte store.
 __device__ __forceinline__ void cell_step(uint32_t& w, uint32_t x, uint32_t neg_r, uint32_t T) {
   const uint32_t nlo = x * neg_r + 0xffffffffu;   // ~(x * r)
   asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, %0;\n\t}" : "+r"(w) : "r"(T), "r"(nlo));
 }
 
+constexpr int CELL_WIN = 192;   // stream words staged per 128-diagonal tile (128 + 32 + 3, rounded up to 6 x 32)
+
 __global__ void __launch_bounds__(256)
 replay_cells_kernel(const uint32_t* __restrict__ X, uint32_t steps, const RT* __restrict__ rt,
                     const WinEntry* __restrict__ win, int G, uint32_t nkb, uint32_t dextra, const ReplayCtl* ctl,
                     uint32_t* __restrict__ bits, unsigned long long x_limit) {
-  __shared__ uint32_t s_x[8][64];  // the 64 stream words a 32-diagonal x 32-step tile touches
+  __shared__ __align__(16) uint32_t s_x[8][CELL_WIN];
   __shared__ RT s_rt[8][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
@@ -159,18 +162,30 @@ replay_cells_kernel(const uint32_t* __restrict__ X, uint32_t steps, const RT* __
 #pragma unroll
   for (int i = 0; i < 32; i++) { rr[i] = 0u - s_rt[wid][i].r; tt[i] = s_rt[wid][i].T; }
   const unsigned long long pos0 = ctl->base + (unsigned long long)g * steps + we.lo + (unsigned long long)kb * 32u;
-  uint32_t* out = bits + (size_t)we.dfirst * nkb + (size_t)kb * D;
-  for (uint32_t d0 = 0; d0 < D; d0 += 32u) {
-    const unsigned long long pos = pos0 + d0;   // cell (d0 + lane, step i) reads word pos + lane + i
-    const bool in_range = pos + 64ull < x_limit;
+  uint32_t* out = bits + (size_t)we.dfirst * nkb + (size_t)kb * D;   // 16-byte aligned: dfirst, D multiples of 32
+  for (uint32_t d0 = 0; d0 < D; d0 += 128u) {
+    const unsigned long long pos = pos0 + d0;   // cell (d0 + d, step i) reads word pos + d + i
+    const bool in_range = pos + CELL_WIN < x_limit;
     __syncwarp();
-    s_x[wid][lane] = in_range ? X[pos + lane] : 0xffffffffu;
-    s_x[wid][32 + lane] = in_range ? X[pos + 32 + lane] : 0xffffffffu;
-    __syncwarp();
-    uint32_t w = 0;
 #pragma unroll
-    for (int i = 31; i >= 0; i--) cell_step(w, s_x[wid][lane + i], rr[i], tt[i]);
-    out[d0 + lane] = w;
+    for (int u = 0; u < CELL_WIN / 32; u++) s_x[wid][32 * u + lane] = in_range ? X[pos + 32 * u + lane] : 0xffffffffu;
+    __syncwarp();
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    const uint4* xq = reinterpret_cast<const uint4*>(&s_x[wid][4 * lane]);
+#pragma unroll
+    for (int q = 8; q >= 0; q--) {
+      const uint4 v = xq[q];                    // words 4 lane + 4 q + (0..3)
+      const uint32_t xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 3; j >= 0; j--) {            // diagonal 4 lane + r uses word j at step i = 4 q + j - r
+        if (4 * q + j - 0 >= 0 && 4 * q + j - 0 < 32) cell_step(w0, xv[j], rr[(4 * q + j - 0) & 31], tt[(4 * q + j - 0) & 31]);
+        if (4 * q + j - 1 >= 0 && 4 * q + j - 1 < 32) cell_step(w1, xv[j], rr[(4 * q + j - 1) & 31], tt[(4 * q + j - 1) & 31]);
+        if (4 * q + j - 2 >= 0 && 4 * q + j - 2 < 32) cell_step(w2, xv[j], rr[(4 * q + j - 2) & 31], tt[(4 * q + j - 2) & 31]);
+        if (4 * q + j - 3 >= 0 && 4 * q + j - 3 < 32) cell_step(w3, xv[j], rr[(4 * q + j - 3) & 31], tt[(4 * q + j - 3) & 31]);
+      }
+    }
+    const uint32_t d = d0 + 4u * lane;
+    if (d < D) *reinterpret_cast<uint4*>(out + d) = make_uint4(w0, w1, w2, w3);   // D is a multiple of 32: all or none
   }
 }
 
