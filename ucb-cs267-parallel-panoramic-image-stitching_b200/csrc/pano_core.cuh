@@ -448,7 +448,7 @@ PANO_HD uint32_t ctz32(uint32_t w) {
 // Segment-boundary offsets are recorded as in walk_offsets.
 PANO_HD uint32_t walk_bits(const uint32_t* bits, uint32_t D, uint32_t nkb, uint32_t d0, uint32_t steps,
                            uint32_t pos0, uint32_t* seg_off, size_t seg_stride) {
-  constexpr uint32_t AHEAD = 16;                       // words in flight on the current diagonal
+  constexpr uint32_t AHEAD = 8;                        // words in flight on the current diagonal (a hop discards them: L2 traffic)
   constexpr uint32_t SEGW = PANO_SEG_STEPS / 32u;      // words per pass-2 segment
   uint32_t d = d0, kb = 0, mask = ~0u;
   while (kb < nkb) {
