@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <exception>
 #include <new>
+#include <mutex>
 #include <thread>
 
 namespace pano {
@@ -698,8 +699,15 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
     try {
       PANO_CUDA(cudaSetDevice(l->device));
       for (int i = li; i < n; i += n_lanes) {
-        DevImage L = to_device(l, lefts[i], wl, hl, stride_l, mem, 0);
-        DevImage R = to_device(l, rights[i], wr, hr, stride_r, mem, 1);
+        DevImage L, R;
+        {
+          // a pair needs both images: keep its two uploads adjacent in the copy engine's queue, otherwise the
+          // lanes' copies interleave (all lefts, then all rights) and no lane can start until most have landed
+          static std::mutex upload_order;
+          std::lock_guard<std::mutex> lk(upload_order);
+          L = to_device(l, lefts[i], wl, hl, stride_l, mem, 0);
+          R = to_device(l, rights[i], wr, hr, stride_r, mem, 1);
+        }
         int s = stitch_pair_device(l, L, R, *hopts, *ropts, &results[i]);
         if (s == PANO_ERR_CUDA) { lane_rc[li] = s; c->err = l->err; return; }
         if (s == PANO_OK && canvases_out && canvases_out[i]) {
