@@ -2,6 +2,7 @@
 same inputs.  Bars (BASELINE.json north_star): keypoints, match lists, RANSAC samples / counts /
 inlier sets bit-exact; homographies within 1e-4 relative (asserted bit-exact here, which is
 stronger); warped pixels within +-1 LSB (asserted exact)."""
+import os
 import numpy as np
 import pytest
 
@@ -380,3 +381,34 @@ def test_resident_band_miss_is_detected_and_rerun(oracle):
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
                        env=dict(os.environ, PANO_REPLAY_Z="0.3"))
     assert p.returncode == 0 and "OK" in p.stdout, p.stderr[-800:]
+
+
+# ---------------- throughput mode: pano_stitch_batch (lanes, prefetched uploads, async downloads) ----
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_stitch_batch_equals_pairs(engine, oracle, mem):
+    """every pair of a batch (several pairs per lane, host buffers with upload / download streams, or device
+    buffers) gives exactly what pano_stitch_pair gives for it: H, counts and canvas bytes"""
+    import torch
+    synth = load_synth()
+    pairs = [synth.make_pair(640, 360, seed=40 + i)[:2] for i in range(7)]
+    lefts, rights = [p[0] for p in pairs], [p[1] for p in pairs]
+    cap = 3 * (2 * 640 + 64) * (360 + 256)
+    if mem == "host":
+        L, R = lefts, rights
+        outs = [np.zeros(cap, np.uint8) for _ in pairs]
+    else:
+        L = [torch.from_numpy(a).cuda() for a in lefts]
+        R = [torch.from_numpy(a).cuda() for a in rights]
+        outs = [torch.zeros(cap, dtype=torch.uint8, device="cuda") for _ in pairs]
+    os.environ["PANO_BATCH_LANES"] = "3"      # 7 pairs on 3 lanes: up to 3 pairs per lane (slot reuse, canvas reuse)
+    try:
+        res, _ = engine.stitchBatch(L, R, canvases_out=outs)
+    finally:
+        os.environ.pop("PANO_BATCH_LANES", None)
+    for i, r in enumerate(res):
+        canvas, p = engine.stitchTwoImages(lefts[i], rights[i])
+        assert r["status"] == p["status"] == 0
+        assert np.array_equal(bits(r["H"]), bits(p["H"])) and r["best"] == p["best"] and r["m"] == p["m"]
+        cw, ch = r["canvas"][0], r["canvas"][1]
+        got = outs[i] if mem == "host" else outs[i].cpu().numpy()
+        assert np.array_equal(got[:cw * ch * 3].reshape(ch, cw, 3), canvas)

@@ -37,6 +37,11 @@ struct pano_ctx {
   std::string err;
   PinnedBuf pin;
   DevBuf up[2];  // staging for host images
+  // batch lanes with host buffers: the next pair's images are uploaded, and the previous canvas downloaded, on
+  // their own streams while this pair is being stitched
+  DevBuf upq[2][2];
+  cudaStream_t st_up = nullptr, st_down = nullptr;
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr};
   DevBuf kpup[2], mup;
   HarrisScratch hs;
   DevKeypoints kpL, kpR;
@@ -289,6 +294,14 @@ void pano_destroy(pano_ctx* c) {
   c->lanes.clear();
   cudaSetDevice(c->device);
   if (c->st) cudaStreamSynchronize(c->st);
+  if (c->st_up) { cudaStreamSynchronize(c->st_up); cudaStreamDestroy(c->st_up); }
+  if (c->st_down) { cudaStreamSynchronize(c->st_down); cudaStreamDestroy(c->st_down); }
+  for (int q = 0; q < 2; q++) {
+    if (c->ev_up[q]) cudaEventDestroy(c->ev_up[q]);
+    if (c->ev_down[q]) cudaEventDestroy(c->ev_down[q]);
+    c->upq[q][0].release();
+    c->upq[q][1].release();
+  }
   DevBuf* bufs[] = {&c->up[0], &c->up[1], &c->kpup[0], &c->kpup[1], &c->mup, &c->hs.resp, &c->hs.mask, &c->hs.rowcnt,
                     &c->hs.rowoff, &c->hs.total, &c->kpL.xy, &c->kpR.xy, &c->ms.flags, &c->ms.tmp, &c->ms.best,
                     &c->ms.cnt, &c->ms.mflags, &c->ms.midx, &c->ms.mtmp, &c->ms.tc_err, &c->dQ.desc, &c->dQ.norm, &c->dQ.orig,
@@ -698,13 +711,47 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
     l->replay_mode = c->replay_mode;   // (resident = 1 pays off from ~32 lanes on: it trades latency for GPU time)
     try {
       PANO_CUDA(cudaSetDevice(l->device));
-      for (int i = li; i < n; i += n_lanes) {
-        DevImage L, R;
+      const bool host_io = mem != PANO_MEM_DEVICE;
+      if (host_io && !l->st_up) {
+        PANO_CUDA(cudaStreamCreateWithFlags(&l->st_up, cudaStreamNonBlocking));
+        PANO_CUDA(cudaStreamCreateWithFlags(&l->st_down, cudaStreamNonBlocking));
+        for (int q = 0; q < 2; q++) {
+          PANO_CUDA(cudaEventCreateWithFlags(&l->ev_up[q], cudaEventDisableTiming));
+          PANO_CUDA(cudaEventCreateWithFlags(&l->ev_down[q], cudaEventDisableTiming));
+        }
+      }
+      DevImage Lq[2], Rq[2];
+      // both images of pair i -> upload slot q, on the lane's upload stream
+      auto enqueue_upload = [&](int i, int q) {
+        const size_t pl = align_up((size_t)wl * 3, 256), pr = align_up((size_t)wr * 3, 256);
+        l->upq[q][0].reserve(pl * hl);
+        l->upq[q][1].reserve(pr * hr);
         {
           // a pair needs both images: keep its two uploads adjacent in the copy engine's queue, otherwise the
           // lanes' copies interleave (all lefts, then all rights) and no lane can start until most have landed
           static std::mutex upload_order;
           std::lock_guard<std::mutex> lk(upload_order);
+          PANO_CUDA(cudaMemcpy2DAsync(l->upq[q][0].p, pl, lefts[i], stride_l, (size_t)wl * 3, hl, cudaMemcpyHostToDevice, l->st_up));
+          PANO_CUDA(cudaMemcpy2DAsync(l->upq[q][1].p, pr, rights[i], stride_r, (size_t)wr * 3, hr, cudaMemcpyHostToDevice, l->st_up));
+        }
+        PANO_CUDA(cudaEventRecord(l->ev_up[q], l->st_up));
+        Lq[q].p = l->upq[q][0].as<uint8_t>(); Lq[q].w = wl; Lq[q].h = hl; Lq[q].stride = pl;
+        Rq[q].p = l->upq[q][1].as<uint8_t>(); Rq[q].w = wr; Rq[q].h = hr; Rq[q].stride = pr;
+      };
+      if (host_io && li < n) enqueue_upload(li, 0);
+      int k = 0;   // pairs done by this lane
+      for (int i = li; i < n; i += n_lanes, k++) {
+        DevImage L, R;
+        if (host_io) {
+          const int q = k & 1;
+          // prefetch the lane's next pair into the other slot (its last user has finished: stitch_pair_device
+          // returns after the pair's last kernel)
+          if (i + n_lanes < n) enqueue_upload(i + n_lanes, q ^ 1);
+          PANO_CUDA(cudaStreamWaitEvent(l->st, l->ev_up[q], 0));
+          // this pair overwrites the canvas buffer that the download of pair k - 2 read
+          if (k >= 2 && canvases_out) PANO_CUDA(cudaStreamWaitEvent(l->st, l->ev_down[q], 0));
+          L = Lq[q]; R = Rq[q];
+        } else {
           L = to_device(l, lefts[i], wl, hl, stride_l, mem, 0);
           R = to_device(l, rights[i], wr, hr, stride_r, mem, 1);
         }
@@ -714,12 +761,22 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
           size_t row = (size_t)l->cw * 3;
           if (row * (size_t)l->ch > canvas_cap_bytes) {
             results[i].status = PANO_ERR_CAPACITY;
+          } else if (host_io) {
+            // (the pair's kernels have completed: no dependency to express)
+            PANO_CUDA(cudaMemcpy2DAsync(canvases_out[i], row, l->canvas[l->cur].p, l->cstride, row, l->ch,
+                                        cudaMemcpyDeviceToHost, l->st_down));
+            PANO_CUDA(cudaEventRecord(l->ev_down[k & 1], l->st_down));
           } else {
             PANO_CUDA(cudaMemcpy2DAsync(canvases_out[i], row, l->canvas[l->cur].p, l->cstride, row, l->ch,
-                                        mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                                        l->st));
+                                        cudaMemcpyDeviceToDevice, l->st));
           }
+        } else if (host_io && canvases_out) {
+          PANO_CUDA(cudaEventRecord(l->ev_down[k & 1], l->st_down));   // keep the event chain defined
         }
+      }
+      if (host_io) {
+        PANO_CUDA(stream_wait(l->st_up));
+        PANO_CUDA(stream_wait(l->st_down));
       }
       PANO_CUDA(stream_wait(l->st));
     } catch (const CudaError& e) {
