@@ -106,3 +106,24 @@ def test_gpu_stitching_executable(files, oracle):
     assert p.returncode == 0, p.stderr
     pj = cv2.imread(outj)
     assert pj is not None and abs(pj.shape[1] - o["canvas"].shape[1]) < 40
+
+
+def test_benchmark_harness_datasets_mode(files, tmp_path):
+    """tools/benchmark_scaling.py: per-dataset runs through pano.sh, parsed from the stage lines
+    the reference's benchmark scripts grep, written as CSV"""
+    import csv
+    import shutil
+    import sys
+    d, _, _, paths = files
+    root = tmp_path / "sets"
+    (root / "pairA").mkdir(parents=True)
+    shutil.copy(paths[("a_left", "png")], root / "pairA" / "a.png")
+    shutil.copy(paths[("b_right", "png")], root / "pairA" / "b.png")
+    exe("serial")
+    out_csv = str(tmp_path / "datasets.csv")
+    p = run([sys.executable, os.path.join(ROOT, "tools", "benchmark_scaling.py"), "datasets", "--root", str(root),
+             "--impls", "serial", "--out-dir", str(tmp_path), "--csv", out_csv])
+    assert p.returncode == 0, p.stderr[-800:]
+    rows = list(csv.DictReader(open(out_csv)))
+    assert len(rows) == 1 and rows[0]["dataset"] == "pairA" and rows[0]["impl"] == "serial" and rows[0]["ok"] == "1"
+    assert float(rows[0]["image_stitching_ms"]) > 0 and float(rows[0]["total_execution_ms"]) > 0
