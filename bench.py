@@ -331,17 +331,19 @@ def run_engine(a):
             "harris_response_kernel": {"ms": t_harris, "alg_bytes": 3 * npx, "launches_per_pair": 2,
                                        "note": "FP64-pipe bound by construction (157 non-fusable FP64 ops/px); "
                                                "algorithmic traffic is 3 B/px"},
-            "warp_overlay_kernel": {"ms": t_warp, "alg_bytes": 3 * (2 * npx + cw * ch), "launches_per_pair": 1,
-                                    "note": "HBM bound: both sources read once, canvas written once"},
+            "warp_fast_kernel": {"ms": t_warp, "alg_bytes": 3 * (2 * npx + cw * ch), "launches_per_pair": 1,
+                                 "note": "HBM bound by its data flow (both sources read once, canvas written once); "
+                                         "the bit-exact fixed-point emulation makes it issue / load-latency bound in practice "
+                                         "(ncu: IPC 3.0, ALU pipe 49 %, DRAM 44 MB)"},
         }
         dom = max(stage_ms, key=stage_ms.get)
-        # The roofline object describes warp_overlay_kernel: the kernel of the step that is HBM bound
+        # The roofline object describes warp_fast_kernel (warp.cu): the kernel of the step that is HBM bound
         # by design (sources read once, canvas written once).  The kernel with the largest share of
-        # the step is replay_cells_kernel (RANSAC sample replay): integer ALU / issue bound (ncu: issue
-        # slots 80 % busy, DRAM < 1 %), so neither an HBM nor a tensor roofline applies to it; the
+        # the step is replay_cells_kernel (RANSAC sample replay): integer ALU bound (ncu: ALU pipe 66 %,
+        # IPC 3.05, DRAM < 1 %), so neither an HBM nor a tensor roofline applies to it; the
         # Harris stencil is FP64-pipe bound (ncu: FP64 pipe 67 % active).  See DESIGN.md section 4 and the
         # launch lists under profiles/.
-        top = "warp_overlay_kernel"
+        top = "warp_fast_kernel"
         ach = kernels[top]["alg_bytes"] / (kernels[top]["ms"] / 1000.0) / 1e9
         match_ops = 2.0 * r0["kr"] * r0["kl"] * 75
         roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
@@ -353,10 +355,12 @@ def run_engine(a):
                     "matcher": {"bound": "tensor", "stage_ms": t_match, "pairs": r0["kr"] * r0["kl"],
                                 "achieved_TOPs": match_ops / (t_match / 1e3) / 1e12,
                                 "note": "whole match stage (gather + tcgen05 kind::i8 GEMM with fused arg-min + emit); "
-                                        "K = 75 makes it epilogue/loader bound, see profiles/ for the tensor-pipe share"},
+                                        "the GEMM kernel itself is 24 us: TMEM-read bound (128 KB of s32 accumulators per 384-cycle tile), "
+                                        "sm__pipe_tensor_cycles_active 21.7 % (profiles/r01_final_match_tc_kernel.ncu-rep)",
+                                "kernel_us_ncu": 24.7, "tensor_pipe_active_pct": 21.7},
                     "stage_ms_per_pair": stage_ms, "dominant_stage": dom,
-                    "dominant_kernel": {"name": "replay_cells_kernel", "bound": "integer ALU / issue (not HBM, not tensor)",
-                                        "evidence": "profiles/r01_top_kernels_v2.ncu-rep, profiles/r01_launches_v7.csv"}}
+                    "dominant_kernel": {"name": "replay_cells_kernel", "bound": "integer ALU (not HBM, not tensor)",
+                                        "evidence": "profiles/r01_final_replay_cells_kernel.ncu-rep, profiles/r01_final_launches.csv"}}
         # ---- CPU baseline: serial oracle on one core, bounded sample ---------------------------
         cpu = None
         if not a.no_cpu:
