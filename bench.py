@@ -180,7 +180,9 @@ def run_engine(a):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("PANO_NCCL_DEBUG", "WARN")   # stdout must be one JSON line
+        # stdout must be one JSON line: NCCL logs (it prints its version even at WARN) go to stderr
+        os.environ["NCCL_DEBUG"] = os.environ.get("PANO_NCCL_DEBUG", os.environ.get("NCCL_DEBUG", "WARN"))
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     # overlapped lanes per GPU: each has a (spin-waiting) host thread, so share the cores between ranks
