@@ -448,21 +448,29 @@ PANO_HD uint32_t ctz32(uint32_t w) {
 // Segment-boundary offsets are recorded as in walk_offsets.
 PANO_HD uint32_t walk_bits(const uint32_t* bits, uint32_t D, uint32_t nkb, uint32_t d0, uint32_t steps,
                            uint32_t pos0, uint32_t* seg_off, size_t seg_stride) {
-  constexpr uint32_t AHEAD = 8;                        // words in flight on the current diagonal (a hop discards them: L2 traffic)
+  // Every round fetches the next AHEAD words of the current diagonal AND of the one above it (independent loads,
+  // adjacent addresses): the first rejection of a round continues on the second diagonal without another L2 round
+  // trip; only the second rejection (or the end of the batch) starts a new round.  A hop discards what is left of
+  // a batch, so a deeper look-ahead only adds L2 traffic.
+  constexpr uint32_t AHEAD = 8;
   constexpr uint32_t SEGW = PANO_SEG_STEPS / 32u;      // words per pass-2 segment
   uint32_t d = d0, kb = 0, mask = ~0u;
   while (kb < nkb) {
-    // independent loads; a hop to the next diagonal discards the rest
-    uint32_t w[AHEAD];
+    uint32_t w[AHEAD], v[AHEAD];
     const uint32_t* p = bits + (size_t)kb * D + d;
     const uint32_t left = nkb - kb;
+    const bool up = d + 1u < D;                        // the diagonal above exists in the evaluated grid
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t i = 0; i < AHEAD; i++) w[i] = i < left ? p[(size_t)i * D] : 0u;
+    for (uint32_t i = 0; i < AHEAD; i++) {
+      w[i] = i < left ? p[(size_t)i * D] : 0u;
+      v[i] = (i < left && up) ? p[(size_t)i * D + 1u] : 0u;
+    }
     w[0] &= mask;
     mask = ~0u;
-    uint32_t adv = left < AHEAD ? left : AHEAD, hit = 0;  // words without a rejection, first word with one
+    const uint32_t lim = left < AHEAD ? left : AHEAD;
+    uint32_t adv = lim, hit = 0;                       // words without a rejection, first word with one
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -474,11 +482,28 @@ PANO_HD uint32_t walk_bits(const uint32_t* bits, uint32_t D, uint32_t nkb, uint3
         seg_off[(size_t)(nb / SEGW - 1u) * seg_stride] = pos0 + d + nb * 32u;
     }
     kb += adv;
-    if (hit) {
-      d++;
-      if (d >= D) return 0xffffffffu;
-      mask = ~0u << ctz32(hit);
+    if (!hit) continue;
+    d++;
+    if (d >= D) return 0xffffffffu;
+    // same step again on the diagonal above, out of the words already fetched: indices adv .. lim - 1
+    const uint32_t m2 = ~0u << ctz32(hit);
+    uint32_t adv2 = lim, hit2 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = (int)AHEAD - 1; i >= 0; i--) {
+      const uint32_t x = (uint32_t)i == adv ? (v[i] & m2) : v[i];
+      if ((uint32_t)i >= adv && x) { adv2 = (uint32_t)i; hit2 = x; }
     }
+    if (seg_off) {
+      for (uint32_t nb = (kb / SEGW + 1u) * SEGW; nb <= kb + (adv2 - adv) && nb < nkb; nb += SEGW)
+        seg_off[(size_t)(nb / SEGW - 1u) * seg_stride] = pos0 + d + nb * 32u;
+    }
+    kb += adv2 - adv;
+    if (!hit2) continue;                               // the rest of the batch is clean on this diagonal
+    d++;
+    if (d >= D) return 0xffffffffu;
+    mask = ~0u << ctz32(hit2);
   }
   return pos0 + d + steps;
 }
