@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cstdlib>
 #include <chrono>
 #include <thread>
 #include <cstdint>
@@ -38,6 +39,25 @@ inline cudaError_t stream_wait(cudaStream_t st) {
     if (e != cudaErrorNotReady) return e;
     std::this_thread::sleep_for(std::chrono::microseconds(20));
   }
+}
+
+// Programmatic dependent launch: the next kernel of a stream is set up while the previous one drains; every kernel
+// launched this way starts with pdl_wait() (= all earlier grids complete and visible) before it touches memory.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("PANO_PDL"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  PANO_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
 }
 
 // every engine kernel launch goes through this: counts it and surfaces launch errors

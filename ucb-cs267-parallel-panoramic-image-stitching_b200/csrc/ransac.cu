@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(256)
 replay_cells_kernel(const uint32_t* __restrict__ X, uint32_t steps, const RT* __restrict__ rt,
                     const WinEntry* __restrict__ win, int G, uint32_t nkb, uint32_t dextra, const ReplayCtl* ctl,
                     uint32_t* __restrict__ bits, unsigned long long x_limit) {
+  pdl_wait();
   __shared__ __align__(16) uint32_t s_x[8][CELL_WIN];
   __shared__ RT s_rt[8][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(RW_THREADS)
 replay_walk_bits_kernel(uint32_t steps, const WinEntry* __restrict__ win, uint32_t nkb, uint32_t dextra,
                         ReplayCtl* ctl, const uint32_t* __restrict__ bits, uint32_t* __restrict__ cand_end,
                         uint32_t* __restrict__ seg_off, int n_cand, unsigned long long stream_len) {
+  pdl_wait();
   const int g = blockIdx.y;
   const WinEntry we = win[g];
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(1024)
 replay_chain_kernel(const WinEntry* __restrict__ win, int G, uint32_t steps, const uint32_t* __restrict__ cand_end,
                     const uint32_t* __restrict__ seg_off, int n_cand, int nseg, ReplayCtl* ctl,
                     unsigned long long* __restrict__ seg_tab /* this chunk's slice */) {
+  pdl_wait();
   extern __shared__ __align__(16) uint32_t s_end[];
   __shared__ WinEntry s_win[1024];
   __shared__ int s_pick[1024];
@@ -288,6 +291,7 @@ __global__ void __launch_bounds__(64)
 replay_segments_kernel(const uint32_t* __restrict__ X, uint32_t n, uint32_t steps, const RT* __restrict__ rt,
                        const unsigned long long* __restrict__ seg_tab, int iters, int nseg, ReplayCtl* ctl,
                        int4* __restrict__ seg_w) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= iters * nseg) return;
   const int t = i / nseg, sgm = i - t * nseg;
@@ -307,6 +311,7 @@ replay_segments_kernel(const uint32_t* __restrict__ X, uint32_t n, uint32_t step
 
 // last writer wins across an iteration's segments
 __global__ void combine_samples_kernel(const int4* __restrict__ seg_w, int iters, int nseg, int4* __restrict__ samples) {
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= iters) return;
   int a[4] = {-1, -1, -1, -1};
@@ -575,6 +580,7 @@ __device__ __forceinline__ void warp_argmax_first(double& v, int& pos, int& k, i
 __global__ void __launch_bounds__(DLT_WARPS * 32)
 dlt_kernel(const float4* __restrict__ pts, const int4* __restrict__ samples, int iters, double* __restrict__ Hs,
            int* __restrict__ valid) {
+  pdl_wait();
   __shared__ DltSmem sm_all[DLT_WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int t = blockIdx.x * DLT_WARPS + wid;
@@ -775,6 +781,7 @@ dlt_kernel(const float4* __restrict__ pts, const int4* __restrict__ samples, int
 __global__ void __launch_bounds__(256)
 score_kernel(const float4* __restrict__ pts, int m, const double* __restrict__ Hs, const int* __restrict__ valid,
              double thr, int* __restrict__ counts) {
+  pdl_wait();
   const int t = blockIdx.x;
   if (!valid[t]) {
     if (threadIdx.x == 0) counts[t] = -1;
@@ -1026,37 +1033,36 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
       dim3 grid((max_w + RW_THREADS - 1) / RW_THREADS, Gc);
       {
         long long warps = (long long)Gc * nkb;
-        replay_cells_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(mt.x.as<uint32_t>(), steps, s.thr.as<RT>(),
-                                                                        s.plan.as<WinEntry>(), Gc, nkb, plan.dextra, ctl,
-                                                                        bits, mt.len + mt.guard - 64);
+        launch_pdl(replay_cells_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, st, mt.x.as<uint32_t>(), steps,
+                   s.thr.as<RT>(), s.plan.as<WinEntry>(), Gc, nkb, plan.dextra, ctl, bits, mt.len + mt.guard - 64);
         PANO_LAUNCH_CHECK();
       }
-      replay_walk_bits_kernel<<<grid, RW_THREADS, 0, st>>>(steps, s.plan.as<WinEntry>(), nkb, plan.dextra, ctl, bits,
-                                                           cand_end, seg_off, (int)n_cand, mt.len);
+      launch_pdl(replay_walk_bits_kernel, grid, dim3(RW_THREADS), 0, st, steps, s.plan.as<WinEntry>(), nkb, plan.dextra,
+                 ctl, bits, cand_end, seg_off, (int)n_cand, mt.len);
       PANO_LAUNCH_CHECK();
-      replay_chain_kernel<<<1, 1024, chain_smem, st>>>(s.plan.as<WinEntry>(), Gc, steps, cand_end, seg_off, (int)n_cand,
-                                                      nseg, ctl, seg_tab + (size_t)c * G * nseg);
+      launch_pdl(replay_chain_kernel, dim3(1), dim3(1024), chain_smem, st, s.plan.as<WinEntry>(), Gc, steps, cand_end,
+                 seg_off, (int)n_cand, nseg, ctl, seg_tab + (size_t)c * G * nseg);
       PANO_LAUNCH_CHECK();
     }
     {
       int nthr = iters * nseg;
       if (pairs)
-        replay_segments_kernel<true><<<(nthr + 63) / 64, 64, 0, st>>>(mt.x.as<uint32_t>(), n, steps, s.thr.as<RT>(), seg_tab,
-                                                                      iters, nseg, ctl, seg_w);
+        launch_pdl(replay_segments_kernel<true>, dim3((nthr + 63) / 64), dim3(64), 0, st, mt.x.as<uint32_t>(), n, steps,
+                   s.thr.as<RT>(), seg_tab, iters, nseg, ctl, seg_w);
       else
-        replay_segments_kernel<false><<<(nthr + 63) / 64, 64, 0, st>>>(mt.x.as<uint32_t>(), n, steps, s.thr.as<RT>(), seg_tab,
-                                                                       iters, nseg, ctl, seg_w);
+        launch_pdl(replay_segments_kernel<false>, dim3((nthr + 63) / 64), dim3(64), 0, st, mt.x.as<uint32_t>(), n, steps,
+                   s.thr.as<RT>(), seg_tab, iters, nseg, ctl, seg_w);
       PANO_LAUNCH_CHECK();
-      combine_samples_kernel<<<(iters + 127) / 128, 128, 0, st>>>(seg_w, iters, nseg, samples_dev);
+      launch_pdl(combine_samples_kernel, dim3((iters + 127) / 128), dim3(128), 0, st, seg_w, iters, nseg, samples_dev);
       PANO_LAUNCH_CHECK();
     }
   }
 
-  dlt_kernel<<<(iters + DLT_WARPS - 1) / DLT_WARPS, DLT_WARPS * 32, 0, st>>>(s.pts.as<float4>(), s.samples.as<int4>(), iters,
-                                                                            s.Hs.as<double>(), s.valid.as<int>());
+  launch_pdl(dlt_kernel, dim3((iters + DLT_WARPS - 1) / DLT_WARPS), dim3(DLT_WARPS * 32), 0, st, s.pts.as<float4>(),
+             s.samples.as<int4>(), iters, s.Hs.as<double>(), s.valid.as<int>());
   PANO_LAUNCH_CHECK();
-  score_kernel<<<iters, 256, 0, st>>>(s.pts.as<float4>(), m, s.Hs.as<double>(), s.valid.as<int>(),
-                                      o.distance_threshold, s.counts.as<int>());
+  launch_pdl(score_kernel, dim3(iters), dim3(256), 0, st, s.pts.as<float4>(), m, s.Hs.as<double>(), s.valid.as<int>(),
+             o.distance_threshold, s.counts.as<int>());
   PANO_LAUNCH_CHECK();
   select_kernel<<<1, 1024, 0, st>>>(s.counts.as<int>(), iters, s.Hs.as<double>(), s.result.as<SelectOut>());
   PANO_LAUNCH_CHECK();
