@@ -673,13 +673,9 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
   if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
   // Pairs are independent: run them on several lanes (child contexts, each with its own stream,
   // scratch and host thread) so that one pair's host synchronisations, copies and low-occupancy
-  // kernels overlap with another pair's work.  PANO_BATCH_LANES (default 6, 1 = sequential).
-  int n_lanes = 6;
-  {
-    // each lane has a host thread that spin-waits in stream synchronisation: stay within the cores
-    unsigned hc = std::thread::hardware_concurrency();
-    if (hc > 0 && (int)hc < n_lanes) n_lanes = (int)hc;
-  }
+  // kernels overlap with another pair's work.  PANO_BATCH_LANES (default 16, 1 = sequential); lanes beyond the
+  // host cores poll-and-sleep instead of spinning inside the driver (g_yield_wait).
+  int n_lanes = 16;
   if (const char* e = getenv("PANO_BATCH_LANES")) n_lanes = atoi(e);
   if (n_lanes < 1) n_lanes = 1;
   if (n_lanes > 32) n_lanes = 32;
