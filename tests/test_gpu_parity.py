@@ -338,7 +338,7 @@ def test_replay_window_miss_is_detected_and_rerun(oracle, small_pair):
                                      (10837, 1000), (20001, 100), (40001, 30)])
 def test_ransac_resident_replay(engine, oracle, m, iters):
     """pano_set_replay_mode(1): samples, counts and H identical to the oracle (and so to the chunked
-    replay); m = 40001 exceeds the resident plan's band limit and must fall back to the chunked path"""
+    replay); m = 20001 and 40001 exceed the resident plan's limits and must fall back to the chunked path"""
     rng = np.random.default_rng(m)
     kp1 = rng.integers(0, 4000, (m, 2)).astype(np.int32)
     kp2 = (kp1 + np.array([900, 3]) + rng.integers(-40, 41, (m, 2))).astype(np.int32)

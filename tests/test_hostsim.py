@@ -84,7 +84,7 @@ def test_replay_total_draws_match_oracle_ransac(hostsim, oracle, small_pair):
 
 @pytest.mark.parametrize("n,iters", [(4, 64), (5, 64), (6, 64), (7, 64), (8, 64), (9, 33), (10, 100), (33, 100),
                                      (256, 300), (257, 300), (1000, 1000), (2500, 1000), (4097, 600),
-                                     (10774, 300), (10837, 200), (20001, 40)])
+                                     (10774, 300), (10837, 200), (12288, 60)])
 def test_resident_replay_matches_std_shuffle(hostsim, oracle, n, iters):
     """replay_resident_kernel's formulation (banded rejection cells from the exact start of every
     iteration, segment walks, chain, max-element tracking) == real std::shuffle."""
@@ -119,6 +119,8 @@ def test_resident_replay_band_miss_is_detected(hostsim, oracle):
 
 
 def test_resident_plan_limits(hostsim):
-    """the single-draw regime (n > 65535) and bands wider than a byte of diagonals stay on the chunked path"""
+    """the single-draw regime (n > 65535), shuffles longer than the CTA's 16 x 12 blocks of 32 steps and bands wider
+    than a byte of diagonals stay on the chunked path"""
     samples = np.zeros((4, 4), np.int32)
-    assert hostsim.hs_replay_resident(C.c_uint32(1), C.c_uint32(70000), 4, 1, C.c_double(0.0), p(samples, C.c_int32), None, None) == 32
+    for n in (70000, 40000, 20001, 12290):
+        assert hostsim.hs_replay_resident(C.c_uint32(1), C.c_uint32(n), 4, 1, C.c_double(0.0), p(samples, C.c_int32), None, None) == 32

@@ -30,15 +30,29 @@ struct CudaError {
   } while (0)
 
 // Host-side wait for a stream.  With more batch lanes than host cores (g_yield_wait > 0) the lanes must not
-// spin inside the driver: poll and sleep instead, so a lane costs a core only while it has host work to do.
+// spin inside the driver, and must not poll it either (every cudaStreamQuery takes the driver lock that the other
+// lanes' kernel launches need): the thread blocks on a blocking-sync event until the GPU interrupts.
 extern std::atomic<int> g_yield_wait;
 inline cudaError_t stream_wait(cudaStream_t st) {
   if (g_yield_wait.load(std::memory_order_relaxed) <= 0) return cudaStreamSynchronize(st);
-  for (;;) {
-    const cudaError_t e = cudaStreamQuery(st);
-    if (e != cudaErrorNotReady) return e;
-    std::this_thread::sleep_for(std::chrono::microseconds(20));
+  struct Ev {
+    cudaEvent_t e = nullptr;
+    int dev = -1;
+    ~Ev() { if (e) cudaEventDestroy(e); }
+  };
+  thread_local Ev ev;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!ev.e || ev.dev != dev) {
+    if (ev.e) cudaEventDestroy(ev.e);
+    ev.e = nullptr;
+    cudaError_t r = cudaEventCreateWithFlags(&ev.e, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (r != cudaSuccess) return r;
+    ev.dev = dev;
   }
+  cudaError_t r = cudaEventRecord(ev.e, st);
+  if (r != cudaSuccess) return r;
+  return cudaEventSynchronize(ev.e);
 }
 
 // Programmatic dependent launch: the next kernel of a stream is set up while the previous one drains; every kernel

@@ -342,7 +342,7 @@ __global__ void combine_samples_kernel(const int4* __restrict__ seg_w, int iters
 //            among the first four elements are replayed exactly by one thread
 // The stream window of the next iteration is prefetched with cp.async while the current one runs.
 // ---------------------------------------------------------------------------------------
-constexpr int RES_THREADS = 1024;
+constexpr int RES_THREADS = 32 * (int)RES_WARPS;
 
 struct ResParams {
   const uint32_t* X;
@@ -359,7 +359,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
                "l"(gsrc) : "memory");
 }
 
-__global__ void __launch_bounds__(RES_THREADS, 1)
+__global__ void __launch_bounds__(RES_THREADS, 2)
 replay_resident_kernel(ResParams P, ReplayCtl* ctl, int4* __restrict__ samples) {
   extern __shared__ __align__(16) uint8_t res_smem[];
   uint32_t* Xs0 = reinterpret_cast<uint32_t*>(res_smem);
@@ -401,7 +401,7 @@ replay_resident_kernel(ResParams P, ReplayCtl* ctl, int4* __restrict__ samples) 
   RT q[RES_MAXB];
 #pragma unroll
   for (uint32_t i = 0; i < RES_MAXB; i++) {
-    const uint32_t k = (warp + 32u * i) * 32u + lane;
+    const uint32_t k = (warp + RES_WARPS * i) * 32u + lane;
     q[i].r = 2u; q[i].T = 0u;                // steps past the end never reject
     if (k < steps) q[i] = P.rt[k];
   }
@@ -438,7 +438,7 @@ replay_resident_kernel(ResParams P, ReplayCtl* ctl, int4* __restrict__ samples) 
       const bool lead = lane == 0;
 #pragma unroll
       for (uint32_t i = 0; i < RES_MAXB; i++) {
-        const uint32_t b = warp + 32u * i;
+        const uint32_t b = warp + RES_WARPS * i;
         if (b < P.nkb) {
           const uint4 B = s_p1[b];
           const uint32_t* px = xl + B.x;

@@ -131,7 +131,9 @@ struct ResidentPlan {
 };
 
 constexpr uint32_t RES_MAX_DIAG = 250;        // diagonals are stored in bytes (255 = miss)
-constexpr uint32_t RES_MAXB = 12;             // 32-step blocks per warp of the kernel (32 warps): steps <= 12288
+constexpr uint32_t RES_WARPS = 16;            // warps of the resident CTA (512 threads: half an SM's registers, so it
+                                              // can be placed next to other kernels' CTAs instead of waiting for an idle SM)
+constexpr uint32_t RES_MAXB = 12;             // 32-step blocks per warp of the kernel: steps <= 32 * RES_WARPS * RES_MAXB
 constexpr size_t RES_SMEM_BUDGET = 200 * 1024;
 
 
@@ -269,7 +271,7 @@ inline ResidentPlan plan_resident(const ReplayPlan& P, uint32_t n, int window_sc
   // [s + steps, s + steps + dmax) are its possible starts, each needs steps + dmax + 32 words
   R.xcap = (steps + 2u * R.dmax + 64u + 3u) / 4u * 4u + 8u;
   R.smem_bytes = resident_smem_bytes(R);
-  R.ok = R.smem_bytes <= RES_SMEM_BUDGET && R.n_entries <= 1024u && nkb <= 32u * RES_MAXB && R.segb <= 255u;
+  R.ok = R.smem_bytes <= RES_SMEM_BUDGET && R.n_entries <= 32u * RES_WARPS && nkb <= RES_WARPS * RES_MAXB && R.segb <= 255u;
   return R;
 }
 
