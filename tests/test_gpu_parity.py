@@ -412,3 +412,31 @@ def test_stitch_batch_equals_pairs(engine, oracle, mem):
         cw, ch = r["canvas"][0], r["canvas"][1]
         got = outs[i] if mem == "host" else outs[i].cpu().numpy()
         assert np.array_equal(got[:cw * ch * 3].reshape(ch, cw, 3), canvas)
+
+
+def test_general_warp_kernel_equals_fast_path(oracle):
+    """PANO_WARP_FAST=0 forces the general (exact-division, 4 px per thread) kernel; it and the fast path must both
+    reproduce the oracle's canvas (pair overlay, plain warpPerspective, band-wise accumulate of chain mode)"""
+    import subprocess
+    import sys
+    import textwrap
+    from conftest import ROOT, PKG
+    code = textwrap.dedent('''
+        import sys, importlib, numpy as np
+        sys.path.insert(0, %r)
+        pkg = importlib.import_module(%r); synth = importlib.import_module(%r + ".synth")
+        from oracle.oracle import Oracle
+        O = Oracle(); eng = pkg.Engine(0, 12345)
+        left, right, _ = synth.make_pair(960, 540, seed=5)
+        canvas, r = eng.stitchTwoImages(left, right)
+        o = O.stitch_pair(left, right, seed=12345)
+        assert r["status"] == 0 and np.array_equal(canvas, o["canvas"])
+        M = np.array([[0.98, 0.03, 40.5], [-0.02, 1.01, 12.25], [1e-5, -2e-5, 1.0]])
+        w = eng.warpPerspective(right, M, (1100, 640))
+        assert np.array_equal(w, O.warp_perspective(right, M, (1100, 640)))
+        print("OK")
+    ''') % (ROOT, PKG, PKG)
+    for fast in ("0", "1"):
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                           env=dict(os.environ, PANO_WARP_FAST=fast))
+        assert p.returncode == 0 and "OK" in p.stdout, (fast, p.stderr[-800:])
