@@ -153,7 +153,9 @@ struct HarrisScratch {
 // Leaves the keypoints in kp (device) and returns their number.
 int harris_detect_device(cudaStream_t st, const DevImage& img, const pano_harris_opts& o,
                          HarrisScratch& s, DevKeypoints& kp, PinnedBuf& pin);
-void harris_response_device(cudaStream_t st, const DevImage& img, double k, double* resp_dev);
+// cand_dev (optional): one word per 32-px row segment, bit = response > thresh (consumed by the NMS kernel)
+void harris_response_device(cudaStream_t st, const DevImage& img, double k, double* resp_dev, double thresh = 0.0,
+                            uint32_t* cand_dev = nullptr, int cand_stride = 0);
 void convolve_f64_device(cudaStream_t st, const double* in, int w, int h, const double* kern_dev,
                          int ksize, double* out);
 

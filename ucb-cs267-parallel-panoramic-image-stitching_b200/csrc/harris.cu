@@ -30,7 +30,8 @@ struct GaussTaps {
 
 __global__ void __launch_bounds__(TX* BY)
 harris_response_kernel(const uint8_t* __restrict__ img, int w, int h, size_t stride, double kparam,
-                       GaussTaps taps, double* __restrict__ resp) {
+                       GaussTaps taps, double* __restrict__ resp, double thresh, uint32_t* __restrict__ cand,
+                       int cand_stride) {
   __shared__ uint8_t sgray[GH][GW + 2];
   __shared__ double sxx[PH][PW];
   __shared__ double syy[PH][PW];
@@ -105,32 +106,58 @@ harris_response_kernel(const uint8_t* __restrict__ img, int w, int h, size_t str
 #pragma unroll
   for (int o = 0; o < RPT; o++) {
     int Y = y0 + ty * RPT + o;
+    double r = 0.0;
     if (X < w && Y < h) {
-      double r = 0.0;
       if (X >= 2 && X <= w - 3 && Y >= 2 && Y <= h - 3) r = harris_resp(axx[o], ayy[o], axy[o], kparam);
       resp[(size_t)Y * w + X] = r;
+    }
+    // one word per 32-px row segment: which pixels exceed the NMS threshold at all (the NMS kernel then only
+    // loads the response around those; a warp is one row of the tile, the tile is 32 px wide)
+    if (cand != nullptr) {
+      const unsigned bits = __ballot_sync(0xffffffffu, X < w && Y < h && r > thresh);
+      if (tx == 0 && Y < h) cand[(size_t)Y * cand_stride + blockIdx.x] = bits;
     }
   }
 }
 
 // K2a: threshold + strict NMS over a (2*half+1)^2 neighbourhood -> bit mask + per-row counts.
 // ref: src/serial/main.cpp:157-180 (keep iff resp > thresh and resp > every neighbour).
+template <int HALF_T>   // HALF_T > 0: neighbourhood known at compile time (3x3: the reference's setting); 0: runtime `half`
 __global__ void nms_mask_kernel(const double* __restrict__ resp, int w, int h, double thresh, int half,
                                 uint32_t* __restrict__ mask, int mask_stride,
                                 uint32_t* __restrict__ rowcnt) {
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (y >= h) return;
+  if (HALF_T > 0) half = HALF_T;
   bool keep = false;
-  if (x >= half && x < w - half && y >= half && y < h - half) {
-    double r = resp[(size_t)y * w + x];
+  // the response kernel left "response > threshold" bits in the mask word this warp is about to overwrite
+  const uint32_t cword = mask[(size_t)y * mask_stride + blockIdx.x];
+  if (cword == 0u) return;   // (the word already holds the result: no keypoint in these 32 px)
+  if (((cword >> threadIdx.x) & 1u) && x >= half && x < w - half && y >= half && y < h - half) {
+    const double* c = resp + (size_t)y * w + x;
+    const double r = *c;
     if (r > thresh) {
-      keep = true;
-      for (int i = -half; i <= half && keep; i++)
-        for (int j = -half; j <= half; j++) {
-          if (i == 0 && j == 0) continue;
-          if (!(r > resp[(size_t)(y + i) * w + (x + j)])) { keep = false; break; }
-        }
+      if (HALF_T > 0) {
+        // all neighbours requested at once (independent loads), then one AND: "keep iff r > every neighbour" does
+        // not depend on the order the reference visits them in
+        double nb[(2 * HALF_T + 1) * (2 * HALF_T + 1)];
+#pragma unroll
+        for (int i = -HALF_T; i <= HALF_T; i++)
+#pragma unroll
+          for (int j = -HALF_T; j <= HALF_T; j++) nb[(i + HALF_T) * (2 * HALF_T + 1) + (j + HALF_T)] = c[(ptrdiff_t)i * w + j];
+        keep = true;
+#pragma unroll
+        for (int q = 0; q < (2 * HALF_T + 1) * (2 * HALF_T + 1); q++)
+          if (q != (2 * HALF_T + 1) * HALF_T + HALF_T) keep = keep && (r > nb[q]);
+      } else {
+        keep = true;
+        for (int i = -half; i <= half && keep; i++)
+          for (int j = -half; j <= half; j++) {
+            if (i == 0 && j == 0) continue;
+            if (!(r > c[(ptrdiff_t)i * w + j])) { keep = false; break; }
+          }
+      }
     }
   }
   unsigned b = __ballot_sync(0xffffffffu, keep);
@@ -281,10 +308,12 @@ void compact_flagged(cudaStream_t st, const uint8_t* flags, int n, int32_t* out_
   PANO_LAUNCH_CHECK();
 }
 
-void harris_response_device(cudaStream_t st, const DevImage& img, double k, double* resp_dev) {
+void harris_response_device(cudaStream_t st, const DevImage& img, double k, double* resp_dev, double thresh,
+                            uint32_t* cand_dev, int cand_stride) {
   static const GaussTaps taps = make_taps();
   dim3 grid((img.w + TX - 1) / TX, (img.h + TY - 1) / TY), block(TX, BY);
-  harris_response_kernel<<<grid, block, 0, st>>>(img.p, img.w, img.h, img.stride, k, taps, resp_dev);
+  harris_response_kernel<<<grid, block, 0, st>>>(img.p, img.w, img.h, img.stride, k, taps, resp_dev, thresh, cand_dev,
+                                                 cand_stride);
   PANO_LAUNCH_CHECK();
 }
 
@@ -306,12 +335,16 @@ int harris_detect_device(cudaStream_t st, const DevImage& img, const pano_harris
   s.total.reserve(sizeof(uint32_t));
   pin.reserve(64);
 
-  harris_response_device(st, img, o.k, s.resp.as<double>());
+  harris_response_device(st, img, o.k, s.resp.as<double>(), o.nms_thresh, s.mask.as<uint32_t>(), mask_stride);
   PANO_CUDA(cudaMemsetAsync(s.rowcnt.p, 0, sizeof(uint32_t) * (size_t)h, st));
   {
     dim3 block(32, 8), grid(mask_stride, (h + 7) / 8);
-    nms_mask_kernel<<<grid, block, 0, st>>>(s.resp.as<double>(), w, h, o.nms_thresh, o.nms_neighborhood / 2,
-                                            s.mask.as<uint32_t>(), mask_stride, s.rowcnt.as<uint32_t>());
+    if (o.nms_neighborhood == 3)
+      nms_mask_kernel<1><<<grid, block, 0, st>>>(s.resp.as<double>(), w, h, o.nms_thresh, 1, s.mask.as<uint32_t>(),
+                                                 mask_stride, s.rowcnt.as<uint32_t>());
+    else
+      nms_mask_kernel<0><<<grid, block, 0, st>>>(s.resp.as<double>(), w, h, o.nms_thresh, o.nms_neighborhood / 2,
+                                                 s.mask.as<uint32_t>(), mask_stride, s.rowcnt.as<uint32_t>());
     PANO_LAUNCH_CHECK();
   }
   exclusive_scan_u32(st, s.rowcnt.as<uint32_t>(), s.rowoff.as<uint32_t>(), h, s.total.as<uint32_t>());
