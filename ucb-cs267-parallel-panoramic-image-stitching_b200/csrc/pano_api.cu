@@ -703,7 +703,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
     pano_ctx* l = c->lanes[li];
     l->seed = c->seed;
     l->matcher = c->matcher;
-    l->replay_target = n_lanes > 1 ? 16000.0 : 0.0;
+    l->replay_target = n_lanes > 1 ? 4000.0 : 0.0;   // small chunks: least speculative work (19.9 k vs 17.8 k MP/s at 16000)
     l->replay_mode = c->replay_mode;   // (resident = 1 pays off from ~32 lanes on: it trades latency for GPU time)
     try {
       PANO_CUDA(cudaSetDevice(l->device));
