@@ -410,7 +410,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--pairs", type=int, default=72, help="4K pairs per GPU per step (one pano_stitch_batch call; 72 = 3, 6 or 9 per lane)")
+    ap.add_argument("--pairs", type=int, default=144, help="4K pairs per GPU per step (one pano_stitch_batch call; 144 = 6, 12 or 18 per lane; BASELINE config 5 is a batch of 256)")
     ap.add_argument("--distinct", type=int, default=4, help="distinct pairs the step cycles over (4 = 189 MB > L2)")
     ap.add_argument("--size", default="3840x2160")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
