@@ -185,6 +185,8 @@ int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescr
 
 struct RansacScratch {
   DevBuf pts, thr, cand_off, cand_samp, base, samples, Hs, valid, counts, result, mask, plan, pts_bits;
+  cudaStream_t side = nullptr;               // a pair's replay runs here while its matches are still being computed
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 struct RansacResult {
   int status;  // PANO_OK / PANO_ERR_*
@@ -205,7 +207,7 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
                            uint32_t seed, MtStream& mt, RansacScratch& s, PinnedBuf& pin,
                            int32_t* samples_out_host, int32_t* counts_out_host,
                            uint8_t* mask_out_host, int window_scale, double replay_target,
-                           int replay_mode);
+                           int replay_mode, int phase = 0);
 
 void warp_overlay_device(cudaStream_t st, const DevImage& left, const DevImage& right,
                          const CanvasGeom& g, uint8_t* canvas, size_t canvas_stride);

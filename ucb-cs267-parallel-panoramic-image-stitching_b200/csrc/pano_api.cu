@@ -31,6 +31,7 @@ struct pano_ctx {
   uint32_t seed = 0;
   int matcher = 0;  // 0 tensor-core, 1 SIMT
   double replay_target = 0;  // candidate walks per replay chunk (0 = default)
+  bool overlap_replay = true;  // stitch: start the shuffle replay as soon as the match count is known (own stream)
   int replay_mode = 0;       // 0: chunked speculative replay (lowest latency), 1: resident one-CTA replay (least work)
   cudaStream_t st = nullptr;
   bool owns_stream = true;
@@ -132,10 +133,11 @@ void run_matcher(pano_ctx* c, const DevDescriptors& q, const DevDescriptors& t) 
     match_simt_device(c->st, q, t, c->best.as<unsigned long long>());
 }
 
-// match stage on device-resident inputs; leaves matches in c->matches; returns count
+// match stage on device-resident inputs; leaves matches in c->matches; returns count.
+// query_ready: c->dQ already holds the query descriptors (nqi of them).
 int match_on_device(pano_ctx* c, const int32_t* kq, int nq, const int32_t* kt, int nt, const DevImage& iq,
-                    const DevImage& it, const pano_harris_opts& o, int offset) {
-  int nqi = build_descriptors_device(c->st, iq, kq, nq, o.patch_size, c->ms, c->dQ, c->pin);
+                    const DevImage& it, const pano_harris_opts& o, int offset, bool query_ready = false, int nqi_ready = 0) {
+  int nqi = query_ready ? nqi_ready : build_descriptors_device(c->st, iq, kq, nq, o.patch_size, c->ms, c->dQ, c->pin);
   int nti = build_descriptors_device(c->st, it, kt, nt, o.patch_size, c->ms, c->dT, c->pin);
   if (nqi == 0 || nti == 0) return 0;
   run_matcher(c, c->dQ, c->dT);
@@ -145,9 +147,19 @@ int match_on_device(pano_ctx* c, const int32_t* kq, int nq, const int32_t* kt, i
 }
 
 RansacResult ransac_retry(pano_ctx* c, const int32_t* kp1, const int32_t* kp2, const pano_dmatch* m, int n,
-                          const pano_ransac_opts& o, int32_t* samples, int32_t* counts, uint8_t* mask) {
+                          const pano_ransac_opts& o, int32_t* samples, int32_t* counts, uint8_t* mask,
+                          bool replay_prelaunched = false) {
   RansacResult r;
   int scale = 1;
+  if (replay_prelaunched) {
+    // the replay for exactly n matches is running (or done) on the side stream: join it and solve on top of it
+    PANO_CUDA(cudaEventRecord(c->rs.ev_join, c->rs.side));
+    PANO_CUDA(cudaStreamWaitEvent(c->st, c->rs.ev_join, 0));
+    r = ransac_device(c->st, kp1, kp2, m, n, o, c->seed, c->mt, c->rs, c->pin, samples, counts, mask, 1,
+                      c->replay_target, c->replay_mode, /*phase=*/2);
+    if (r.status >= 0) return r;
+    scale = 2;   // a speculation window was missed: re-run the whole thing wider, in order
+  }
   for (;;) {
     r = ransac_device(c->st, kp1, kp2, m, n, o, c->seed, c->mt, c->rs, c->pin, samples, counts, mask, scale,
                       c->replay_target, c->replay_mode);
@@ -159,6 +171,19 @@ RansacResult ransac_retry(pano_ctx* c, const int32_t* kp1, const int32_t* kp2, c
     r.status = PANO_ERR_CUDA;
   }
   return r;
+}
+
+// Enqueues the shuffle replay for n matches on the context's side stream (it needs the COUNT only).
+void prelaunch_replay(pano_ctx* c, int n, const pano_ransac_opts& o) {
+  if (!c->rs.side) {
+    PANO_CUDA(cudaStreamCreateWithFlags(&c->rs.side, cudaStreamNonBlocking));
+    PANO_CUDA(cudaEventCreateWithFlags(&c->rs.ev_fork, cudaEventDisableTiming));
+    PANO_CUDA(cudaEventCreateWithFlags(&c->rs.ev_join, cudaEventDisableTiming));
+  }
+  PANO_CUDA(cudaEventRecord(c->rs.ev_fork, c->st));          // earlier users of the replay scratch have finished
+  PANO_CUDA(cudaStreamWaitEvent(c->rs.side, c->rs.ev_fork, 0));
+  ransac_device(c->rs.side, nullptr, nullptr, nullptr, n, o, c->seed, c->mt, c->rs, c->pin, nullptr, nullptr, nullptr, 1,
+                c->replay_target, c->replay_mode, /*phase=*/1);
 }
 
 void fill_canvas_info(const CanvasGeom& g, pano_canvas_info* info) {
@@ -177,15 +202,33 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
   res->best_iteration = -1;
   cudaStream_t st = c->st;
   PANO_CUDA(cudaEventRecord(c->ev[0], st));
-  // 1. corner detection (ref :316-317)
-  res->n_kp_left = harris_detect_device(st, L, ho, c->hs, c->kpL, c->pin);
+  // 1. corner detection (ref :316-317) and 2. matching: right = query, left = train (ref :320).  The right image
+  // goes first: once its in-border keypoints are counted the number of matches M is known (every query keypoint
+  // gets its nearest neighbour; the max-SSD filter is vacuous at the reference's 1e8), and the shuffle replay -
+  // which depends on nothing but M - starts on its own stream underneath the left image's detection and the
+  // matching.  If the filter does remove matches the pre-launched replay is discarded and RANSAC runs in order.
   res->n_kp_right = harris_detect_device(st, R, ho, c->hs, c->kpR, c->pin);
+  bool prelaunched = false;
+  int nqi = 0;
+  const bool try_overlap = c->overlap_replay && ro.num_samples == 4;
+  if (try_overlap) {
+    nqi = build_descriptors_device(st, R, c->kpR.xy.as<int32_t>(), c->kpR.count, ho.patch_size, c->ms, c->dQ, c->pin);
+    if (nqi >= ro.num_samples && ro.num_iterations > 0) {
+      prelaunch_replay(c, nqi, ro);
+      prelaunched = true;
+    }
+  }
+  res->n_kp_left = harris_detect_device(st, L, ho, c->hs, c->kpL, c->pin);
   PANO_CUDA(cudaEventRecord(c->ev[1], st));
-  // 2. matching: right = query, left = train (ref :320)
   int m = match_on_device(c, c->kpR.xy.as<int32_t>(), c->kpR.count, c->kpL.xy.as<int32_t>(), c->kpL.count, R, L,
-                          ho, 0);
+                          ho, 0, try_overlap, nqi);
   res->n_matches = m;
   PANO_CUDA(cudaEventRecord(c->ev[2], st));
+  if (prelaunched && m != nqi) {   // not the count the replay was started for: let it drain, then ignore it
+    PANO_CUDA(cudaEventRecord(c->rs.ev_join, c->rs.side));
+    PANO_CUDA(cudaStreamWaitEvent(st, c->rs.ev_join, 0));
+    prelaunched = false;
+  }
   auto finish = [&](int status) {
     PANO_CUDA(cudaEventRecord(c->ev[4], st));
     PANO_CUDA(cudaEventSynchronize(c->ev[4]));
@@ -198,7 +241,7 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
   if (m == 0) return finish(PANO_ERR_NO_MATCHES);
   // 3. RANSAC (ref :327-332)
   RansacResult rr = ransac_retry(c, c->kpR.xy.as<int32_t>(), c->kpL.xy.as<int32_t>(), c->matches.as<pano_dmatch>(),
-                                 m, ro, nullptr, nullptr, nullptr);
+                                 m, ro, nullptr, nullptr, nullptr, prelaunched);
   PANO_CUDA(cudaEventRecord(c->ev[3], st));
   if (rr.status != PANO_OK) {
     int s = finish(rr.status);
@@ -294,6 +337,9 @@ void pano_destroy(pano_ctx* c) {
   c->lanes.clear();
   cudaSetDevice(c->device);
   if (c->st) cudaStreamSynchronize(c->st);
+  if (c->rs.side) { cudaStreamSynchronize(c->rs.side); cudaStreamDestroy(c->rs.side); }
+  if (c->rs.ev_fork) cudaEventDestroy(c->rs.ev_fork);
+  if (c->rs.ev_join) cudaEventDestroy(c->rs.ev_join);
   if (c->st_up) { cudaStreamSynchronize(c->st_up); cudaStreamDestroy(c->st_up); }
   if (c->st_down) { cudaStreamSynchronize(c->st_down); cudaStreamDestroy(c->st_down); }
   for (int q = 0; q < 2; q++) {
@@ -704,6 +750,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
     l->seed = c->seed;
     l->matcher = c->matcher;
     l->replay_target = n_lanes > 1 ? 4000.0 : 0.0;   // small chunks: least speculative work (19.9 k vs 17.8 k MP/s at 16000)
+    l->overlap_replay = false;   // (throughput mode overlaps across pairs; a second stream per lane only adds queue aliasing)
     l->replay_mode = c->replay_mode;   // (resident = 1 pays off from ~32 lanes on: it trades latency for GPU time)
     try {
       PANO_CUDA(cudaSetDevice(l->device));

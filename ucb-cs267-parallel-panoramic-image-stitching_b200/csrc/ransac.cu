@@ -907,7 +907,11 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
                            const pano_dmatch* matches_dev, int m, const pano_ransac_opts& o, uint32_t seed,
                            MtStream& mt, RansacScratch& s, PinnedBuf& pin, int32_t* samples_out_host,
                            int32_t* counts_out_host, uint8_t* mask_out_host, int window_scale, double replay_target,
-                           int replay_mode) {
+                           int replay_mode, int phase) {
+  // phase 0: everything; 1: only the shuffle replay (it depends on nothing but the match COUNT m, so a caller can
+  // enqueue it on another stream while the matches are still being computed); 2: only the solve (points, DLT,
+  // scoring, selection) on top of a replay enqueued by phase 1 with the same m / options / scale
+  const bool do_replay = phase != 2, do_solve = phase != 1;
   RansacResult res;
   memset(&res, 0, sizeof res);
   res.best_iter = -1;
@@ -965,7 +969,7 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
 
   // ---- stream: everything the walks can touch, with margin ---------------------------------
   uint64_t need = plan.stream_need;
-  mt_ensure(st, mt, seed, need, (uint64_t)steps + 4096);
+  if (do_replay) mt_ensure(st, mt, seed, need, (uint64_t)steps + 4096);
 
   // ---- buffers ---------------------------------------------------------------------------
   const int nseg = (int)((steps + PANO_SEG_STEPS - 1) / PANO_SEG_STEPS);
@@ -987,13 +991,15 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   s.mask.reserve((size_t)m);
   pin.reserve(sizeof(SelectOut) + 64);
 
-  PANO_CUDA(cudaMemcpyAsync(s.thr.p, plan.rt.data(), sizeof(RT) * plan.rt.size(), cudaMemcpyHostToDevice, st));
-  if (!resident)
-    PANO_CUDA(cudaMemcpyAsync(s.plan.p, win.data(), sizeof(WinEntry) * win.size(), cudaMemcpyHostToDevice, st));
-  PANO_CUDA(cudaMemsetAsync(s.base.p, 0, sizeof(ReplayCtl), st));
+  if (do_replay) {
+    PANO_CUDA(cudaMemcpyAsync(s.thr.p, plan.rt.data(), sizeof(RT) * plan.rt.size(), cudaMemcpyHostToDevice, st));
+    if (!resident)
+      PANO_CUDA(cudaMemcpyAsync(s.plan.p, win.data(), sizeof(WinEntry) * win.size(), cudaMemcpyHostToDevice, st));
+    PANO_CUDA(cudaMemsetAsync(s.base.p, 0, sizeof(ReplayCtl), st));
+  }
   uint32_t* bits = s.pts_bits.as<uint32_t>();
   int* dbi = reinterpret_cast<int*>(bits + (size_t)plan.n_diag * nkb);
-  if (!resident)
+  if (!resident && do_replay)
     PANO_CUDA(cudaMemcpyAsync(dbi, plan.diag_block_iter.data(), sizeof(int) * (size_t)n_dblocks, cudaMemcpyHostToDevice, st));
   ReplayCtl* ctl = s.base.as<ReplayCtl>();
   int* status_ptr = &ctl->status;
@@ -1003,10 +1009,14 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   int4* samples_dev = s.samples.as<int4>();
   int4* seg_w = samples_dev + (size_t)n_chunks * G;
 
-  build_points_kernel<<<(m + 255) / 256, 256, 0, st>>>(kp1_dev, kp2_dev, matches_dev, m, s.pts.as<float4>());
-  PANO_LAUNCH_CHECK();
+  if (do_solve) {
+    build_points_kernel<<<(m + 255) / 256, 256, 0, st>>>(kp1_dev, kp2_dev, matches_dev, m, s.pts.as<float4>());
+    PANO_LAUNCH_CHECK();
+  }
 
-  if (resident) {
+  if (!do_replay) {
+    // (samples were produced by an earlier phase-1 call)
+  } else if (resident) {
     // one CTA, iterations in order from exact offsets (throughput mode: leaves the other SMs to other pairs)
     ResBlock* blk_dev = s.plan.as<ResBlock>();
     uint32_t* eoff_dev = reinterpret_cast<uint32_t*>(blk_dev + rplan.nkb);
@@ -1058,6 +1068,10 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
     }
   }
 
+  if (!do_solve) {
+    res.status = PANO_OK;
+    return res;
+  }
   launch_pdl(dlt_kernel, dim3((iters + DLT_WARPS - 1) / DLT_WARPS), dim3(DLT_WARPS * 32), 0, st, s.pts.as<float4>(),
              s.samples.as<int4>(), iters, s.Hs.as<double>(), s.valid.as<int>());
   PANO_LAUNCH_CHECK();
