@@ -22,6 +22,8 @@ int hs_find_homography4(const float* src, const float* dst, double* H) {
   return find_homography4(src, dst, H, LtL, V);
 }
 
+double hs_inlier_d2_limit(double thr) { return inlier_d2_limit(thr); }
+
 int hs_is_inlier(const double* H, float x, float y, float qx, float qy, double thr) {
   return is_inlier(H, x, y, qx, qy, thr) ? 1 : 0;
 }

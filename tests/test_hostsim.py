@@ -124,3 +124,18 @@ def test_resident_plan_limits(hostsim):
     samples = np.zeros((4, 4), np.int32)
     for n in (70000, 40000, 20001, 12290):
         assert hostsim.hs_replay_resident(C.c_uint32(1), C.c_uint32(n), 4, 1, C.c_double(0.0), p(samples, C.c_int32), None, None) == 32
+
+
+def test_inlier_limit_is_exact_sqrt_threshold(hostsim):
+    """inlier_d2_limit(thr): d2 < limit  <=>  sqrt(d2) < thr for the doubles around the limit (score kernel's
+    square-root-free predicate)"""
+    import struct
+    hostsim.hs_inlier_d2_limit.restype = C.c_double
+    for thr in (3.0, 1.0, 0.5, 2.9999999, 1e-3, 7.25, 1e6):
+        lim = hostsim.hs_inlier_d2_limit(C.c_double(thr))
+        bits_ = struct.unpack("<Q", struct.pack("<d", lim))[0]
+        for k in range(-3, 4):
+            x = struct.unpack("<d", struct.pack("<Q", bits_ + k))[0]
+            assert (np.sqrt(np.float64(x)) < thr) == (x < lim), (thr, k)
+    assert hostsim.hs_inlier_d2_limit(C.c_double(0.0)) == 0.0 and hostsim.hs_inlier_d2_limit(C.c_double(-1.0)) == 0.0
+    assert np.isnan(hostsim.hs_inlier_d2_limit(C.c_double(float("nan"))))

@@ -8,6 +8,7 @@
 // operators and the translation unit is built with -ffp-contract=off.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <cfloat>
 #include <cmath>
 
@@ -238,6 +239,38 @@ PANO_HD bool is_inlier(const double* H, float x, float y, float qx, float qy, do
   float dx = PANO_FSUB(ex, qx), dy = PANO_FSUB(ey, qy);
   double d2 = PANO_DADD(PANO_DMUL((double)dx, (double)dx), PANO_DMUL((double)dy, (double)dy));
   return PANO_DSQRT(d2) < thr;
+}
+
+// The same predicate without the square root: sqrt is monotone and correctly rounded, so  sqrt(d2) < thr  holds
+// exactly for  d2 < lim  where lim is the smallest double whose rounded square root reaches thr (inlier_d2_limit,
+// computed once on the host by bisection over the doubles).  NaN / infinite d2 fail both forms.
+PANO_HD bool is_inlier_lim(const double* H, float x, float y, float qx, float qy, double lim) {
+  double xd = (double)x, yd = (double)y;
+  double X = PANO_DADD(PANO_DADD(PANO_DMUL(H[0], xd), PANO_DMUL(H[1], yd)), H[2]);
+  double Y = PANO_DADD(PANO_DADD(PANO_DMUL(H[3], xd), PANO_DMUL(H[4], yd)), H[5]);
+  double Wd = PANO_DADD(PANO_DADD(PANO_DMUL(H[6], xd), PANO_DMUL(H[7], yd)), H[8]);
+  double s = PANO_DDIV(1., Wd);
+  float ex = PANO_D2F(PANO_DMUL(X, s));
+  float ey = PANO_D2F(PANO_DMUL(Y, s));
+  float dx = PANO_FSUB(ex, qx), dy = PANO_FSUB(ey, qy);
+  double d2 = PANO_DADD(PANO_DMUL((double)dx, (double)dx), PANO_DMUL((double)dy, (double)dy));
+  return d2 < lim;
+}
+// (host only) smallest non-negative double x with sqrt(x) >= thr (so sqrt(d2) < thr  <=>  d2 < x); 0 if thr <= 0, NaN if thr is NaN
+inline double inlier_d2_limit(double thr) {
+  if (thr != thr) return thr;
+  if (!(thr > 0.0)) return 0.0;
+  if (std::isinf(thr)) return thr;               // every finite d2 qualifies, infinity does not
+  uint64_t lo = 0, hi = 0x7ff0000000000000ull;   // bit patterns of non-negative doubles are ordered like the values
+  while (lo < hi) {                              // invariant: sqrt(hi) >= thr
+    const uint64_t mid = lo + (hi - lo) / 2;
+    double x;
+    memcpy(&x, &mid, sizeof x);
+    if (std::sqrt(x) >= thr) hi = mid; else lo = mid + 1;
+  }
+  double x;
+  memcpy(&x, &lo, sizeof x);
+  return x;
 }
 
 // cv::perspectiveTransform, Point2f with a 3x3 double matrix.  ref: src/serial/main.cpp:342

@@ -797,7 +797,7 @@ score_kernel(const float4* __restrict__ pts, int m, const double* __restrict__ H
   int c = 0;
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
     float4 p = pts[i];
-    c += is_inlier(H, p.x, p.y, p.z, p.w, thr) ? 1 : 0;
+    c += is_inlier_lim(H, p.x, p.y, p.z, p.w, thr) ? 1 : 0;   // thr = inlier_d2_limit(distance threshold)
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -1076,7 +1076,7 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
              s.samples.as<int4>(), iters, s.Hs.as<double>(), s.valid.as<int>());
   PANO_LAUNCH_CHECK();
   launch_pdl(score_kernel, dim3(iters), dim3(256), 0, st, s.pts.as<float4>(), m, s.Hs.as<double>(), s.valid.as<int>(),
-             o.distance_threshold, s.counts.as<int>());
+             inlier_d2_limit(o.distance_threshold), s.counts.as<int>());
   PANO_LAUNCH_CHECK();
   select_kernel<<<1, 1024, 0, st>>>(s.counts.as<int>(), iters, s.Hs.as<double>(), s.result.as<SelectOut>());
   PANO_LAUNCH_CHECK();
