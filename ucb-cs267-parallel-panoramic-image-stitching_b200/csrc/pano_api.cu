@@ -730,7 +730,10 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
   {
     const unsigned hc = std::thread::hardware_concurrency();
     const char* e = getenv("PANO_YIELD_WAIT");
-    const bool yield_wait = e ? atoi(e) != 0 : (hc > 0 && n_lanes + 1 > (int)hc);
+    // (one process per GPU: the other ranks of this node have as many lane threads on the same cores)
+    const char* lw = getenv("LOCAL_WORLD_SIZE");
+    const int ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
+    const bool yield_wait = e ? atoi(e) != 0 : (hc > 0 && n_lanes * ranks + 1 > (int)hc);
     g_yield_wait = yield_wait ? 1 : 0;
   }
   while ((int)c->lanes.size() < n_lanes) {
