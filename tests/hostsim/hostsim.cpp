@@ -220,4 +220,36 @@ int hs_replay_resident(uint32_t seed, uint32_t n, int iters, int window_scale, d
   return 0;
 }
 
+// warp_coord_fast (the warp kernel's fast coordinate path) against the exact warp_coord over a whole canvas.
+// seed_mode: 0 = reciprocal truncated to 20 mantissa bits (what MUFU.RCP64H delivers), 1 = 2^-12 relative error,
+// 2 = a useless seed (half the reciprocal), 3 = the correctly rounded reciprocal.
+// out[0] = pixels whose accepted fast result differs from the exact one (must be 0), out[1] = pixels sent to the
+// exact path, out[2] = pixels checked.
+void hs_warp_fast_check(const double* Minv, int cw, int ch, int step, int seed_mode, uint64_t* out) {
+  out[0] = out[1] = out[2] = 0;
+  double Mx[3] = {32.0 * Minv[0], 32.0 * Minv[1], 32.0 * Minv[2]};
+  double My[3] = {32.0 * Minv[3], 32.0 * Minv[4], 32.0 * Minv[5]};
+  for (int y = 0; y < ch; y += step)
+    for (int xb = 0; xb < cw; xb += 64) {
+      const double xbd = (double)xb, yd = (double)y;
+      const double X0 = (Mx[0] * xbd + Mx[1] * yd) + Mx[2];
+      const double Y0 = (My[0] * xbd + My[1] * yd) + My[2];
+      const double W0 = (Minv[6] * xbd + Minv[7] * yd) + Minv[8];
+      for (int x1 = 0; x1 < 64 && xb + x1 < cw; x1++) {
+        const double Wd = W0 + Minv[6] * (double)x1;
+        double r0 = 1.0 / Wd;
+        if (seed_mode == 0) { uint64_t b; memcpy(&b, &r0, 8); b &= ~0xffffffffull; memcpy(&r0, &b, 8); }
+        else if (seed_mode == 1) r0 *= 1.000244140625;
+        else if (seed_mode == 2) r0 *= 0.5;
+        int Xf, Yf, Xe, Ye;
+        bool need;
+        warp_coord_fast(X0, Y0, W0, Mx[0], My[0], Minv[6], x1, r0, &Xf, &Yf, &need);
+        warp_coord(Minv, xb + x1, y, 64, &Xe, &Ye);
+        out[2]++;
+        if (need) out[1]++;
+        else if (Xf != Xe || Yf != Ye) out[0]++;
+      }
+    }
+}
+
 }  // extern "C"

@@ -139,3 +139,29 @@ def test_inlier_limit_is_exact_sqrt_threshold(hostsim):
             assert (np.sqrt(np.float64(x)) < thr) == (x < lim), (thr, k)
     assert hostsim.hs_inlier_d2_limit(C.c_double(0.0)) == 0.0 and hostsim.hs_inlier_d2_limit(C.c_double(-1.0)) == 0.0
     assert np.isnan(hostsim.hs_inlier_d2_limit(C.c_double(float("nan"))))
+
+
+@pytest.mark.parametrize("seed_mode", [0, 1, 2, 3])
+def test_warp_fast_coordinates_never_differ_from_exact(hostsim, seed_mode):
+    """warp.cu's fast coordinate path (checked Newton reciprocal + magic rounding, pano_core.cuh warp_coord_fast) either
+    reproduces OpenCV's exact  rint((X0 + M0 x1) * (32 / W))  or asks for the exact path - for a good seed, a poor
+    seed and a useless seed (which must send every pixel to the exact path), over whole canvases"""
+    rng = np.random.default_rng(5 + seed_mode)
+    out = np.zeros(3, np.uint64)
+    total_need = total = 0
+    mats = [np.array([[1.0046794925793106, -0.009686860045644952, 1923.8011703686257],
+                      [0.006395609059110648, 0.999516018010321, 0.0],
+                      [8.627383134815669e-07, -1.129114095386824e-06, 1.0]])]
+    for _ in range(6):
+        mats.append(np.array([[1 + rng.normal() * 0.05, rng.normal() * 0.05, rng.uniform(0, 2500)],
+                              [rng.normal() * 0.05, 1 + rng.normal() * 0.05, rng.uniform(0, 300)],
+                              [rng.normal() * 3e-6, rng.normal() * 3e-6, 1.0]]))
+    for H in mats:
+        Minv = np.ascontiguousarray(np.linalg.inv(H))
+        hostsim.hs_warp_fast_check(p(Minv, C.c_double), 5763, 2182, 7, seed_mode, p(out, C.c_uint64))
+        assert out[0] == 0, (seed_mode, H, out)
+        total_need += int(out[1]); total += int(out[2])
+    if seed_mode == 2:
+        assert total_need == total            # a useless seed must never be trusted
+    else:
+        assert total_need < total * 1e-3      # the exact path stays rare (about 6e-5 of the pixels)

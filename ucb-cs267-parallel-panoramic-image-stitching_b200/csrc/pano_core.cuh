@@ -27,6 +27,7 @@
 #define PANO_FSUB(a, b) __fsub_rn((a), (b))
 #define PANO_D2F(a) __double2float_rn((a))
 #define PANO_RINT_I(a) __double2int_rn((a))
+#define PANO_DFMA(a, b, c) __fma_rn((a), (b), (c))
 #else
 #define PANO_DMUL(a, b) ((a) * (b))
 #define PANO_DADD(a, b) ((a) + (b))
@@ -36,6 +37,7 @@
 #define PANO_FSUB(a, b) ((a) - (b))
 #define PANO_D2F(a) ((float)(a))
 #define PANO_RINT_I(a) ((int)lrint((a)))
+#define PANO_DFMA(a, b, c) (std::fma((a), (b), (c)))
 #endif
 
 namespace pano {
@@ -381,6 +383,52 @@ PANO_HD void warp_coord(const double* M, int x, int y, int bw0, int* Xo, int* Yo
   const int xb = (x / bw0) * bw0;
   const WarpRow r = warp_row_origin(M, xb, y);
   warp_coord_from(M, r, x - xb, Xo, Yo);
+}
+
+// ----------------------------------------------------------------------------------------
+// Fast evaluation of warp_coord_from for the warp kernel's fast path (warp.cu).  X0s, Y0s are the row-origin
+// numerators scaled by 32 (a power of two commutes with every rounding), M0s = 32 M[0], M3s = 32 M[3], M6 = M[6].
+//   OpenCV:  W = 32 / (W0 + M6 x1);  X = rint((X0 + M0 x1) * W)
+// Here 1 / Wd comes from two Newton steps on a seed r0 (the device's MUFU.RCP64H; ANY seed is safe: the second
+// step's residual e1 bounds the relative error of r2 by e1^2 + 2^-52), the product is rounded at 2^-20 with a magic
+// constant (mantissa of v + 1.5 * 2^32 = 2^51 + round(v * 2^20)), and the result is accepted only if its fraction
+// is at least 16 * 2^-20 away from one half and |e1| < 2^-22 (then |approx - exact| < 2^-22 * 2^-43.9 * ... is far
+// below the distance to the rounding boundary for |v| < 2^22, which the caller guarantees).  Otherwise *exact_needed
+// is set and the caller evaluates the exact expression (warp_coord).  Returns X, Y in 1/32 px.
+// ----------------------------------------------------------------------------------------
+PANO_HD void pano_d2words(double v, uint32_t* lo, uint32_t* hi) {
+#if defined(__CUDA_ARCH__)
+  *lo = (uint32_t)__double2loint(v);
+  *hi = (uint32_t)__double2hiint(v);
+#else
+  uint64_t b;
+  memcpy(&b, &v, sizeof b);
+  *lo = (uint32_t)b;
+  *hi = (uint32_t)(b >> 32);
+#endif
+}
+PANO_HD void warp_coord_fast(double X0s, double Y0s, double W0, double M0s, double M3s, double M6, int x1, double r0,
+                             int* Xo, int* Yo, bool* exact_needed) {
+  const double x1d = (double)x1;
+  const double Wd = PANO_DADD(W0, PANO_DMUL(M6, x1d));
+  const double Xn = PANO_DADD(X0s, PANO_DMUL(M0s, x1d));
+  const double Yn = PANO_DADD(Y0s, PANO_DMUL(M3s, x1d));
+  const double e0 = PANO_DFMA(-Wd, r0, 1.0);
+  const double r1 = PANO_DFMA(r0, e0, r0);
+  const double e1 = PANO_DFMA(-Wd, r1, 1.0);
+  const double r2 = PANO_DFMA(r1, e1, r1);
+  const double mx = PANO_DADD(PANO_DMUL(Xn, r2), 6442450944.0);
+  const double my = PANO_DADD(PANO_DMUL(Yn, r2), 6442450944.0);
+  uint32_t xl, xh, yl, yh;
+  pano_d2words(mx, &xl, &xh);
+  pano_d2words(my, &yl, &yh);
+  // fraction within 16 * 2^-20 of one half?  ((frac + 2^19 + 16) mod 2^20 <= 32)
+  const uint32_t tx = (xl + 0x80010u) & 0xFFFFFu, ty = (yl + 0x80010u) & 0xFFFFFu;
+  *exact_needed = (tx < ty ? tx : ty) <= 32u || !(fabs(e1) < 2.384185791015625e-07);   // |e1| < 2^-22
+  const uint32_t xl2 = xl + 0x80000u, yl2 = yl + 0x80000u;
+  const uint32_t xh2 = xh + (xl2 < xl ? 1u : 0u), yh2 = yh + (yl2 < yl ? 1u : 0u);
+  *Xo = (int)(((xl2 >> 20) | (xh2 << 12)) ^ 0x80000000u);
+  *Yo = (int)(((yl2 >> 20) | (yh2 << 12)) ^ 0x80000000u);
 }
 
 PANO_HD int sat_short(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }

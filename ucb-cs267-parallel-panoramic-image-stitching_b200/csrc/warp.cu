@@ -234,30 +234,12 @@ warp_fast_kernel(const uint8_t* __restrict__ left, size_t lstride, const uint8_t
         continue;
       }
       if (grp_in) {
-        const double x1d = (double)(32 * g + lane);
-        const double Wd = __dadd_rn(W0, __dmul_rn(F.Mw[0], x1d));
-        const double Xn = __dadd_rn(X0, __dmul_rn(F.Mx[0], x1d));
-        const double Yn = __dadd_rn(Y0, __dmul_rn(F.My[0], x1d));
-        const double r0 = rcp_seed(Wd);
-        const double e0 = __fma_rn(-Wd, r0, 1.0);
-        const double r1 = __fma_rn(r0, e0, r0);
-        const double e1 = __fma_rn(-Wd, r1, 1.0);
-        const double r2 = __fma_rn(r1, e1, r1);
-        // magic rounding: the mantissa of (v + 1.5 * 2^32) is 2^51 + round(v * 2^20)
-        const double mx = __dadd_rn(__dmul_rn(Xn, r2), 6442450944.0);
-        const double my = __dadd_rn(__dmul_rn(Yn, r2), 6442450944.0);
-        const uint32_t xl = (uint32_t)__double2loint(mx), xh = (uint32_t)__double2hiint(mx);
-        const uint32_t yl = (uint32_t)__double2loint(my), yh = (uint32_t)__double2hiint(my);
-        // fraction within 16 * 2^-20 of one half?  ((frac + 2^19 + 16) mod 2^20 <= 32)
-        const uint32_t tx = (xl + 0x80010u) & 0xFFFFFu, ty = (yl + 0x80010u) & 0xFFFFFu;
-        const bool exact_needed = min(tx, ty) <= 32u || !(fabs(e1) < 2.384185791015625e-07);   // |e1| < 2^-22
+        // OpenCV's X = rint((X0 + M0 x1) * (32 / W)) with a checked Newton reciprocal and magic rounding
+        // (pano_core.cuh warp_coord_fast; the host tier tests it against the exact expression)
+        const double Wseed = __dadd_rn(W0, __dmul_rn(F.Mw[0], (double)(32 * g + lane)));
         int X, Y;
-        {
-          const uint32_t xl2 = xl + 0x80000u, yl2 = yl + 0x80000u;
-          const uint32_t xh2 = xh + (xl2 < xl ? 1u : 0u), yh2 = yh + (yl2 < yl ? 1u : 0u);
-          X = (int)(__funnelshift_r(xl2, xh2, 20) ^ 0x80000000u);
-          Y = (int)(__funnelshift_r(yl2, yh2, 20) ^ 0x80000000u);
-        }
+        bool exact_needed;
+        warp_coord_fast(X0, Y0, W0, F.Mx[0], F.My[0], F.Mw[0], 32 * g + lane, rcp_seed(Wseed), &X, &Y, &exact_needed);
         if (x < P.cw) {
           if (exact_needed) warp_coord(P.M, x, y, P.bw0, &X, &Y);
           const int sx = X >> 5, sy = Y >> 5;
