@@ -180,9 +180,13 @@ def run_engine(a):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout must be one JSON line: NCCL logs (it prints its version even at WARN) go to stderr
-        os.environ["NCCL_DEBUG"] = os.environ.get("PANO_NCCL_DEBUG", os.environ.get("NCCL_DEBUG", "WARN"))
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout must be one JSON line: NCCL prints its version to stdout at every NCCL_DEBUG level above NONE
+        # (WARN included), so the variable is removed unless PANO_NCCL_DEBUG asks for a level (then to stderr)
+        if "PANO_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["PANO_NCCL_DEBUG"]
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     # overlapped lanes per GPU: each has a host thread (lanes beyond the cores poll-and-sleep instead of spinning);

@@ -27,7 +27,10 @@ def main():
     import torch
     import torch.distributed as dist
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    os.environ["NCCL_DEBUG"] = os.environ.get("PANO_NCCL_DEBUG", "WARN")
+    if "PANO_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["PANO_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)   # (any level above NONE prints the NCCL version to stdout)
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module(PKG)
