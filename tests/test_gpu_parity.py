@@ -326,6 +326,11 @@ def test_replay_window_miss_is_detected_and_rerun(oracle, small_pair):
         kl, kr = O.detect(left), O.detect(right); m = O.match(kr, kl, right, left)
         g = eng.computeHomography(kr, kl, m, details=True); c = O.ransac(kr, kl, m, seed=12345)
         assert np.array_equal(g["samples"], c["samples"]) and np.array_equal(g["counts"], c["counts"])
+        # the fused pair call pre-launches the replay on a side stream: a miss there must fall back to the in-order
+        # re-run as well
+        canvas, r = eng.stitchTwoImages(left, right); o = O.stitch_pair(left, right, seed=12345)
+        assert r["status"] == 0 and np.array_equal(canvas, o["canvas"])
+        assert np.array_equal(r["H"].view(np.uint64), o["H"].view(np.uint64))
         print("OK", len(m))
     ''') % (ROOT, PKG, PKG)
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
