@@ -724,29 +724,27 @@ dlt_kernel(const float4* __restrict__ pts, const int4* __restrict__ samples, int
       sm.V[9 * l + i] = __dadd_rn(__dmul_rn(a0, s), __dmul_rn(b0, c));
     }
     __syncwarp();
-    // refresh indR / indC of rows k and l only (as OpenCV does)
-    if (lane < 4) {
-      const int idx = (lane & 1) ? l : k;
-      if (lane < 2) {
-        if (idx < 8) {
-          int mm = idx + 1;
-          double mv = fabs(sm.S[9 * idx + mm]);
-          for (int i = idx + 2; i < 9; i++) {
-            double val = fabs(sm.S[9 * idx + i]);
-            if (mv < val) mv = val, mm = i;
-          }
-          sm.indR[idx] = mm;
-        }
-      } else {
-        if (idx > 0) {
-          int mm = 0;
-          double mv = fabs(sm.S[idx]);
-          for (int i = 1; i < idx; i++) {
-            double val = fabs(sm.S[9 * i + idx]);
-            if (mv < val) mv = val, mm = i;
-          }
-          sm.indC[idx] = mm;
-        }
+    // refresh indR / indC of rows k and l only (as OpenCV does): four independent "first maximum" scans of at most
+    // 8 elements, one per group of 8 lanes (group 0: indR[k], 1: indR[l], 2: indC[k], 3: indC[l]), reduced with
+    // three xor-shuffles inside the group; ties keep the lowest index = OpenCV's strict '<' scan
+    {
+      const int grp = lane >> 3, j = lane & 7;
+      const int idx = (grp & 1) ? l : k;
+      const bool rowscan = grp < 2;
+      // row scan: elements idx+1 .. 8 of row idx; column scan: elements 0 .. idx-1 of column idx (S is symmetric)
+      const int e = rowscan ? idx + 1 + j : j;
+      const bool valid = rowscan ? (idx < 8 && e < 9) : (idx > 0 && e < idx);
+      double v = valid ? fabs(sm.S[9 * idx + (valid ? e : 0)]) : -1.0;
+      int pos = j;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
+        if (v2 > v || (v2 == v && p2 < pos)) { v = v2; pos = p2; }
+      }
+      if (j == 0) {
+        if (rowscan) { if (idx < 8) sm.indR[idx] = idx + 1 + pos; }
+        else         { if (idx > 0) sm.indC[idx] = pos; }
       }
     }
     __syncwarp();
