@@ -1,0 +1,3 @@
+// opencv2/features2d.hpp stand-in (test infrastructure): the whole slice of cv:: the reference uses lives in cvshim.hpp
+#pragma once
+#include "../cvshim.hpp"

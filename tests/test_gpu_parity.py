@@ -445,3 +445,21 @@ def test_general_warp_kernel_equals_fast_path(oracle):
         p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
                            env=dict(os.environ, PANO_WARP_FAST=fast))
         assert p.returncode == 0 and "OK" in p.stdout, (fast, p.stderr[-800:])
+
+
+def test_ransac_rejects_out_of_range_match_indices(engine, oracle, small_pair):
+    """pano_ransac checks the caller's match indices against n1 / n2 on the device: an index outside the keypoint
+    lists (the reference would read past its vectors) is reported as PANO_ERR_INVALID, never dereferenced, and the
+    context keeps working afterwards"""
+    pkg = load_pkg()
+    left, right, _ = small_pair
+    kl, kr = oracle.detect(left), oracle.detect(right)
+    m = oracle.match(kr, kl, right, left)
+    for field, bad in (("queryIdx", len(kr) + 3), ("trainIdx", len(kl)), ("trainIdx", -1)):
+        mb = m.copy()
+        mb[field][7] = bad
+        with pytest.raises(pkg.PanoError) as ei:
+            engine.computeHomography(kr, kl, mb)
+        assert ei.value.status == pkg.PANO_ERR_INVALID
+    H = engine.computeHomography(kr, kl, m)
+    assert np.array_equal(bits(H), bits(oracle.ransac(kr, kl, m, seed=12345)["H"]))

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -32,9 +33,11 @@ struct CudaError {
 // Host-side wait for a stream.  With more batch lanes than host cores (g_yield_wait > 0) the lanes must not
 // spin inside the driver, and must not poll it either (every cudaStreamQuery takes the driver lock that the other
 // lanes' kernel launches need): the thread blocks on a blocking-sync event until the GPU interrupts.
-extern std::atomic<int> g_yield_wait;
+// The flag is per host thread (a batch call sets it in its own lane threads), so concurrent batch calls on other
+// contexts / GPUs do not flip each other's wait mode.
+extern thread_local int t_yield_wait;
 inline cudaError_t stream_wait(cudaStream_t st) {
-  if (g_yield_wait.load(std::memory_order_relaxed) <= 0) return cudaStreamSynchronize(st);
+  if (t_yield_wait <= 0) return cudaStreamSynchronize(st);
   struct Ev {
     cudaEvent_t e = nullptr;
     int dev = -1;
@@ -170,25 +173,34 @@ void compact_flagged(cudaStream_t st, const uint8_t* flags, int n, int32_t* out_
 struct MatchScratch {
   DevBuf flags, tmp, best, cnt, mflags, midx, mtmp, tc_err;
 };
+// Device-side error word of a context (bits OR-ed in by kernels, read back with every result the host waits for):
+constexpr int PANO_ERRW_TC_ABORT = 1;    // tensor-core matcher: a pipeline wait gave up (CTA aborted)
+constexpr int PANO_ERRW_NO_BEST = 2;     // a query row has no minimum although train descriptors exist
+constexpr int PANO_ERRW_BAD_INDEX = 4;   // a match refers to a keypoint outside [0, n1) x [0, n2)
 int build_descriptors_device(cudaStream_t st, const DevImage& img, const int32_t* xy, int n, int patch,
                              MatchScratch& s, DevDescriptors& d, PinnedBuf& pin);
 // best[i] = (ssd << 32 | j) over all train descriptors, lowest j on ties
 void match_simt_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
                        unsigned long long* best);
 void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
-                     unsigned long long* best, DevBuf& errbuf);
+                     unsigned long long* best, DevBuf& keybuf, int* errw);
 bool match_tc_available();
+void match_tc_disable();
 // turns best[] into pano_match records (ascending query order), applying maxSSD; returns count
 int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
                         const unsigned long long* best, double max_ssd, int offset, int patch,
-                        MatchScratch& s, pano_dmatch* out_dev, PinnedBuf& pin);
+                        MatchScratch& s, pano_dmatch* out_dev, PinnedBuf& pin, int* errw);
 
 struct RansacScratch {
   DevBuf pts, thr, cand_off, cand_samp, base, samples, Hs, valid, counts, result, mask, plan, pts_bits;
+  std::shared_ptr<void> plan_cache;          // host-side replay plans of this context (ransac.cu), keyed by (M, iterations, ...)
+  int* errw = nullptr;                       // the context's device error word (see PANO_ERRW_*)
+  int n1 = 0, n2 = 0;                        // keypoint counts the match indices are checked against (0 = unknown)
   cudaStream_t side = nullptr;               // a pair's replay runs here while its matches are still being computed
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 struct RansacResult {
+  int errw;    // the context's device error word at the time of the read-back (0 = clean)
   int status;  // PANO_OK / PANO_ERR_*
   double H[9];
   int best_count, best_iter;

@@ -104,11 +104,14 @@ match_simt_kernel(const uint8_t* __restrict__ qd, int nq, const uint8_t* __restr
 __global__ void emit_matches_kernel(const unsigned long long* __restrict__ best, int nq,
                                     const int32_t* __restrict__ qorig, const int32_t* __restrict__ torig,
                                     double max_ssd, int offset, pano_dmatch* __restrict__ out,
-                                    uint8_t* __restrict__ flags) {
+                                    uint8_t* __restrict__ flags, int* __restrict__ errw) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nq) return;
   unsigned long long key = best[i];
   uint32_t ssd = (uint32_t)(key >> 32), j = (uint32_t)key;
+  // every query row has a minimum when train descriptors exist; a row without one means the matcher did not
+  // finish (aborted CTA): flag it, the host fails the call when it reads the error word
+  if (key == ~0ull) atomicOr(errw, PANO_ERRW_NO_BEST);
   bool ok = key != ~0ull && (double)ssd < max_ssd;
   pano_dmatch m;
   m.query_idx = qorig[i] + offset;
@@ -175,7 +178,7 @@ void match_simt_device(cudaStream_t st, const DevDescriptors& q, const DevDescri
 
 int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
                         const unsigned long long* best, double max_ssd, int offset, int patch,
-                        MatchScratch& s, pano_dmatch* out_dev, PinnedBuf& pin) {
+                        MatchScratch& s, pano_dmatch* out_dev, PinnedBuf& pin, int* errw) {
   const int nq = q.count;
   if (nq == 0 || t.count == 0) return 0;
   // every SSD is <= patch^2*3*255^2; above that bound the threshold can never reject
@@ -183,7 +186,7 @@ int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescr
   const bool need_filter = !(max_ssd > ssd_bound);
   if (!need_filter) {
     emit_matches_kernel<<<(nq + 255) / 256, 256, 0, st>>>(best, nq, q.orig.as<int32_t>(), t.orig.as<int32_t>(),
-                                                         max_ssd, offset, out_dev, nullptr);
+                                                         max_ssd, offset, out_dev, nullptr, errw);
     PANO_LAUNCH_CHECK();
     return nq;
   }
@@ -194,7 +197,7 @@ int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescr
   pin.reserve(64);
   emit_matches_kernel<<<(nq + 255) / 256, 256, 0, st>>>(best, nq, q.orig.as<int32_t>(), t.orig.as<int32_t>(),
                                                        max_ssd, offset, s.mtmp.as<pano_dmatch>(),
-                                                       s.mflags.as<uint8_t>());
+                                                       s.mflags.as<uint8_t>(), errw);
   PANO_LAUNCH_CHECK();
   compact_flagged(st, s.mflags.as<uint8_t>(), nq, s.midx.as<int32_t>(), s.cnt.as<uint32_t>(), s.tmp);
   PANO_CUDA(cudaMemcpyAsync(pin.p, s.cnt.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -310,7 +310,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0 && S.abort_flag) atomicExch(err, 1);
+  if (threadIdx.x == 0 && S.abort_flag) atomicOr(err, PANO_ERRW_TC_ABORT);
   if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
@@ -327,6 +327,7 @@ std::atomic<int> g_tc_state{0};  // 0 unknown, 1 usable, -1 disabled after a fai
 }  // namespace
 
 bool match_tc_available() { return g_tc_state >= 0; }
+void match_tc_disable() { g_tc_state = -1; }
 
 namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -356,44 +357,41 @@ void make_tmap(CUtensorMap* map, const void* base, size_t rows, uint32_t box_row
 }  // namespace
 
 void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t, unsigned long long* best,
-                     DevBuf& errbuf) {
+                     DevBuf& keybuf, int* errw) {
   PANO_CUDA(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * (size_t)q.count, st));
   if (q.count == 0 || t.count == 0) return;
   const int n_qtiles = (q.count + TM - 1) / TM;
   const int n_ttiles = (t.count + TN - 1) / TN;
-  // errbuf: [0] pipeline error flag, [256 B ...] the train side's column constants
-  errbuf.reserve(256 + sizeof(int) * (size_t)n_ttiles * TN);
-  PANO_CUDA(cudaMemsetAsync(errbuf.p, 0, sizeof(int), st));
-  int* tkey = reinterpret_cast<int*>(errbuf.as<uint8_t>() + 256);
+  // keybuf: the train side's column constants
+  keybuf.reserve(256 + sizeof(int) * (size_t)n_ttiles * TN);
+  int* tkey = reinterpret_cast<int*>(keybuf.as<uint8_t>() + 256);
   tkey_kernel<<<(n_ttiles * TN + 255) / 256, 256, 0, st>>>(t.norm.as<uint32_t>(), t.count, n_ttiles * TN, tkey);
   PANO_LAUNCH_CHECK();
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
   // flattened (query tile, train tile) grid split into equal contiguous runs, one per SM
   const int n_tiles = n_qtiles * n_ttiles;
   const int grid = n_tiles < sms ? n_tiles : sms;
   const size_t smem = sizeof(Smem) + 1024;
-  PANO_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool attr_set = [&] {
+    PANO_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return true;
+  }();
+  (void)attr_set;
   // descriptor buffers are padded to a multiple of 256 rows (build_descriptors_device)
   CUtensorMap tmap_q, tmap_t;
   make_tmap(&tmap_q, q.desc.p, ((size_t)q.count + 255) / 256 * 256, TM);
   make_tmap(&tmap_t, t.desc.p, ((size_t)t.count + 255) / 256 * 256, TN);
+  // A CTA whose pipeline wait gives up ORs PANO_ERRW_TC_ABORT into the context's error word; the host sees it
+  // with the next result it waits for (every call, not only the first), fails the call and disables this path.
   match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_t, q.norm.as<uint32_t>(), q.count,
-                                                  tkey, t.count, n_ttiles, n_tiles, best,
-                                                  errbuf.as<int>());
+                                                  tkey, t.count, n_ttiles, n_tiles, best, errw);
   PANO_LAUNCH_CHECK();
-  if (g_tc_state == 0) {
-    // first use on this process: make sure the pipeline ran to completion
-    int e = 0;
-    PANO_CUDA(cudaMemcpyAsync(&e, errbuf.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    PANO_CUDA(stream_wait(st));
-    if (e != 0) {
-      g_tc_state = -1;
-      throw CudaError{cudaErrorLaunchFailure, "tensor-core matcher pipeline timed out", __FILE__, __LINE__};
-    }
-    g_tc_state = 1;
-  }
+  if (g_tc_state == 0) g_tc_state = 1;
 }
 
 }  // namespace pano

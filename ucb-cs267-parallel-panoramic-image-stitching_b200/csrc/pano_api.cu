@@ -12,15 +12,10 @@
 #include <thread>
 
 namespace pano {
-std::atomic<int> g_yield_wait{0};
-
-// Batch lanes are independent streams; with the default of 8 hardware work queues, streams alias onto the same
-// queue and a lane's kernels wait behind another lane's.  Has to be in the environment before the CUDA context
-// exists, so it is set when the library is loaded (an explicit setting wins).
-static const int g_env_init = [] {
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
-  return 0;
-}();
+thread_local int t_yield_wait = 0;
+// (The library does not touch the process environment.  Batch lanes are independent streams; with the default of 8
+// hardware work queues they alias, so callers that batch should export CUDA_DEVICE_MAX_CONNECTIONS=32 before the
+// CUDA context exists - bench.py and the executables do; see INTEGRATION.md.)
 std::atomic<uint64_t> g_kernel_launches{0};
 }
 
@@ -37,6 +32,7 @@ struct pano_ctx {
   bool owns_stream = true;
   std::string err;
   PinnedBuf pin;
+  DevBuf errw;   // device error word (PANO_ERRW_* bits), read back with every result the host waits for
   DevBuf up[2];  // staging for host images
   // batch lanes with host buffers: the next pair's images are uploaded, and the previous canvas downloaded, on
   // their own streams while this pair is being stitched
@@ -128,7 +124,7 @@ int check_harris(const pano_harris_opts& o) {
 void run_matcher(pano_ctx* c, const DevDescriptors& q, const DevDescriptors& t) {
   c->best.reserve(sizeof(unsigned long long) * (size_t)std::max(q.count, 1));
   if (c->matcher == 0 && match_tc_available())
-    match_tc_device(c->st, q, t, c->best.as<unsigned long long>(), c->ms.tc_err);
+    match_tc_device(c->st, q, t, c->best.as<unsigned long long>(), c->ms.tc_err, c->errw.as<int>());
   else
     match_simt_device(c->st, q, t, c->best.as<unsigned long long>());
 }
@@ -143,7 +139,29 @@ int match_on_device(pano_ctx* c, const int32_t* kq, int nq, const int32_t* kt, i
   run_matcher(c, c->dQ, c->dT);
   c->matches.reserve(sizeof(pano_dmatch) * (size_t)nqi);
   return emit_matches_device(c->st, c->dQ, c->dT, c->best.as<unsigned long long>(), o.max_ssd_thresh, offset,
-                             o.patch_size, c->ms, c->matches.as<pano_dmatch>(), c->pin);
+                             o.patch_size, c->ms, c->matches.as<pano_dmatch>(), c->pin, c->errw.as<int>());
+}
+
+// Turns a non-zero device error word into a failed call: message, word cleared, and a matcher whose pipeline
+// aborted is not used again by this process (the SIMT matcher takes over on the next call).
+int fail_errw(pano_ctx* c, int errw) {
+  char buf[256];
+  snprintf(buf, sizeof buf, "device error word 0x%x:%s%s%s", errw,
+           (errw & PANO_ERRW_TC_ABORT) ? " tensor-core matcher pipeline timed out;" : "",
+           (errw & PANO_ERRW_NO_BEST) ? " a query row has no nearest neighbour (matcher did not finish);" : "",
+           (errw & PANO_ERRW_BAD_INDEX) ? " a match index is outside the keypoint lists;" : "");
+  c->err = buf;
+  if (errw & (PANO_ERRW_TC_ABORT | PANO_ERRW_NO_BEST)) match_tc_disable();
+  cudaMemsetAsync(c->errw.p, 0, sizeof(int), c->st);
+  return (errw & ~PANO_ERRW_BAD_INDEX) ? PANO_ERR_CUDA : PANO_ERR_INVALID;
+}
+
+// waits for the context's stream and returns the device error word as it was at that point
+int wait_errw(pano_ctx* c) {
+  int* slot = reinterpret_cast<int*>(c->pin.as<char>() + 1024);
+  PANO_CUDA(cudaMemcpyAsync(slot, c->errw.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  PANO_CUDA(stream_wait(c->st));
+  return *slot;
 }
 
 RansacResult ransac_retry(pano_ctx* c, const int32_t* kp1, const int32_t* kp2, const pano_dmatch* m, int n,
@@ -157,16 +175,16 @@ RansacResult ransac_retry(pano_ctx* c, const int32_t* kp1, const int32_t* kp2, c
     PANO_CUDA(cudaStreamWaitEvent(c->st, c->rs.ev_join, 0));
     r = ransac_device(c->st, kp1, kp2, m, n, o, c->seed, c->mt, c->rs, c->pin, samples, counts, mask, 1,
                       c->replay_target, c->replay_mode, /*phase=*/2);
-    if (r.status >= 0) return r;
+    if (r.status >= 0 || r.errw) return r;
     scale = 2;   // a speculation window was missed: re-run the whole thing wider, in order
   }
   for (;;) {
     r = ransac_device(c->st, kp1, kp2, m, n, o, c->seed, c->mt, c->rs, c->pin, samples, counts, mask, scale,
                       c->replay_target, c->replay_mode);
-    if (r.status >= 0 || scale >= 16) break;
+    if (r.status >= 0 || r.errw || scale >= 16) break;
     scale *= 2;  // a speculation window was missed: re-run wider (exactness is never traded)
   }
-  if (r.status < 0) {
+  if (r.status < 0 && !r.errw) {
     c->err = "shuffle replay could not be resolved";
     r.status = PANO_ERR_CUDA;
   }
@@ -230,8 +248,11 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
     prelaunched = false;
   }
   auto finish = [&](int status) {
+    int* ew_slot = reinterpret_cast<int*>(c->pin.as<char>() + 1024);
+    PANO_CUDA(cudaMemcpyAsync(ew_slot, c->errw.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     PANO_CUDA(cudaEventRecord(c->ev[4], st));
     PANO_CUDA(cudaEventSynchronize(c->ev[4]));
+    if (*ew_slot) status = fail_errw(c, *ew_slot);
     cudaEventElapsedTime(&res->ms_detect, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&res->ms_match, c->ev[1], c->ev[2]);
     cudaEventElapsedTime(&res->ms_total, c->ev[0], c->ev[4]);
@@ -240,9 +261,12 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
   };
   if (m == 0) return finish(PANO_ERR_NO_MATCHES);
   // 3. RANSAC (ref :327-332)
+  c->rs.n1 = c->kpR.count;
+  c->rs.n2 = c->kpL.count;
   RansacResult rr = ransac_retry(c, c->kpR.xy.as<int32_t>(), c->kpL.xy.as<int32_t>(), c->matches.as<pano_dmatch>(),
                                  m, ro, nullptr, nullptr, nullptr, prelaunched);
   PANO_CUDA(cudaEventRecord(c->ev[3], st));
+  if (rr.errw) rr.status = fail_errw(c, rr.errw);
   if (rr.status != PANO_OK) {
     int s = finish(rr.status);
     cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
@@ -256,9 +280,9 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
   canvas_geometry(L.w, L.h, R.w, R.h, rr.H, &g);
   fill_canvas_info(g, &res->canvas);
   if (homography_only) {  // chain mode: the canvas is composed later from all homographies
-    finish(PANO_OK);
+    int s = finish(PANO_OK);
     cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
-    return PANO_OK;
+    return s;
   }
   if (!g.ok) {
     int s = finish(PANO_ERR_ROI);
@@ -269,7 +293,7 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
   size_t pitch = align_up((size_t)g.cw * 3, 256);
   c->canvas[nxt].reserve(pitch * (size_t)g.ch);
   warp_overlay_device(st, L, R, g, c->canvas[nxt].as<uint8_t>(), pitch);
-  finish(PANO_OK);
+  if (int s = finish(PANO_OK)) return s;
   cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
   cudaEventElapsedTime(&res->ms_warp, c->ev[3], c->ev[4]);
   c->cur = nxt;
@@ -322,6 +346,9 @@ int pano_create(int device, uint32_t seed, pano_ctx** out) {
     PANO_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (auto& e : c->ev) PANO_CUDA(cudaEventCreate(&e));
     c->pin.reserve(4096);
+    c->errw.reserve(256);
+    PANO_CUDA(cudaMemsetAsync(c->errw.p, 0, 256, c->st));
+    c->rs.errw = c->errw.as<int>();
   } catch (const CudaError&) {
     cudaGetLastError();
     delete c;
@@ -348,7 +375,7 @@ void pano_destroy(pano_ctx* c) {
     c->upq[q][0].release();
     c->upq[q][1].release();
   }
-  DevBuf* bufs[] = {&c->up[0], &c->up[1], &c->kpup[0], &c->kpup[1], &c->mup, &c->hs.resp, &c->hs.mask, &c->hs.rowcnt,
+  DevBuf* bufs[] = {&c->errw, &c->up[0], &c->up[1], &c->kpup[0], &c->kpup[1], &c->mup, &c->hs.resp, &c->hs.mask, &c->hs.rowcnt,
                     &c->hs.rowoff, &c->hs.total, &c->kpL.xy, &c->kpR.xy, &c->ms.flags, &c->ms.tmp, &c->ms.best,
                     &c->ms.cnt, &c->ms.mflags, &c->ms.midx, &c->ms.mtmp, &c->ms.tc_err, &c->dQ.desc, &c->dQ.norm, &c->dQ.orig,
                     &c->dT.desc, &c->dT.norm, &c->dT.orig, &c->best, &c->matches, &c->rs.pts, &c->rs.thr,
@@ -460,7 +487,7 @@ int pano_match(pano_ctx* c, const int32_t* kp_query, int n_query, const int32_t*
   if (out && ncopy > 0)
     PANO_CUDA(cudaMemcpyAsync(out, c->matches.p, sizeof(pano_dmatch) * (size_t)ncopy,
                               mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
-  PANO_CUDA(stream_wait(c->st));
+  if (int ew = wait_errw(c)) return fail_errw(c, ew);
   return (out && m > cap) ? PANO_ERR_CAPACITY : PANO_OK;
   API_CATCH(c)
 }
@@ -478,7 +505,10 @@ int pano_ransac(pano_ctx* c, const int32_t* kp1, int n1, const int32_t* kp2, int
   const int32_t* d1 = (const int32_t*)upload(c, c->kpup[0], kp1, sizeof(int32_t) * 2 * (size_t)n1, mem);
   const int32_t* d2 = (const int32_t*)upload(c, c->kpup[1], kp2, sizeof(int32_t) * 2 * (size_t)n2, mem);
   const pano_dmatch* dm = (const pano_dmatch*)upload(c, c->mup, matches, sizeof(pano_dmatch) * (size_t)n_matches, mem);
+  c->rs.n1 = n1;   // the indices of the caller's matches are checked against the caller's counts on the device
+  c->rs.n2 = n2;
   RansacResult r = ransac_retry(c, d1, d2, dm, n_matches, *opts, samples_out, counts_out, inlier_mask_out);
+  if (r.errw) return fail_errw(c, r.errw);
   if (best_inliers) *best_inliers = r.best_count;
   if (best_iteration) *best_iteration = r.best_iter;
   if (r.status == PANO_OK) memcpy(H_out, r.H, sizeof r.H);
@@ -720,21 +750,21 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
   // Pairs are independent: run them on several lanes (child contexts, each with its own stream,
   // scratch and host thread) so that one pair's host synchronisations, copies and low-occupancy
   // kernels overlap with another pair's work.  PANO_BATCH_LANES (default 16, 1 = sequential); lanes beyond the
-  // host cores poll-and-sleep instead of spinning inside the driver (g_yield_wait).
+  // host cores poll-and-sleep instead of spinning inside the driver (t_yield_wait, set per lane thread).
   int n_lanes = 16;
   if (const char* e = getenv("PANO_BATCH_LANES")) n_lanes = atoi(e);
   if (n_lanes < 1) n_lanes = 1;
   if (n_lanes > 32) n_lanes = 32;
   if (n_lanes > n) n_lanes = n > 0 ? n : 1;
   // lanes beyond the host cores (or PANO_YIELD_WAIT=1): waits poll and sleep instead of spinning in the driver
+  bool yield_wait = false;
   {
     const unsigned hc = std::thread::hardware_concurrency();
     const char* e = getenv("PANO_YIELD_WAIT");
     // (one process per GPU: the other ranks of this node have as many lane threads on the same cores)
     const char* lw = getenv("LOCAL_WORLD_SIZE");
     const int ranks = lw && atoi(lw) > 0 ? atoi(lw) : 1;
-    const bool yield_wait = e ? atoi(e) != 0 : (hc > 0 && n_lanes * ranks + 1 > (int)hc);
-    g_yield_wait = yield_wait ? 1 : 0;
+    yield_wait = e ? atoi(e) != 0 : (hc > 0 && n_lanes * ranks + 1 > (int)hc);
   }
   while ((int)c->lanes.size() < n_lanes) {
     pano_ctx* l = nullptr;
@@ -748,8 +778,10 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
   PANO_CUDA(stream_wait(c->st));
   PANO_CUDA(cudaEventRecord(e0, c->st));
   std::vector<int> lane_rc((size_t)n_lanes, PANO_OK);
+  std::vector<std::string> lane_err((size_t)n_lanes);   // merged into c->err after the join (no shared writes)
   auto work = [&](int li) {
     pano_ctx* l = c->lanes[li];
+    t_yield_wait = yield_wait ? 1 : 0;
     l->seed = c->seed;
     l->matcher = c->matcher;
     l->replay_target = n_lanes > 1 ? 4000.0 : 0.0;   // small chunks: least speculative work (19.9 k vs 17.8 k MP/s at 16000)
@@ -802,7 +834,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
           R = to_device(l, rights[i], wr, hr, stride_r, mem, 1);
         }
         int s = stitch_pair_device(l, L, R, *hopts, *ropts, &results[i]);
-        if (s == PANO_ERR_CUDA) { lane_rc[li] = s; c->err = l->err; return; }
+        if (s == PANO_ERR_CUDA) { lane_rc[li] = s; lane_err[li] = l->err; t_yield_wait = 0; return; }
         if (s == PANO_OK && canvases_out && canvases_out[i]) {
           size_t row = (size_t)l->cw * 3;
           if (row * (size_t)l->ch > canvas_cap_bytes) {
@@ -829,10 +861,11 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
       char buf[512];
       snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e.e, cudaGetErrorString(e.e), e.file, e.line,
                e.what);
-      c->err = buf;
+      lane_err[li] = buf;
       cudaGetLastError();
       lane_rc[li] = PANO_ERR_CUDA;
     }
+    t_yield_wait = 0;
   };
   if (n_lanes == 1) {
     work(0);
@@ -842,8 +875,8 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
     for (auto& t : th) t.join();
   }
   int rc = PANO_OK;
-  for (int s : lane_rc)
-    if (s != PANO_OK) rc = s;
+  for (int li = 0; li < n_lanes; li++)
+    if (lane_rc[li] != PANO_OK) { rc = lane_rc[li]; c->err = lane_err[li]; }
   PANO_CUDA(cudaEventRecord(e1, c->st));
   PANO_CUDA(cudaEventSynchronize(e1));
   float ms = 0;

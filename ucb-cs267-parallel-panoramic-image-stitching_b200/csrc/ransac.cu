@@ -538,11 +538,18 @@ replay_resident_kernel(ResParams P, ReplayCtl* ctl, int4* __restrict__ samples) 
 // ---------------------------------------------------------------------------------------
 // K6 / K7
 // ---------------------------------------------------------------------------------------
-__global__ void build_points_kernel(const int32_t* __restrict__ kp1, const int32_t* __restrict__ kp2,
-                                    const pano_dmatch* __restrict__ m, int n, float4* __restrict__ pts) {
+__global__ void build_points_kernel(const int32_t* __restrict__ kp1, int n1, const int32_t* __restrict__ kp2, int n2,
+                                    const pano_dmatch* __restrict__ m, int n, float4* __restrict__ pts,
+                                    int* __restrict__ errw) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   pano_dmatch mm = m[i];
+  // n1 / n2 > 0: the caller's keypoint counts; an index outside them is reported, never dereferenced
+  if (mm.query_idx < 0 || mm.train_idx < 0 || (n1 > 0 && mm.query_idx >= n1) || (n2 > 0 && mm.train_idx >= n2)) {
+    atomicOr(errw, PANO_ERRW_BAD_INDEX);
+    pts[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   pts[i] = make_float4((float)kp1[2 * mm.query_idx], (float)kp1[2 * mm.query_idx + 1],
                        (float)kp2[2 * mm.train_idx], (float)kp2[2 * mm.train_idx + 1]);
 }
@@ -940,7 +947,9 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   // plans depend only on (M, iterations, window scale, chunk target): keep the most recent ones
   struct PlanKey { uint32_t n; int iters, scale; double target; };
   struct Plans { ReplayPlan chunked; ResidentPlan resident; };
-  thread_local std::vector<std::pair<PlanKey, Plans>> plan_cache;
+  typedef std::vector<std::pair<PlanKey, Plans>> PlanCache;   // lives in the context: lanes keep theirs across batch calls
+  if (!s.plan_cache) s.plan_cache = std::make_shared<PlanCache>();
+  PlanCache& plan_cache = *static_cast<PlanCache*>(s.plan_cache.get());
   const Plans* plan_ptr = nullptr;
   for (auto& e : plan_cache)
     if (e.first.n == n && e.first.iters == iters && e.first.scale == window_scale && e.first.target == target_cand)  // (z_sigma is process-constant)
@@ -1008,7 +1017,8 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   int4* seg_w = samples_dev + (size_t)n_chunks * G;
 
   if (do_solve) {
-    build_points_kernel<<<(m + 255) / 256, 256, 0, st>>>(kp1_dev, kp2_dev, matches_dev, m, s.pts.as<float4>());
+    build_points_kernel<<<(m + 255) / 256, 256, 0, st>>>(kp1_dev, s.n1, kp2_dev, s.n2, matches_dev, m, s.pts.as<float4>(),
+                                                         s.errw);
     PANO_LAUNCH_CHECK();
   }
 
@@ -1086,11 +1096,17 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
   char* pp = pin.as<char>();
   PANO_CUDA(cudaMemcpyAsync(pp, s.result.p, sizeof(SelectOut), cudaMemcpyDeviceToHost, st));
   PANO_CUDA(cudaMemcpyAsync(pp + sizeof(SelectOut), status_ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PANO_CUDA(cudaMemcpyAsync(pp + sizeof(SelectOut) + sizeof(int), s.errw, sizeof(int), cudaMemcpyDeviceToHost, st));
   PANO_CUDA(stream_wait(st));
   SelectOut so;
   memcpy(&so, pp, sizeof so);
   int replay_status;
   memcpy(&replay_status, pp + sizeof(SelectOut), sizeof(int));
+  memcpy(&res.errw, pp + sizeof(SelectOut) + sizeof(int), sizeof(int));
+  if (res.errw != 0) {   // matcher abort / missing minimum / bad match index: the caller fails the call
+    res.status = PANO_ERR_CUDA;
+    return res;
+  }
   if (replay_status != 0) {
     // a speculation window was missed (bit 0) or the stream margin was too small (bit 1):
     // nothing was guessed; tell the caller to re-run with wider windows
