@@ -225,7 +225,7 @@ int hs_replay_resident(uint32_t seed, uint32_t n, int iters, int window_scale, d
 // 2 = a useless seed (half the reciprocal), 3 = the correctly rounded reciprocal.
 // out[0] = pixels whose accepted fast result differs from the exact one (must be 0), out[1] = pixels sent to the
 // exact path, out[2] = pixels checked.
-void hs_warp_fast_check(const double* Minv, int cw, int ch, int step, int seed_mode, uint64_t* out) {
+void hs_warp_fast_check(const double* Minv, int cw, int ch, int step, int seed_mode, uint64_t* out, int variant) {
   out[0] = out[1] = out[2] = 0;
   double Mx[3] = {32.0 * Minv[0], 32.0 * Minv[1], 32.0 * Minv[2]};
   double My[3] = {32.0 * Minv[3], 32.0 * Minv[4], 32.0 * Minv[5]};
@@ -243,7 +243,8 @@ void hs_warp_fast_check(const double* Minv, int cw, int ch, int step, int seed_m
         else if (seed_mode == 2) r0 *= 0.5;
         int Xf, Yf, Xe, Ye;
         bool need;
-        warp_coord_fast(X0, Y0, W0, Mx[0], My[0], Minv[6], x1, r0, &Xf, &Yf, &need);
+        if (variant == 2) warp_coord_fast2(X0, Y0, W0, Mx[0], My[0], Minv[6], (double)x1, r0, &Xf, &Yf, &need);
+        else warp_coord_fast(X0, Y0, W0, Mx[0], My[0], Minv[6], (double)x1, r0, &Xf, &Yf, &need);
         warp_coord(Minv, xb + x1, y, 64, &Xe, &Ye);
         out[2]++;
         if (need) out[1]++;

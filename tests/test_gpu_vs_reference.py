@@ -38,7 +38,10 @@ def small():
 
 @pytest.fixture(scope="module")
 def runs():
-    return json.load(open(os.path.join(GOLDEN, "ref_runs.json")))
+    f = os.path.join(GOLDEN, "ref_runs.json")
+    if not os.path.exists(f):
+        pytest.skip("tests/golden/ref_runs.json not generated (oracle/gen_ref_golden.py)")
+    return json.load(open(f))
 
 
 def test_engine_equals_reference_small_vectors(engine, small):

@@ -141,8 +141,9 @@ def test_inlier_limit_is_exact_sqrt_threshold(hostsim):
     assert np.isnan(hostsim.hs_inlier_d2_limit(C.c_double(float("nan"))))
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("seed_mode", [0, 1, 2, 3])
-def test_warp_fast_coordinates_never_differ_from_exact(hostsim, seed_mode):
+def test_warp_fast_coordinates_never_differ_from_exact(hostsim, seed_mode, variant):
     """warp.cu's fast coordinate path (checked Newton reciprocal + magic rounding, pano_core.cuh warp_coord_fast) either
     reproduces OpenCV's exact  rint((X0 + M0 x1) * (32 / W))  or asks for the exact path - for a good seed, a poor
     seed and a useless seed (which must send every pixel to the exact path), over whole canvases"""
@@ -158,7 +159,7 @@ def test_warp_fast_coordinates_never_differ_from_exact(hostsim, seed_mode):
                               [rng.normal() * 3e-6, rng.normal() * 3e-6, 1.0]]))
     for H in mats:
         Minv = np.ascontiguousarray(np.linalg.inv(H))
-        hostsim.hs_warp_fast_check(p(Minv, C.c_double), 5763, 2182, 7, seed_mode, p(out, C.c_uint64))
+        hostsim.hs_warp_fast_check(p(Minv, C.c_double), 5763, 2182, 7, seed_mode, p(out, C.c_uint64), variant)
         assert out[0] == 0, (seed_mode, H, out)
         total_need += int(out[1]); total += int(out[2])
     if seed_mode == 2:

@@ -407,18 +407,19 @@ PANO_HD void pano_d2words(double v, uint32_t* lo, uint32_t* hi) {
   *hi = (uint32_t)(b >> 32);
 #endif
 }
-PANO_HD void warp_coord_fast(double X0s, double Y0s, double W0, double M0s, double M3s, double M6, int x1, double r0,
+PANO_HD void warp_coord_fast(double X0s, double Y0s, double W0, double M0s, double M3s, double M6, double x1d, double r0,
                              int* Xo, int* Yo, bool* exact_needed) {
-  const double x1d = (double)x1;
-  const double Wd = PANO_DADD(W0, PANO_DMUL(M6, x1d));
-  const double Xn = PANO_DADD(X0s, PANO_DMUL(M0s, x1d));
-  const double Yn = PANO_DADD(Y0s, PANO_DMUL(M3s, x1d));
+  // (fused multiply-adds throughout: this is the APPROXIMATE evaluation, one ulp here or there is far inside the
+  // tolerance that the acceptance test below enforces; the exact path keeps OpenCV's separately rounded operations)
+  const double Wd = PANO_DFMA(M6, x1d, W0);
+  const double Xn = PANO_DFMA(M0s, x1d, X0s);
+  const double Yn = PANO_DFMA(M3s, x1d, Y0s);
   const double e0 = PANO_DFMA(-Wd, r0, 1.0);
   const double r1 = PANO_DFMA(r0, e0, r0);
   const double e1 = PANO_DFMA(-Wd, r1, 1.0);
   const double r2 = PANO_DFMA(r1, e1, r1);
-  const double mx = PANO_DADD(PANO_DMUL(Xn, r2), 6442450944.0);
-  const double my = PANO_DADD(PANO_DMUL(Yn, r2), 6442450944.0);
+  const double mx = PANO_DFMA(Xn, r2, 6442450944.0);
+  const double my = PANO_DFMA(Yn, r2, 6442450944.0);
   uint32_t xl, xh, yl, yh;
   pano_d2words(mx, &xl, &xh);
   pano_d2words(my, &yl, &yh);
@@ -429,6 +430,34 @@ PANO_HD void warp_coord_fast(double X0s, double Y0s, double W0, double M0s, doub
   const uint32_t xh2 = xh + (xl2 < xl ? 1u : 0u), yh2 = yh + (yl2 < yl ? 1u : 0u);
   *Xo = (int)(((xl2 >> 20) | (xh2 << 12)) ^ 0x80000000u);
   *Yo = (int)(((yl2 >> 20) | (yh2 << 12)) ^ 0x80000000u);
+}
+
+// Second formulation of the same check, all in the FP64 pipe (the quad warp kernel: integer issue slots are what
+// bounds it).  mx = fma(Xn, r2, 1.5 * 2^52) holds rint(Xn * r2) in its low mantissa word (round to nearest even of the
+// exact product, |v| < 2^31); rnd = mx - 1.5 * 2^52 is that integer as a double (exact), d = fma(Xn, r2, -rnd) the
+// signed distance of the approximate value from it (exact up to one rounding of a number below 1).  The result is
+// accepted only if |d| <= 0.5 - 2^-16, i.e. the approximate value is at least 2^-16 away from the rounding boundary:
+// the same margin as above, against an approximation error below 2^22 * (2^-44 + 3 * 2^-53) < 2^-21.
+PANO_HD void warp_coord_fast2(double X0s, double Y0s, double W0, double M0s, double M3s, double M6, double x1d, double r0,
+                              int* Xo, int* Yo, bool* exact_needed) {
+  const double Wd = PANO_DFMA(M6, x1d, W0);
+  const double Xn = PANO_DFMA(M0s, x1d, X0s);
+  const double Yn = PANO_DFMA(M3s, x1d, Y0s);
+  const double e0 = PANO_DFMA(-Wd, r0, 1.0);
+  const double r1 = PANO_DFMA(r0, e0, r0);
+  const double e1 = PANO_DFMA(-Wd, r1, 1.0);
+  const double r2 = PANO_DFMA(r1, e1, r1);
+  const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+  const double mx = PANO_DFMA(Xn, r2, MAGIC), my = PANO_DFMA(Yn, r2, MAGIC);
+  const double dx = PANO_DFMA(Xn, r2, -PANO_DSUB(mx, MAGIC)), dy = PANO_DFMA(Yn, r2, -PANO_DSUB(my, MAGIC));
+  const double lim = 0.4999847412109375;     // 0.5 - 2^-16
+  // (written so that a NaN anywhere - e.g. a zero denominator - fails the test and takes the exact path)
+  *exact_needed = !(fabs(dx) <= lim && fabs(dy) <= lim && fabs(e1) < 2.384185791015625e-07);
+  uint32_t lo, hi;
+  pano_d2words(mx, &lo, &hi);
+  *Xo = (int)lo;
+  pano_d2words(my, &lo, &hi);
+  *Yo = (int)lo;
 }
 
 PANO_HD int sat_short(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }

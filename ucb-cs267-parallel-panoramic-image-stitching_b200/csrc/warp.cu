@@ -239,7 +239,7 @@ warp_fast_kernel(const uint8_t* __restrict__ left, size_t lstride, const uint8_t
         const double Wseed = __dadd_rn(W0, __dmul_rn(F.Mw[0], (double)(32 * g + lane)));
         int X, Y;
         bool exact_needed;
-        warp_coord_fast(X0, Y0, W0, F.Mx[0], F.My[0], F.Mw[0], 32 * g + lane, rcp_seed(Wseed), &X, &Y, &exact_needed);
+        warp_coord_fast(X0, Y0, W0, F.Mx[0], F.My[0], F.Mw[0], (double)(32 * g + lane), rcp_seed(Wseed), &X, &Y, &exact_needed);
         if (x < P.cw) {
           if (exact_needed) warp_coord(P.M, x, y, P.bw0, &X, &Y);
           const int sx = X >> 5, sy = Y >> 5;
@@ -266,6 +266,167 @@ warp_fast_kernel(const uint8_t* __restrict__ left, size_t lstride, const uint8_t
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Quad kernel (round 2): the fast path with FOUR adjacent canvas pixels per thread.
+//   * a thread owns 12 contiguous canvas bytes = three aligned 32-bit words: no byte stores, a warp writes 384
+//     contiguous bytes of one canvas row; the left image is read as words too (funnel-shifted to the canvas phase);
+//   * the four pixels are independent chains (coordinates, 6 tap words each, DP4A bilinear): 24 tap loads in flight
+//     per thread hide the L1/L2 latency that stalled the one-pixel-per-lane kernel (ncu r01: long-scoreboard bound);
+//   * OpenCV's 64-px coordinate block, the row-origin numerators and every bounds decision are computed once per
+//     thread instead of once per pixel; a 128-px warp span is two coordinate blocks (lanes 0-15 / 16-31);
+//   * a block is 8 warps = 8 adjacent canvas rows of the same 128 columns, so the source rows are reused from L1.
+// Arithmetic per pixel is unchanged (warp_coord_fast with its exact fallback, bilinear_dp4a, warp_pixel on the
+// border ring), so results are identical to the other two kernels; tests/test_gpu_parity.py compares all three.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t px_of(const uint8_t* __restrict__ p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+warp_quad_kernel(const uint8_t* __restrict__ left, size_t lstride, const uint8_t* __restrict__ right, size_t rstride,
+                 const FastParams F, uint8_t* __restrict__ canvas, size_t cstride) {
+  const WarpParams& P = F.W;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int yb = blockIdx.y * 8 + wrp;            // row inside the band
+  const int x0 = blockIdx.x * 128 + lane * 4;     // first of this thread's four pixels
+  if (yb >= P.ch || x0 >= P.cw) return;
+  const int y = yb + P.y0;
+  uint8_t* crow = canvas + (size_t)yb * cstride;
+  uint32_t px[4] = {0u, 0u, 0u, 0u};
+  const bool full = x0 + 3 < P.cw;                // all four pixels exist
+  if (y >= P.by0 && y <= P.by1 && !(x0 + 3 < P.bx0 || x0 > P.bx1)) {
+    const int xb = x0 & ~63;
+    const double xbd = (double)xb, yd = (double)y;
+    // row-origin numerators of the 64-px block (ref arithmetic of warp_row_origin, X and Y scaled by 32)
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(F.Mx[0], xbd), __dmul_rn(F.Mx[1], yd)), F.Mx[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(F.My[0], xbd), __dmul_rn(F.My[1], yd)), F.My[2]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(F.Mw[0], xbd), __dmul_rn(F.Mw[1], yd)), F.Mw[2]);
+    const double x1d0 = (double)(x0 - xb);
+    const uint32_t rs = (uint32_t)rstride;
+    int X[4], Y[4];
+    bool need[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const double x1d = x1d0 + (double)i;        // small integers: exact
+      warp_coord_fast2(X0, Y0, W0, F.Mx[0], F.My[0], F.Mw[0], x1d, rcp_seed(__fma_rn(F.Mw[0], x1d, W0)), &X[i], &Y[i],
+                       &need[i]);
+    }
+    bool fast4 = full & !(need[0] | need[1] | need[2] | need[3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      fast4 = fast4 & ((unsigned)(X[i] >> 5) < (unsigned)(P.ws - 1)) & ((unsigned)(Y[i] >> 5) < (unsigned)(P.hs - 2));
+    if (fast4) {
+      // the common case, branch-free: all 24 tap words are requested before the first one is used
+      uint32_t u[4][6];
+      uint32_t sh[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t off = (uint32_t)(Y[i] >> 5) * rs + 3u * (uint32_t)(X[i] >> 5);    // sources are < 4 GB
+        const uint32_t a = off & 3u;                                                   // base and pitch are multiples of 4
+        sh[i] = 8u * a;
+        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(right + (off - a));
+        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(right + (off - a + rs));
+        u[i][0] = q0[0]; u[i][1] = q0[1]; u[i][2] = q0[2];
+        u[i][3] = q1[0]; u[i][4] = q1[1]; u[i][5] = q1[2];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int fx = X[i] & 31, fy = Y[i] & 31;
+        const uint32_t alo = __funnelshift_r(u[i][0], u[i][1], sh[i]), ahi = __funnelshift_r(u[i][1], u[i][2], sh[i]);
+        const uint32_t blo = __funnelshift_r(u[i][3], u[i][4], sh[i]), bhi = __funnelshift_r(u[i][4], u[i][5], sh[i]);
+        const uint32_t wx = (uint32_t)(32 - fx) | ((uint32_t)fx << 24);                 // bytes 0 and 3
+        const int gy = 32 - fy;
+        uint32_t out = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const uint32_t ta = c == 0 ? alo : __funnelshift_r(alo, ahi, 8 * c);          // p0[c] . . p1[c]
+          const uint32_t tb = c == 0 ? blo : __funnelshift_r(blo, bhi, 8 * c);
+          const int h0 = (int)__dp4a(ta, wx, 0u), h1 = (int)__dp4a(tb, wx, 0u);
+          out |= (uint32_t)((gy * h0 + fy * h1 + 512) >> 10) << (8 * c);
+        }
+        px[i] = out;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (x0 + i < P.cw) {
+          int Xi = X[i], Yi = Y[i];
+          if (need[i]) warp_coord(P.M, x0 + i, y, P.bw0, &Xi, &Yi);
+          const int sx = Xi >> 5, sy = Yi >> 5;
+          uint32_t v;
+          if ((unsigned)sx < (unsigned)(P.ws - 1) && (unsigned)sy < (unsigned)(P.hs - 2))
+            v = bilinear_dp4a(right, rs, sx, sy, Xi & 31, Yi & 31);
+          else
+            v = warp_pixel(right, rstride, P.ws, P.hs, Xi, Yi);   // border ring / outside: general path
+          px[i] = v;
+        }
+      }
+    }
+  }
+  if (MODE == 1) {
+    const int ly = y - P.offy, lx0 = x0 - P.offx;
+    if (ly >= 0 && ly < P.hl && lx0 + 3 >= 0 && lx0 < P.wl && ((px[0] == 0u) | (px[1] == 0u) | (px[2] == 0u) | (px[3] == 0u))) {
+      const uint8_t* lrowp = left + (size_t)ly * lstride;
+      if (lx0 >= 0 && lx0 + 4 <= P.wl && ly + 1 < P.hl) {
+        // 12 bytes of the left row as words (base and pitch of the engine's images are 4-byte aligned; the row below
+        // keeps the last word's over-read inside the image)
+        const uint8_t* sp = lrowp + 3u * (uint32_t)lx0;
+        const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 3u), sh = 8u * a;
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(sp - a);
+        const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3];
+        const uint32_t l0 = __funnelshift_r(w0, w1, sh), l1 = __funnelshift_r(w1, w2, sh), l2 = __funnelshift_r(w2, w3, sh);
+        if (px[0] == 0u) px[0] = l0 & 0xffffffu;
+        if (px[1] == 0u) px[1] = __funnelshift_r(l0, l1, 24) & 0xffffffu;
+        if (px[2] == 0u) px[2] = __funnelshift_r(l1, l2, 16) & 0xffffffu;
+        if (px[3] == 0u) px[3] = l2 >> 8;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int lx = lx0 + i;
+          if (px[i] == 0u && lx >= 0 && lx < P.wl) px[i] = px_of(lrowp + 3u * (uint32_t)lx);
+        }
+      }
+    }
+  }
+  uint8_t* o = crow + 3u * (uint32_t)x0;
+  if (MODE == 2) {
+    // accumulate: only non-black warped pixels overwrite what the band already holds
+    if ((px[0] | px[1] | px[2] | px[3]) == 0u) return;
+    if (!(full && F.copy_words && px[0] != 0u && px[1] != 0u && px[2] != 0u && px[3] != 0u)) {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (px[i] != 0u && x0 + i < P.cw) {
+          o[3 * i] = (uint8_t)px[i];
+          o[3 * i + 1] = (uint8_t)(px[i] >> 8);
+          o[3 * i + 2] = (uint8_t)(px[i] >> 16);
+        }
+      return;
+    }
+  }
+  if (full && F.copy_words) {
+    uint32_t* ow = reinterpret_cast<uint32_t*>(o);   // 3 * x0 = 12 * (x0 / 4): word aligned
+    ow[0] = px[0] | (px[1] << 24);
+    ow[1] = (px[1] >> 8) | (px[2] << 16);
+    ow[2] = (px[2] >> 16) | (px[3] << 8);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (x0 + i < P.cw) {
+        o[3 * i] = (uint8_t)px[i];
+        o[3 * i + 1] = (uint8_t)(px[i] >> 8);
+        o[3 * i + 2] = (uint8_t)(px[i] >> 16);
+      }
+  }
+}
+
+// PANO_WARP_KERNEL: 0 = quad kernel (default), 1 = the round-1 one-pixel-per-lane fast kernel (kept for A/B runs
+// and as a second implementation the tests compare against)
+int warp_kernel_choice() {
+  const char* e = getenv("PANO_WARP_KERNEL");
+  return e ? atoi(e) : 0;
 }
 
 // PANO_WARP_FAST=0 forces the general kernel (tests compare the two)
@@ -299,6 +460,12 @@ void launch_fast(cudaStream_t st, const uint8_t* left, size_t lstride, const uin
   for (int i = 0; i < 3; i++) { F.Mx[i] = 32.0 * P.M[i]; F.My[i] = 32.0 * P.M[3 + i]; F.Mw[i] = P.M[6 + i]; }
   F.W = P;
   F.copy_words = ((reinterpret_cast<uintptr_t>(canvas) & 3u) == 0 && (cstride & 3u) == 0) ? 1 : 0;
+  const bool left_words = MODE != 1 || ((reinterpret_cast<uintptr_t>(left) & 3u) == 0 && (lstride & 3u) == 0);
+  if (warp_kernel_choice() == 0 && left_words) {
+    dim3 qgrid((P.cw + 127) / 128, (P.ch + 7) / 8);
+    warp_quad_kernel<MODE><<<qgrid, dim3(256), 0, st>>>(left, lstride, right, rstride, F, canvas, cstride);
+    return;
+  }
   dim3 block(256), grid((P.cw + 255) / 256, (P.ch + 7) / 8);
   static const int minb = [] { const char* e = getenv("PANO_WARP_MINB"); return e ? atoi(e) : 5; }();
   if (minb >= 6)
