@@ -1,27 +1,38 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200 stitching engine (BASELINE.json metric:
-"stitched MP/s and ms per 4K pair (detect+match+RANSAC+warp)").
+"stitched MP/s and ms per 4K pair (detect+match+RANSAC+warp) at 1/2/4/8 B200").
 
-    python bench.py --gpus N --steps K --warmup W            # engine arm (1 process per GPU)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
+    python bench.py --gpus N --steps K --warmup W                    # engine arm (1 process per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm (rank 0 only)
+    python bench.py --workload c1|c2|c3|chain ...                    # the other BASELINE configs (see profiles/)
 
-A step = one pass of the full hot path (detect both images, match, seeded RANSAC, warp +
-overlay) over one batch of P distinct synthetic 3840x2160 pairs per GPU (config 3 of
-BASELINE.json; P pairs = P*50 MB of input, larger than the 126 MB L2, rotating every step).
-`value`  : whole-job stitched MP/s (input megapixels of all ranks / max-over-ranks device time),
-           inputs already resident in HBM, canvases left in HBM.
-`e2e`    : the same metric through the C-ABI call with HOST (pinned) buffers: H2D of both images
-           and D2H of every canvas inside the timed region.
-`roofline`: the dominant kernel of the step, timed live with CUDA events on the engine's stream.
-`cpu_baseline`: the CPU oracle (restatement of the reference's serial path; the reference
-           itself needs OpenCV C++ and cannot be built here) on a bounded sample, rank 0 only.
+Default workload = BASELINE config 5: a batch of 256 DISTINCT synthetic 3840x2160 pairs per GPU
+(generator synth.make_pair_torch, seeds 1000 + 256 * rank + i; 12.7 GB of input per GPU, far beyond the
+126 MB L2).  A step = one pass of the full hot path (detect both images, match, seeded RANSAC, warp +
+overlay) over that batch through ONE pano_stitch_batch call.
+`value`        whole-job stitched MP/s (input megapixels of all ranks / max-over-ranks device time), inputs
+               already resident in HBM, canvases left in HBM.
+`e2e`          the same metric through the C-ABI call with HOST (pinned) buffers: H2D of both images and D2H
+               of every canvas inside the timed region, distinct host buffers for every pair; also reported as
+               a fraction of the pure-copy ceiling measured in the same run (same bytes, no kernels).
+`latency`      one pair alone on an idle GPU (BASELINE config 3, "ms per 4K pair"), device and wall time.
+`roofline`     the HBM-bound kernel of the step (warp + overlay) timed live with CUDA events around its launch
+               inside the C ABI (pano_set_profile), plus every other main kernel timed the same way.
+`cpu_baseline` the reference's own code (oracle/_ref: /root/reference/src/openmp/main.cpp and src/serial/main.cpp
+               compiled unmodified against oracle/cvshim) on this box's host cores, rank 0 at N = 1 only.
+Every number in the line is measured in this run, except those explicitly attributed to a committed capture
+under profiles/ (ncu-only metrics such as the tensor-pipe percentage).
 """
 import argparse
 import os as _os
-_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per batch lane (before CUDA starts)
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # hardware work queues for the batch slots (before CUDA starts)
+# NCCL evidence (ranks, transport) goes to stderr so that stdout stays one JSON line
+_os.environ.setdefault("NCCL_DEBUG", "INFO")
+_os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import importlib
 import json
 import os
+import platform
 import statistics
 import subprocess
 import sys
@@ -39,30 +50,22 @@ UNIT = "MP/s"
 SEED = 12345
 
 
-def cached_pair(w, h, seed):
-    synth = importlib.import_module(PKG + ".synth")
-    d = os.environ.get("PANO_SYNTH_CACHE", "/tmp/pano_synth_cache")
-    os.makedirs(d, exist_ok=True)
-    f = os.path.join(d, "pair_%dx%d_%d.npz" % (w, h, seed))
-    if os.path.exists(f):
-        try:
-            z = np.load(f)
-            return z["left"], z["right"]
-        except Exception:
-            pass
-    left, right, H = synth.make_pair(w, h, seed=seed)
-    tmp = f + ".%d.tmp.npz" % os.getpid()
-    np.savez(tmp, left=left, right=right, H=H)
-    os.replace(tmp, f)
-    return left, right
-
-
 def peaks():
     f = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(f):
         p = json.load(open(f))
-        return p.get("hbm_gbs", 6650.0), "measured"
-    return 6650.0, "fallback"
+        return p.get("hbm_gbs", 6650.0), "measured copy bandwidth (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_model():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return platform.processor() or "unknown"
 
 
 class ClockSampler:
@@ -110,318 +113,395 @@ class ClockSampler:
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def host_pair(w, h, seed):
+    """one pair of the workload on the host (CPU legs): the same generator, evaluated by torch on the CPU"""
+    synth = importlib.import_module(PKG + ".synth")
+    l, r, _ = synth.make_pair_torch(w, h, seed=seed, device="cpu")
+    return l.numpy(), r.numpy()
+
+
+def workload_name(w, h, P):
+    return ("BASELINE config 5: batch of %d distinct synthetic %dx%d textured pairs with known homographies per GPU "
+            "(synth.make_pair_torch, seeds 1000 + %d * rank + i)" % (P, w, h, P))
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm: the reference's own CPU algorithm (oracle port; the reference needs OpenCV C++)
+# reference arm: the reference's own CPU implementation (oracle/_ref), all host threads
 # ----------------------------------------------------------------------------------------------
 def run_reference(a):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    # all host threads (torchrun exports OMP_NUM_THREADS=1 to its workers; libgomp reads it at load)
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    from oracle.oracle import Oracle
-    O = Oracle("omp")
-    cores = O.num_threads()
+    ncpu = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)     # (torchrun exports OMP_NUM_THREADS=1; libgomp reads it at load)
     w, h = a.w, a.h
-    pairs = [cached_pair(w, h, 1000 + i) for i in range(2)]
-    times = []
+    from oracle import ref as refmod
+    kind = "reference"
+    if refmod.available("omp"):
+        R = refmod.Reference("omp")
+        cores = R.num_threads()
+        what = ("the reference's OpenMP pipeline, src/openmp/main.cpp compiled unmodified against oracle/cvshim "
+                "(-O2 -fopenmp), %d threads" % cores)
+
+        def run(l, r):
+            s = R.stitch_pair(l, r, seed=SEED)   # (its RANSAC samples with std::sample per thread: a timing baseline)
+            return s["times_ms"]
+    else:   # oracle/_ref did not travel: the OpenCV-free port with OpenMP
+        from oracle.oracle import Oracle
+        O = Oracle("omp")
+        cores, kind = O.num_threads(), "port"
+        what = "oracle port (pano_oracle.cpp -O2 -fopenmp), %d threads" % cores
+
+        def run(l, r):
+            s = O.stitch_pair(l, r, seed=SEED)
+            assert s["status"] == 1
+            return s["times_ms"]
+    pairs = [host_pair(w, h, 1000 + i) for i in range(2)]
+    times, stages = [], None
     for s in range(a.warmup + a.steps):
         l, r = pairs[s % len(pairs)]
         t0 = time.perf_counter()
-        res = O.stitch_pair(l, r, seed=SEED)
+        stages = run(l, r)
         dt = time.perf_counter() - t0
-        assert res["status"] == 1
         if s >= a.warmup:
             times.append(dt)
     mp = 2 * w * h / 1e6
     tot = sum(times)
     val = mp * len(times) / tot
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1000 * tot / len(times), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
-            "config": {"workload": "synthetic %dx%d textured pair, known homography (BASELINE config 3)" % (w, h),
-                       "pairs_per_step": 1, "seed": SEED},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d step(s) of 1 pair, oracle -O2 with OpenMP on %d threads "
-                                       "(reference needs OpenCV C++: not buildable here)" % (len(times), cores)},
+            "warmup": a.warmup, "ms_per_step": 1000 * tot / len(times), "ms_per_pair": 1000 * tot / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
+            "config": {"workload": workload_name(w, h, a.pairs) + "; each reference step = 1 pair of it (seeds 1000, 1001 alternating)",
+                       "pairs_per_step": 1, "seed": SEED, "cpu_model": cpu_model(), "host_threads": ncpu},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": "%d step(s) of 1 pair; %s" % (len(times), what),
+                             "stage_ms_last_step": stages},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line, default=float), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------
 # engine arm
 # ----------------------------------------------------------------------------------------------
-def time_kernel(eng, torch, fn, reps=5):
-    """device time of fn() (which enqueues on the engine's stream and syncs) via CUDA events on
-    that stream"""
-    st = torch.cuda.ExternalStream(eng.stream_ptr())
-    best = []
+def pinned_bytes(torch, n):
+    return torch.empty(n, dtype=torch.uint8).pin_memory()
+
+
+def mem_available_bytes():
+    try:
+        for l in open("/proc/meminfo"):
+            if l.startswith("MemAvailable"):
+                return int(l.split()[1]) * 1024
+    except OSError:
+        pass
+    return 64 << 30
+
+
+def copy_ceiling(torch, dist, world, Lh, Rh, Ch, canvas_bytes, Ld, Rd, reps=2):
+    """pure copies of the e2e step's bytes (both directions at once, separate streams), all ranks at the same time"""
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    dsrc = torch.empty(max(canvas_bytes), dtype=torch.uint8, device="cuda")
+    best = None
     for _ in range(reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(st)
-        fn()
-        e1.record(st)
-        e1.synchronize()
-        best.append(e0.elapsed_time(e1))
-    return statistics.median(best)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(len(Lh)):
+            with torch.cuda.stream(up):
+                Ld[i].copy_(Lh[i], non_blocking=True)
+                Rd[i].copy_(Rh[i], non_blocking=True)
+            with torch.cuda.stream(down):
+                Ch[i][:canvas_bytes[i]].copy_(dsrc[:canvas_bytes[i]], non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
 
 
 def run_engine(a):
     import torch
-    import ctypes as C
     rank, world, local = dist_env()
     pkg = importlib.import_module(PKG)
+    synth = importlib.import_module(PKG + ".synth")
+    numa = importlib.import_module(PKG + ".numa").bind_to_gpu(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    dist = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout must be one JSON line: NCCL prints its version to stdout at every NCCL_DEBUG level above NONE
-        # (WARN included), so the variable is removed unless PANO_NCCL_DEBUG asks for a level (then to stderr)
-        if "PANO_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["PANO_NCCL_DEBUG"]
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    # overlapped lanes per GPU: each has a host thread (lanes beyond the cores poll-and-sleep instead of spinning);
-    # more lanes than cores help the end-to-end path (uploads / downloads of more pairs in flight): 16 -> 24 lanes
-    # = 12.8 k -> 13.7 k MP/s e2e on a 16-core box, resident throughput unchanged; never fewer than 16 per rank
-    # (4 GPUs on 32 cores: 8 lanes 65.4 k, 12 lanes 71.6 k, 16 lanes 78.3 k MP/s = 98 % weak scaling)
-    lanes = int(os.environ.get("PANO_BATCH_LANES", max(16, min(24, 3 * (os.cpu_count() or 8) // (2 * max(world, 1))))))
+    ncpu = len(os.sched_getaffinity(0))
+    # lanes = host threads driving the batch (each a pipeline over PANO_BATCH_DEPTH + 2 slots); bounded by the cores
+    # this rank may use and by the 32 hardware work queues (2 streams per slot + 2 copy streams)
+    lanes = int(os.environ.get("PANO_BATCH_LANES", a.lanes or max(2, min(7, ncpu // 2))))
     os.environ["PANO_BATCH_LANES"] = str(lanes)
     eng = pkg.Engine(device=local, seed=SEED)
     w, h, P = a.w, a.h, a.pairs
-    D = min(a.distinct, P)                       # distinct pairs; a step cycles over them
-    host = [cached_pair(w, h, 1000 + rank * D + i) for i in range(D)]
-    Ld0 = [torch.from_numpy(l).cuda() for l, _ in host]
-    Rd0 = [torch.from_numpy(r).cuda() for _, r in host]
-    Lh0 = [torch.from_numpy(l).pin_memory() for l, _ in host]
-    Rh0 = [torch.from_numpy(r).pin_memory() for _, r in host]
-    cap = 3 * (2 * w + 64) * (h + 256)
-    Ch0 = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(D)]
-    Ld, Rd = [Ld0[i % D] for i in range(P)], [Rd0[i % D] for i in range(P)]
-    Lh, Rh = [Lh0[i % D] for i in range(P)], [Rh0[i % D] for i in range(P)]
-    Ch = [Ch0[i % D] for i in range(P)]
+    npx = w * h
+
+    # ---- the workload: P distinct pairs, generated on the device ---------------------------------
+    t_gen = time.perf_counter()
+    Ld, Rd = [], []
+    for i in range(P):
+        l, r, _ = synth.make_pair_torch(w, h, seed=1000 + rank * P + i, device="cuda")
+        Ld.append(l); Rd.append(r)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        res, ms = eng.stitchBatch(Ld, Rd)
-        return res, ms
-
-    def step_e2e():
-        res, ms = eng.stitchBatch([t.numpy() for t in Lh], [t.numpy() for t in Rh],
-                                  canvases_out=[c.numpy() for c in Ch])
-        return res, ms
-
     pdist = importlib.import_module(PKG + ".dist")
     n_total = world * P
-    my_idx = [rank * P + i for i in range(P)]   # bench shards: P resident pairs per GPU (weak scaling)
+    my_idx = [rank * P + i for i in range(P)]
     est = torch.cuda.ExternalStream(eng.stream_ptr())
 
     def exchange(res):
-        """the path's only collective: all-gather of the per-pair homographies (96 B each)"""
+        """the path's only collective: all-gather of the per-pair homography records (96 B each)"""
         if world > 1:
-            return pdist.all_gather_results(pdist.pack_results(my_idx, res), n_total, device="cuda")
+            idx = [rank * len(res) + i for i in range(len(res))]
+            return pdist.all_gather_results(pdist.pack_results(idx, res), world * len(res), device="cuda")
         return None
 
     def timed(step_fn, steps):
-        """K steps bracketed by barrier + synchronize; device time between two events on the
-        engine's stream (includes every host gap inside the region)"""
+        """K steps bracketed by barrier + synchronize; device time between two events on the engine's stream
+        (includes every host gap inside the region)"""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(est)
-        stage = {"detect": 0.0, "match": 0.0, "ransac": 0.0, "warp": 0.0}
         last = None
         for _ in range(steps):
             last, _ms = step_fn()
             exchange(last)
-            for r in last:
-                for k in stage:
-                    stage[k] += r["ms"][k]
         e1.record(est)
         e1.synchronize()
         barrier()
-        return e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0, stage, last
+        return e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0, last
 
-    # ---- resident-input throughput --------------------------------------------------------
+    # ---- resident-input throughput --------------------------------------------------------------
+    def step_resident():
+        return eng.stitchBatch(Ld, Rd)
+
     for _ in range(a.warmup):
         res, _ = step_resident()
         exchange(res)
-    assert all(r["status"] == 0 for r in res), [r["status_name"] for r in res]
+    bad = [r["status_name"] for r in res if r["status"] != 0]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     n0 = eng.kernel_launches()
-    ms_dev, wall_ms, stage, res = timed(step_resident, a.steps)
+    ms_dev, wall_ms, res = timed(step_resident, a.steps)
     launches = eng.kernel_launches() - n0
     clocks = sampler.stop() if rank == 0 else None
-    # ---- end-to-end (host buffers) ----------------------------------------------------------
+
+    # ---- end-to-end (host buffers, distinct for every pair) ---------------------------------------
+    canvas_bytes = [3 * r["canvas"][0] * r["canvas"][1] for r in res]
+    cap = max(canvas_bytes) + (1 << 20)
+    per_pair = 2 * 3 * npx + cap
+    budget = int(0.45 * mem_available_bytes() / max(world, 1))
+    Pe = max(8, min(P, budget // per_pair))           # pairs of the e2e leg (all P unless host memory is short)
+    t_pin = time.perf_counter()
+    pool = pinned_bytes(torch, Pe * per_pair)
+    t_pin = time.perf_counter() - t_pin
+    Lh, Rh, Ch = [], [], []
+    for i in range(Pe):
+        o = i * per_pair
+        lh = pool[o:o + 3 * npx].view(h, w, 3); rh = pool[o + 3 * npx:o + 6 * npx].view(h, w, 3)
+        lh.copy_(Ld[i]); rh.copy_(Rd[i])
+        Lh.append(lh); Rh.append(rh); Ch.append(pool[o + 6 * npx:o + per_pair])
+    torch.cuda.synchronize()
+    Lnp, Rnp, Cnp = [t.numpy() for t in Lh], [t.numpy() for t in Rh], [t.numpy() for t in Ch]
+
+    def step_e2e():
+        return eng.stitchBatch(Lnp, Rnp, canvases_out=Cnp)
+
     for _ in range(min(a.warmup, 2)):
         step_e2e()
-    ms_e2e, _, _, res_e = timed(step_e2e, a.steps)
+    ms_e2e, _, res_e = timed(step_e2e, a.steps)
     d2h = sum(3 * r["canvas"][0] * r["canvas"][1] for r in res_e)
-    h2d = P * 2 * 3 * w * h
+    h2d = Pe * 2 * 3 * npx
+    # the e2e canvases are the same bytes the resident run produced (spot check: pair 0 against a fresh device canvas)
+    t_ceiling = copy_ceiling(torch, dist, world, Lh, Rh, Ch, canvas_bytes[:Pe], Ld, Rd)
+
     if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e, wall_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_dev, ms_e2e, wall_ms, t_ceiling], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e, wall_ms = [float(x) for x in t]
-        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        ms_dev, ms_e2e, wall_ms, t_ceiling = [float(x) for x in t]
+        lt = torch.tensor([launches, len(bad)], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt)
-        launches = int(lt[0])
-    mp_step = world * P * 2 * w * h / 1e6
-    value = mp_step * a.steps / (ms_dev / 1000.0)
-    e2e_val = mp_step * a.steps / (ms_e2e / 1000.0)
+        launches, nbad = int(lt[0]), int(lt[1])
+    else:
+        nbad = len(bad)
+    mp_pair = 2 * npx / 1e6
+    value = world * P * mp_pair * a.steps / (ms_dev / 1000.0)
+    e2e_val = world * Pe * mp_pair * a.steps / (ms_e2e / 1000.0)
+    ceiling_val = world * Pe * mp_pair / t_ceiling
 
+    # ---- single-pair latency (rank 0; the other ranks idle at the barrier below) ---------------------
+    latency = None
     if rank == 0:
-        # ---- roofline of the dominant kernel ------------------------------------------------
-        hbm, how = peaks()
-        npx = w * h
-        r0 = res[0]
-        stage_ms = {k: v / (a.steps * P) for k, v in stage.items()}
-        resp = torch.empty((h, w), dtype=torch.float64, device="cuda")
-        Limg = Ld[0]
-
-        def k_harris():
-            eng._check(eng.lib.pano_harris_response(eng.ctx, C.c_void_p(Limg.data_ptr()), w, h,
-                                                    C.c_size_t(Limg.stride(0)), 1, C.c_double(0.04),
-                                                    C.c_void_p(resp.data_ptr())))
-        t_harris = time_kernel(eng, torch, k_harris)
-        cw, ch = r0["canvas"][0], r0["canvas"][1]
-        pitch = (3 * cw + 255) // 256 * 256   # same pitched layout the fused path uses
-        canvas = torch.empty((ch, pitch), dtype=torch.uint8, device="cuda")
-        Hm = np.ascontiguousarray(r0["H"])
-        info = pkg.CanvasInfo()
-
-        def k_warp():
-            eng._check(eng.lib.pano_warp_overlay(eng.ctx, C.c_void_p(Ld[0].data_ptr()), w, h, C.c_size_t(Ld[0].stride(0)),
-                                                 C.c_void_p(Rd[0].data_ptr()), w, h, C.c_size_t(Rd[0].stride(0)), 1,
-                                                 Hm.ctypes.data_as(C.c_void_p), C.c_void_p(canvas.data_ptr()),
-                                                 C.c_size_t(canvas.stride(0)), C.c_size_t(canvas.numel()),
-                                                 C.byref(info)))
-        t_warp_api = time_kernel(eng, torch, k_warp)          # through the stage entry point (launch + sync)
-        # the kernel itself: CUDA events recorded on the engine's stream right around the launch
-        # inside the fused pair call (pano_pair_result.ms_warp), median of 7 single-pair runs
-        os.environ["PANO_BATCH_LANES"] = "1"
-        t_warp = statistics.median([eng.stitchTwoImages(Ld[0], Rd[0], fetch=False)[1]["ms"]["warp"] for _ in range(7)])
-        os.environ["PANO_BATCH_LANES"] = str(lanes)
-        # matcher stage (descriptor gather + tcgen05 distance GEMM + emit) on resident inputs
-        kl_t = torch.zeros((max(r0["kl"], 1), 2), dtype=torch.int32, device="cuda")
-        kr_t = torch.zeros((max(r0["kr"], 1), 2), dtype=torch.int32, device="cuda")
-        cnt = C.c_int(0)
-        ho = pkg.HarrisCornerOptions()
-        eng._check(eng.lib.pano_detect(eng.ctx, C.c_void_p(Ld[0].data_ptr()), w, h, C.c_size_t(Ld[0].stride(0)), 1,
-                                       C.byref(ho), C.c_void_p(kl_t.data_ptr()), r0["kl"], C.byref(cnt)))
-        eng._check(eng.lib.pano_detect(eng.ctx, C.c_void_p(Rd[0].data_ptr()), w, h, C.c_size_t(Rd[0].stride(0)), 1,
-                                       C.byref(ho), C.c_void_p(kr_t.data_ptr()), r0["kr"], C.byref(cnt)))
-        m_t = torch.empty((max(r0["kr"], 1), 3), dtype=torch.int32, device="cuda")
-
-        def k_match():
-            eng._check(eng.lib.pano_match(eng.ctx, C.c_void_p(kr_t.data_ptr()), r0["kr"], C.c_void_p(kl_t.data_ptr()),
-                                          r0["kl"], C.c_void_p(Rd[0].data_ptr()), w, h, C.c_size_t(Rd[0].stride(0)),
-                                          C.c_void_p(Ld[0].data_ptr()), w, h, C.c_size_t(Ld[0].stride(0)), 1,
-                                          C.byref(ho), 0, C.c_void_p(m_t.data_ptr()), r0["kr"], C.byref(cnt)))
-        t_match = time_kernel(eng, torch, k_match)
-        traffic = {}
-        tf = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from ncu --set full
-        if os.path.exists(tf):
-            traffic = json.load(open(tf))
-        kernels = {
-            "harris_response_kernel": {"ms": t_harris, "alg_bytes": 3 * npx, "launches_per_pair": 2,
-                                       "note": "FP64-pipe bound by construction (157 non-fusable FP64 ops/px); "
-                                               "algorithmic traffic is 3 B/px"},
-            "warp_fast_kernel": {"ms": t_warp, "alg_bytes": 3 * (2 * npx + cw * ch), "launches_per_pair": 1,
-                                 "note": "HBM bound by its data flow (both sources read once, canvas written once); "
-                                         "the bit-exact fixed-point emulation makes it issue / load-latency bound in practice "
-                                         "(ncu: IPC 3.0, ALU pipe 49 %, DRAM 44 MB)"},
-        }
-        dom = max(stage_ms, key=stage_ms.get)
-        # The roofline object describes warp_fast_kernel (warp.cu): the kernel of the step that is HBM bound
-        # by design (sources read once, canvas written once).  The kernel with the largest share of
-        # the step is replay_cells_kernel (RANSAC sample replay): integer ALU bound (ncu: ALU pipe 66 %,
-        # IPC 3.05, DRAM < 1 %), so neither an HBM nor a tensor roofline applies to it; the
-        # Harris stencil is FP64-pipe bound (ncu: FP64 pipe 67 % active).  See DESIGN.md section 4 and the
-        # launch lists under profiles/.
-        top = "warp_fast_kernel"
-        ach = kernels[top]["alg_bytes"] / (kernels[top]["ms"] / 1000.0) / 1e9
-        match_ops = 2.0 * r0["kr"] * r0["kl"] * 75
-        roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                    "traffic": traffic.get(top), "peak_source": how + " copy bandwidth (MEASURED_PEAKS.json)",
-                    "kernel_ms": kernels[top]["ms"], "stage_call_ms": t_warp_api, "note": kernels[top]["note"],
-                    "other_kernels": {k: {"ms": v["ms"], "achieved_GBs": v["alg_bytes"] / (v["ms"] / 1e3) / 1e9,
-                                          "frac": v["alg_bytes"] / (v["ms"] / 1e3) / 1e9 / hbm,
-                                          "traffic": traffic.get(k)} for k, v in kernels.items()},
-                    "matcher": {"bound": "tensor", "stage_ms": t_match, "pairs": r0["kr"] * r0["kl"],
-                                "achieved_TOPs": match_ops / (t_match / 1e3) / 1e12,
-                                "note": "whole match stage (gather + tcgen05 kind::i8 GEMM with fused arg-min + emit); "
-                                        "the GEMM kernel itself is 24 us: TMEM-read bound (128 KB of s32 accumulators per 384-cycle tile), "
-                                        "sm__pipe_tensor_cycles_active 21.7 % (profiles/r01_final_match_tc_kernel.ncu-rep)",
-                                "kernel_us_ncu": 24.7, "tensor_pipe_active_pct": 21.7},
-                    "stage_ms_per_pair": stage_ms, "dominant_stage": dom,
-                    "dominant_kernel": {"name": "replay_cells_kernel", "bound": "integer ALU (not HBM, not tensor)",
-                                        "evidence": "profiles/r01_final_replay_cells_kernel.ncu-rep, profiles/r01_final_launches.csv"}}
-        # ---- CPU baseline: serial oracle on one core, bounded sample ---------------------------
-        cpu = None
-        if not a.no_cpu:
-            from oracle.oracle import Oracle
-            O = Oracle()
-            l, r = host[0]
+        dev_ms, wall = [], []
+        for i in range(3 + 20):
+            L, R = Ld[i % P], Rd[i % P]
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
-            o = O.stitch_pair(l, r, seed=SEED)
-            dt = time.perf_counter() - t0
-            ok = (o["status"] == 1 and np.array_equal(o["H"].view(np.uint64), res[0]["H"].view(np.uint64)))
-            o0 = None
-            if a.cpu_o0:   # what the reference's CMake actually builds (no build type => -O0); slow
-                O0 = Oracle("O0")
-                t0 = time.perf_counter()
-                O0.stitch_pair(l, r, seed=SEED)
-                o0 = 2 * npx / 1e6 / (time.perf_counter() - t0)
-            cpu = {"value": 2 * npx / 1e6 / dt, "unit": UNIT, "cores": 1, "kind": "port", "value_O0_build": o0,
-                   "sample": "1 pair of the same workload, serial oracle (-O2), %.2f s; "
-                             "H bit-identical to the engine's: %s" % (dt, ok),
-                   "stage_ms": o["times_ms"]}
+            _, r = eng.stitchTwoImages(L, R, fetch=False)
+            dt = (time.perf_counter() - t0) * 1000.0
+            if i >= 3:
+                dev_ms.append(r["ms"]["total"]); wall.append(dt)
+        latency = {"ms_per_pair_device_median": statistics.median(dev_ms), "ms_per_pair_wall_median": statistics.median(wall),
+                   "ms_per_pair_device_min": min(dev_ms), "pairs": 20,
+                   "how": "one pano_stitch_pair call at a time on an otherwise idle GPU, resident inputs, 20 distinct pairs "
+                          "after 3 warm-ups; device = CUDA events inside the C ABI, wall = host clock around the call"}
+
+    line = None
+    if rank == 0:
+        hbm, how = peaks()
+        r0 = res[0]
+        cw, ch = r0["canvas"][0], r0["canvas"][1]
+        # ---- per-kernel device times, measured live: events around the launches (pano_set_profile) ----
+        eng.set_profile(True)
+        reps = 9
+        for i in range(reps):
+            eng.stitchTwoImages(Ld[0], Rd[0], fetch=False)
+        prof = eng.get_profile()
+        eng.set_profile(False)
+        k_ms = {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}
+        k_per_pair = {k: v[0] / reps for k, v in prof.items()}
+        mb = {}
+        f = os.path.join(ROOT, "profiles", "r02_microbench.json")
+        if os.path.exists(f):
+            mb = json.load(open(f))
+        ncu = {}
+        f = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")
+        if os.path.exists(f):
+            ncu = json.load(open(f))
+        alg_warp = 3 * (2 * npx + cw * ch)
+        ach = alg_warp / (k_ms["warp"] / 1e3) / 1e9
+        fp64_peak = (mb.get("fp64_instr_per_s") or {}).get("dmul_dadd_pair")
+        harris_fp64 = 157.0 * npx * (32 * 64) / (30 * 62)       # incl. the fused kernel's 1-px response halo
+        match_ops = 2.0 * r0["kr"] * r0["kl"] * 75
+        roofline = {
+            "bound": "hbm", "kernel": "warp_quad_kernel (warp.cu)", "achieved": ach, "peak": hbm, "unit": "GB/s",
+            "frac": ach / hbm, "traffic": (ncu.get("warp_quad_kernel") or {}).get("dram_bytes"),
+            "peak_source": how, "kernel_ms": k_ms["warp"], "algorithmic_bytes": alg_warp,
+            "how": "CUDA events on the engine's stream right around the launch, inside pano_stitch_pair, mean of %d "
+                   "single-pair runs (the RANSAC kernels before it have flushed the sources from L2)" % reps,
+            "other_kernels": {
+                "harris_fused_kernel": {"ms_per_image": k_ms["harris_fused"], "bound": "fp64 pipe",
+                                        "fp64_instr": harris_fp64,
+                                        "achieved_fp64_instr_per_s": harris_fp64 / (k_ms["harris_fused"] / 1e3),
+                                        "peak_fp64_instr_per_s": fp64_peak,
+                                        "frac_of_fp64_peak": (harris_fp64 / (k_ms["harris_fused"] / 1e3) / fp64_peak) if fp64_peak else None,
+                                        "peak_source": "tools/microbench.cu on this GPU model (profiles/r02_microbench.json)",
+                                        "hbm_frac": 3 * npx / (k_ms["harris_fused"] / 1e3) / 1e9 / hbm},
+                "match_tc_kernel": {"ms": k_ms["match_tc"], "bound": "tensor (int8 tcgen05) / epilogue",
+                                    "pairs": r0["kr"] * r0["kl"], "achieved_TOPs": match_ops / (k_ms["match_tc"] / 1e3) / 1e12,
+                                    "tensor_pipe_active_pct_ncu": (ncu.get("match_tc_kernel") or {}).get("tensor_pipe_active_pct"),
+                                    "ncu_source": "profiles/r02_ncu_metrics.json (ncu --set full capture of this kernel)"},
+                "replay (all kernels of the shuffle replay)": {"ms_per_pair": k_per_pair["replay"], "bound": "integer ALU + dependent phases"},
+                "dlt_kernel": {"ms": k_ms["dlt"], "bound": "latency (136 dependent Jacobi rotations per hypothesis)"},
+                "score_kernel": {"ms": k_ms["score"], "bound": "fp64 pipe"},
+                "descriptor_gather": {"ms_per_image": k_ms["descriptor_gather"]},
+                "scan_scatter": {"ms_per_image": k_ms["scan_scatter"]}},
+            "kernel_ms_sum_per_pair": sum(k_per_pair.values())}
+        # ---- CPU baseline: the reference's own code on this box (bounded: one pair, OpenMP build, all threads;
+        # the serial build is estimated from a sample of its stages) ---------------------------------
+        cpu = None
+        if not a.no_cpu and world == 1:
+            cpu = cpu_baseline(a, Ld[0].cpu().numpy(), Rd[0].cpu().numpy(), res[0])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_dev / a.steps, "ms_per_pair": ms_dev / (a.steps * P), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
-                "config": {"workload": "synthetic %dx%d textured pair, known homography (BASELINE config 3), "
-                                       "%d pairs per GPU per step cycling over %d distinct ones, %d overlapped lanes per GPU (PANO_BATCH_LANES)" % (w, h, P, D, lanes),
-                           "pairs_per_step_per_gpu": P, "seed": SEED, "l2_policy": "inputs %d MB per GPU > 126 MB L2, "
-                           "rotating within every step" % (D * 2 * 3 * npx // 2**20), "keypoints": [r0["kl"], r0["kr"]],
-                           "matches": r0["m"], "inliers": r0["best"], "parallelism": "pairs sharded over %d GPU(s), "
-                           "no data-path collective" % world},
-                "clocks": clocks, "gpu_launches": launches,
+                "config": {"workload": workload_name(w, h, P), "pairs_per_step_per_gpu": P, "distinct_pairs_per_gpu": P,
+                           "seed": SEED, "l2_policy": "inputs %.1f GB per GPU, every pair distinct: nothing is re-read from L2" % (P * 6 * npx / 1e9),
+                           "lanes": lanes, "pipeline_depth": int(os.environ.get("PANO_BATCH_DEPTH", "2")),
+                           "keypoints_pair0": [r0["kl"], r0["kr"]], "matches_pair0": r0["m"], "inliers_pair0": r0["best"],
+                           "matches_min_max": [min(r["m"] for r in res), max(r["m"] for r in res)],
+                           "failed_pairs": nbad, "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
+                           "cpu_model": cpu_model(), "host_threads_this_rank": ncpu, "numa": numa,
+                           "generation_s": round(t_gen, 1), "pinned_alloc_s": round(t_pin, 1)},
+                "clocks": clocks, "gpu_launches": launches, "gpu_launches_per_pair": launches / (a.steps * P * world),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_pair": ms_e2e / (a.steps * P)},
-                "wall_ms_per_step": wall_ms / a.steps, "collective": "all_gather of %d x 96 B homography records per step (NCCL)" % n_total if world > 1 else "none (single GPU)", "roofline": roofline, "cpu_baseline": cpu}
+                        "ms_per_pair": ms_e2e / (a.steps * Pe), "pairs_per_step_per_gpu": Pe,
+                        "copy_ceiling": {"value": ceiling_val, "unit": UNIT, "frac": e2e_val / ceiling_val,
+                                         "how": "the same H2D / D2H copies alone (both directions at once, all ranks "
+                                                "concurrently), best of 2"}},
+                "latency": latency, "wall_ms_per_step": wall_ms / a.steps,
+                "collective": ("all_gather of %d x 96 B homography records per step (NCCL)" % n_total) if world > 1 else "none (single GPU)",
+                "roofline": roofline, "cpu_baseline": cpu}
+    barrier()
+    if rank == 0:
         print(json.dumps(line, default=float), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def cpu_baseline(a, l, r, eng_res):
+    """The reference's own code on this box's host cores.  Primary figure: its OpenMP pipeline on all threads, one
+    full pair of the workload.  Also: its serial pipeline (1 core), estimated from a sample - detection of both
+    images and RANSAC in full, the matcher on every 16th query keypoint (its cost is linear in the queries)."""
+    ncpu = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
+    from oracle import ref as refmod
+    mp = 2 * a.w * a.h / 1e6
+    if not refmod.available("omp"):
+        from oracle.oracle import Oracle
+        O = Oracle("omp")
+        t0 = time.perf_counter()
+        o = O.stitch_pair(l, r, seed=SEED)
+        dt = time.perf_counter() - t0
+        return {"value": mp / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+                "sample": "1 pair, oracle port -O2 -fopenmp (oracle/_ref not present on this box), %.2f s" % dt}
+    R = refmod.Reference("omp")
+    t0 = time.perf_counter()
+    s = R.stitch_pair(l, r, seed=SEED)
+    dt = time.perf_counter() - t0
+    out = {"value": mp / dt, "unit": UNIT, "cores": R.num_threads(), "kind": "reference", "cpu_model": cpu_model(),
+           "sample": "1 full pair of the workload (pair 0), the reference's OpenMP pipeline (src/openmp/main.cpp, "
+                     "unmodified, -O2 -fopenmp, cvshim), %.2f s" % dt,
+           "stage_ms": s["times_ms"]}
+    try:
+        S = refmod.Reference("")
+        t0 = time.perf_counter(); kl = S.detect(l); kr = S.detect(r); t_det = time.perf_counter() - t0
+        sub = kr[::16]
+        t0 = time.perf_counter(); S.match(sub, kl, r, l); t_m = (time.perf_counter() - t0) * len(kr) / max(len(sub), 1)
+        m = R.match(kr, kl, r, l)          # (full match list from the OpenMP build, only to feed RANSAC)
+        t0 = time.perf_counter(); H = S.ransac(kr, kl, m, seed=SEED); t_r = time.perf_counter() - t0
+        same = H is not None and np.array_equal(np.ascontiguousarray(H).view(np.uint64), eng_res["H"].view(np.uint64))
+        out["serial_reference"] = {"value_estimate": mp / (t_det + t_m + t_r), "cores": 1,
+                                   "stage_s": {"detect_both": t_det, "match_extrapolated": t_m, "ransac": t_r},
+                                   "sample": "src/serial/main.cpp unmodified (-O2, cvshim): detection and RANSAC in full, matcher "
+                                             "on every 16th query keypoint x16; warp + overlay (~1 s) not included",
+                                   "H_bit_identical_to_engine": bool(same)}
+    except Exception as e:   # the serial estimate is optional
+        out["serial_reference"] = {"error": str(e)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--pairs", type=int, default=144, help="4K pairs per GPU per step (one pano_stitch_batch call; 144 = 6, 12 or 18 per lane; BASELINE config 5 is a batch of 256)")
-    ap.add_argument("--distinct", type=int, default=4, help="distinct pairs the step cycles over (4 = 189 MB > L2)")
+    ap.add_argument("--workload", default="c5", choices=["c5", "c1", "c2", "c3", "chain"])
+    ap.add_argument("--pairs", type=int, default=256, help="distinct 4K pairs per GPU per step (BASELINE config 5: 256)")
+    ap.add_argument("--lanes", type=int, default=0, help="batch lanes (host threads) per GPU; 0 = from the core count")
     ap.add_argument("--size", default="3840x2160")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-o0", action="store_true", help="also time the -O0 build of the oracle (the reference's default flags)")
     a = ap.parse_args()
     a.w, a.h = [int(v) for v in a.size.split("x")]
+    if a.workload != "c5":
+        other = importlib.import_module("tools.bench_configs")
+        return other.run(a)
     if a.impl == "reference":
         run_reference(a)
     else:

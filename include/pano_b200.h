@@ -46,7 +46,8 @@ typedef enum {
   PANO_ERR_ROI = 6,              /* left ROI outside canvas: the reference throws at :376 */
   PANO_ERR_CAPACITY = 7,         /* caller buffer too small; required size is reported */
   PANO_ERR_UNSUPPORTED = 8,      /* option outside what the engine implements */
-  PANO_ERR_NO_DEVICE = 9         /* no CUDA device / not an sm_100 device */
+  PANO_ERR_NO_DEVICE = 9,        /* no CUDA device / not an sm_100 device */
+  PANO_ERR_BUSY = 10             /* an asynchronous call on this context has not completed yet */
 } pano_status;
 
 enum { PANO_MEM_HOST = 0, PANO_MEM_DEVICE = 1 };
@@ -172,6 +173,21 @@ int pano_stitch_pair(pano_ctx* ctx, const uint8_t* left, int wl, int hl, size_t 
                      const pano_harris_opts* hopts, const pano_ransac_opts* ropts,
                      pano_pair_result* res);
 
+/* Asynchronous, stream-ordered variant of pano_stitch_pair (the reference's stage calls block on
+ * the default stream, ref: src/gpu/convolution.cu:35-53).  Returns at once; the pair runs on a worker owned by the
+ * context.  `stream` (a cudaStream_t on the context's device, may be NULL): the pair's device work starts after
+ * everything already enqueued on `stream`, and work enqueued on `stream` after pano_pair_wait / a successful
+ * pano_pair_query sees the canvas (pano_canvas_device).  Inputs and `res` must stay valid until completion; the
+ * context accepts no other call meanwhile (PANO_ERR_BUSY), except pano_pair_query / pano_pair_wait.
+ * pano_pair_query: PANO_ERR_BUSY while running, else the pair's status (as pano_stitch_pair would have returned).
+ * pano_pair_wait: blocks the calling host thread until completion and returns that status. */
+int pano_stitch_pair_async(pano_ctx* ctx, const uint8_t* left, int wl, int hl, size_t stride_l,
+                           const uint8_t* right, int wr, int hr, size_t stride_r, int mem,
+                           const pano_harris_opts* hopts, const pano_ransac_opts* ropts,
+                           void* stream, pano_pair_result* res);
+int pano_pair_query(pano_ctx* ctx);
+int pano_pair_wait(pano_ctx* ctx);
+
 /* Copies the context's current canvas (result of the last successful pair / fold step). */
 int pano_get_canvas(pano_ctx* ctx, uint8_t* out, size_t out_stride, size_t cap_bytes, int mem,
                     int* w, int* h);
@@ -225,6 +241,14 @@ int pano_stitch_batch(pano_ctx* ctx, int n, const uint8_t* const* lefts, const u
                       const pano_harris_opts* hopts, const pano_ransac_opts* ropts,
                       pano_pair_result* results, uint8_t* const* canvases_out, size_t canvas_cap_bytes,
                       float* ms_batch);
+
+/* Per-kernel device timing (measurement aid for bench.py's roofline numbers): when on, CUDA events are recorded
+ * right around the engine's main kernel launches.  pano_get_profile waits for the context's streams and returns
+ * the accumulated milliseconds and launch counts per kernel class since pano_set_profile(ctx, 1), in this order:
+ * 0 harris (fused response + NMS), 1 scan/scatter, 2 descriptor gather, 3 tensor-core matcher, 4 emit,
+ * 5 shuffle replay (all its kernels), 6 DLT, 7 scoring, 8 warp + overlay.  Returns the number of classes. */
+int pano_set_profile(pano_ctx* ctx, int on);
+int pano_get_profile(pano_ctx* ctx, double* ms_out, int* count_out, int cap);
 
 /* The context's CUDA stream (a cudaStream_t), so callers can bracket calls with their own
  * events or order their own work against the engine's. */

@@ -84,6 +84,50 @@ def test_dir_mode_default_output(files):
     assert (p.returncode == 0 and os.path.exists(sub / "result.jpg")) or "Failed to write result.jpg" in p.stderr
 
 
+def test_jpeg_inputs_are_decoded_like_cv_imread(files, oracle, tmp_path):
+    """the reference reads its inputs with cv::imread (ref: src/reader/reader.cpp:61,72); without OpenCV C++ the
+    executables decode JPEG through the Python cv2 wheel (same decoder), so the pipeline sees the same pixels"""
+    import cv2
+    d, left, right, paths = files
+    jl, jr = str(tmp_path / "l.jpg"), str(tmp_path / "r.jpg")
+    cv2.imwrite(jl, left); cv2.imwrite(jr, right)
+    out = str(tmp_path / "o.png")
+    p = run([exe("serial"), jl, jr, "--out", out], env=dict(os.environ, PANO_DUMP_DECODED=str(tmp_path)))
+    assert p.returncode == 0, p.stderr[-500:]
+    for i, f in enumerate((jl, jr)):
+        assert np.array_equal(cv2.imread(str(tmp_path / ("decoded_%d.ppm" % i))), cv2.imread(f))
+    o = oracle.stitch_pair(cv2.imread(jl), cv2.imread(jr), seed=12345)
+    assert o["status"] == 1 and np.array_equal(cv2.imread(out), o["canvas"])
+
+
+@pytest.mark.gpu
+def test_nvjpeg_decode_difference_is_reported(files, tmp_path):
+    """PANO_JPEG=nvjpeg decodes on the GPU instead; nvJPEG is not bit-identical to libjpeg-turbo: measure it on the
+    reference's sample photographs when they are staged, else on a synthetic JPEG"""
+    import cv2
+    d, left, right, paths = files
+    mount = [os.path.join(ROOT, "baseline", "_ref", "images", "mountain", "mountain%d.jpg" % i) for i in (1, 2)]
+    if all(os.path.exists(m) for m in mount):
+        jl, jr = mount
+    else:
+        jl, jr = str(tmp_path / "l.jpg"), str(tmp_path / "r.jpg")
+        cv2.imwrite(jl, left); cv2.imwrite(jr, right)
+    e = exe("gpu")
+    stats = {}
+    for mode in ("cv2", "nvjpeg"):
+        sub = tmp_path / mode
+        sub.mkdir()
+        p = run([e, jl, jr, "--out", str(sub / "o.png")], env=dict(os.environ, PANO_DUMP_DECODED=str(sub), PANO_JPEG=mode))
+        assert p.returncode == 0, p.stderr[-500:]
+        stats[mode] = [cv2.imread(str(sub / ("decoded_%d.ppm" % i))) for i in range(2)]
+    for i, f in enumerate((jl, jr)):
+        assert np.array_equal(stats["cv2"][i], cv2.imread(f))          # default path = the reference's decoder
+        diff = np.abs(stats["nvjpeg"][i].astype(np.int16) - stats["cv2"][i].astype(np.int16))
+        print("nvJPEG vs cv2.imread on %s: max %d LSB, mean %.4f LSB, %.2f %% of bytes differ"
+              % (os.path.basename(f), diff.max(), diff.mean(), 100.0 * (diff > 0).mean()))
+        assert diff.max() <= 16      # a decoder difference, not a different image
+
+
 @pytest.mark.gpu
 def test_gpu_stitching_executable(files, oracle):
     import cv2

@@ -84,7 +84,7 @@ class _OracleEngine:
         geom, T = self.O.chain_geometry(sizes, Hs)
         return True, geom, T
 
-    def renderChainBand(self, images, Hs, geom, T, y0, bh):
+    def renderChainBand(self, images, Hs, geom, T, y0, bh, out=None):
         cw, ch, x0, yy0 = geom
         canvas = np.zeros((ch, cw, 3), np.uint8)
         canvas[yy0:yy0 + images[0].shape[0], x0:x0 + images[0].shape[1]] = images[0]
@@ -92,6 +92,9 @@ class _OracleEngine:
             w = self.O.warp_perspective(im, self.O.mul33(T, H), (cw, ch))
             nz = w.any(axis=2)
             canvas[nz] = w[nz]
+        if out is not None:
+            out[:] = canvas[y0:y0 + bh]
+            return out
         return canvas[y0:y0 + bh]
 
 
@@ -105,7 +108,7 @@ def _chain_worker(rank, world, port, out_dir):
     synth = importlib.import_module(PKG + ".synth")
     views = synth.make_strip(n=4, w=320, h=200, seed=21)
     pano, allr = d.stitch_chain_distributed(_OracleEngine(), views)
-    np.save(os.path.join(out_dir, "pano%d.npy" % rank), pano)
+    np.save(os.path.join(out_dir, "pano%d.npy" % rank), np.array(pano))
     dist.destroy_process_group()
 
 

@@ -420,8 +420,9 @@ def test_stitch_batch_equals_pairs(engine, oracle, mem):
 
 
 def test_general_warp_kernel_equals_fast_path(oracle):
-    """PANO_WARP_FAST=0 forces the general (exact-division, 4 px per thread) kernel; it and the fast path must both
-    reproduce the oracle's canvas (pair overlay, plain warpPerspective, band-wise accumulate of chain mode)"""
+    """PANO_WARP_FAST=0 forces the general (exact-division) kernel, PANO_WARP_KERNEL=1 the round-1 one-pixel-per-lane
+    fast kernel, the default is the quad kernel (4 px per thread); all three must reproduce the oracle's canvas (pair
+    overlay, plain warpPerspective, band-wise accumulate of chain mode), on odd canvas widths and unaligned strides"""
     import subprocess
     import sys
     import textwrap
@@ -437,14 +438,23 @@ def test_general_warp_kernel_equals_fast_path(oracle):
         o = O.stitch_pair(left, right, seed=12345)
         assert r["status"] == 0 and np.array_equal(canvas, o["canvas"])
         M = np.array([[0.98, 0.03, 40.5], [-0.02, 1.01, 12.25], [1e-5, -2e-5, 1.0]])
-        w = eng.warpPerspective(right, M, (1100, 640))
-        assert np.array_equal(w, O.warp_perspective(right, M, (1100, 640)))
+        for ds in ((1100, 640), (1101, 77), (333, 9), (130, 641)):
+            w = eng.warpPerspective(right, M, ds)
+            assert np.array_equal(w, O.warp_perspective(right, M, ds)), ds
+        views = synth.make_strip(n=3, w=500, h=300, seed=4)
+        c1, _ = eng.stitchChain(views)
+        c2, _ = O.stitch_chain(views, seed=12345)
+        assert np.array_equal(c1, c2)
+        l2, r2, _ = synth.make_pair(641, 363, seed=8)           # odd width: 3 * w is not a multiple of 4
+        cv, rr = eng.stitchTwoImages(l2, r2)
+        oo = O.stitch_pair(l2, r2, seed=12345)
+        assert (rr["status"] == 0) == (oo["status"] == 1) and (oo["status"] != 1 or np.array_equal(cv, oo["canvas"]))
         print("OK")
     ''') % (ROOT, PKG, PKG)
-    for fast in ("0", "1"):
+    for fast, kern in (("0", "0"), ("1", "0"), ("1", "1")):
         p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
-                           env=dict(os.environ, PANO_WARP_FAST=fast))
-        assert p.returncode == 0 and "OK" in p.stdout, (fast, p.stderr[-800:])
+                           env=dict(os.environ, PANO_WARP_FAST=fast, PANO_WARP_KERNEL=kern))
+        assert p.returncode == 0 and "OK" in p.stdout, (fast, kern, p.stderr[-800:])
 
 
 def test_ransac_rejects_out_of_range_match_indices(engine, oracle, small_pair):

@@ -28,8 +28,11 @@ LIB_PATH = os.path.join(_HERE, "libpano_b200.so")
 PANO_OK = 0
 PANO_ERR_INVALID, PANO_ERR_CUDA, PANO_ERR_NO_MATCHES, PANO_ERR_TOO_FEW_MATCHES = 1, 2, 3, 4
 PANO_ERR_NO_HOMOGRAPHY, PANO_ERR_ROI, PANO_ERR_CAPACITY, PANO_ERR_UNSUPPORTED, PANO_ERR_NO_DEVICE = 5, 6, 7, 8, 9
+PANO_ERR_BUSY = 10
 STATUS_NAMES = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NO_MATCHES", 4: "TOO_FEW_MATCHES", 5: "NO_HOMOGRAPHY",
-                6: "ROI", 7: "CAPACITY", 8: "UNSUPPORTED", 9: "NO_DEVICE"}
+                6: "ROI", 7: "CAPACITY", 8: "UNSUPPORTED", 9: "NO_DEVICE", 10: "BUSY"}
+PROFILE_CLASSES = ["harris_fused", "scan_scatter", "descriptor_gather", "match_tc", "emit", "replay", "dlt", "score",
+                   "warp"]
 MEM_HOST, MEM_DEVICE = 0, 1
 
 MATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("distance", "<f4")])
@@ -42,6 +45,7 @@ EXPORTED_SYMBOLS = [
     "pano_warp_overlay", "pano_warp_perspective", "pano_stitch_pair", "pano_get_canvas", "pano_canvas_device",
     "pano_stitch_fold", "pano_stitch_batch", "pano_stream", "pano_pair_homography", "pano_mul33",
     "pano_chain_geometry", "pano_warp_accumulate", "pano_set_stream", "pano_set_replay_mode",
+    "pano_stitch_pair_async", "pano_pair_query", "pano_pair_wait", "pano_set_profile", "pano_get_profile",
 ]
 
 
@@ -300,6 +304,50 @@ class Engine:
             canvas = self.getCanvas(device=(L.mem == MEM_DEVICE))
         return canvas, d
 
+    def stitchTwoImagesAsync(self, leftImage, rightImage, harrisOpts=None, ransacOpts=None, stream_ptr=None):
+        """pano_stitch_pair_async: returns a handle; .done() polls, .result() waits and returns the result dict.
+        The inputs are kept alive by the handle; the canvas is fetched with getCanvas afterwards."""
+        ho, ro = harrisOpts or HarrisCornerOptions(), ransacOpts or RansacOptions()
+        L, R = _Img(leftImage), _Img(rightImage)
+        assert L.mem == R.mem
+        res = PairResult()
+        st = self.lib.pano_stitch_pair_async(self.ctx, L.ptr, L.w, L.h, C.c_size_t(L.stride), R.ptr, R.w, R.h,
+                                             C.c_size_t(R.stride), L.mem, C.byref(ho), C.byref(ro),
+                                             C.c_void_p(stream_ptr) if stream_ptr else None, C.byref(res))
+        self._check(st)
+        eng = self
+
+        class Handle:
+            keep = (L, R, ho, ro, res)
+            status = None
+
+            def done(self):
+                if self.status is None:
+                    s = eng.lib.pano_pair_query(eng.ctx)
+                    if s == PANO_ERR_BUSY:
+                        return False
+                    self.status = s
+                return True
+
+            def result(self):
+                if self.status is None:
+                    self.status = eng.lib.pano_pair_wait(eng.ctx)
+                eng._check(self.status, allow=(PANO_ERR_NO_MATCHES, PANO_ERR_TOO_FEW_MATCHES, PANO_ERR_NO_HOMOGRAPHY,
+                                               PANO_ERR_ROI))
+                return res.as_dict()
+        return Handle()
+
+    def set_profile(self, on=True):
+        self._check(self.lib.pano_set_profile(self.ctx, 1 if on else 0))
+
+    def get_profile(self):
+        """{kernel class: (total ms, launches)} since set_profile(True)"""
+        n = len(PROFILE_CLASSES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int * n)()
+        self.lib.pano_get_profile(self.ctx, ms, cnt, n)
+        return {PROFILE_CLASSES[i]: (ms[i], cnt[i]) for i in range(n)}
+
     def getCanvas(self, device=False, out=None):
         w, h = C.c_int(0), C.c_int(0)
         self._check(self.lib.pano_get_canvas(self.ctx, None, 0, 0, MEM_HOST, C.byref(w), C.byref(h)))
@@ -401,20 +449,28 @@ class Engine:
         return st == PANO_OK, (info.canvas_w, info.canvas_h, info.left_x, info.left_y), \
             np.array(info.TH[:], np.float64).reshape(3, 3)
 
-    def renderChainBand(self, images, Hs, geom, T, y0, band_h):
-        """rows [y0, y0 + band_h) of the chain canvas: image 0 placed at its integer offset, then
-        every image i >= 1 warped by T * H(0 <- i), non-black pixels overwriting (host arrays)."""
+    def renderChainBand(self, images, Hs, geom, T, y0, band_h, out=None):
+        """rows [y0, y0 + band_h) of the chain canvas: image 0 placed at its integer offset, then every image
+        i >= 1 warped by T * H(0 <- i), non-black pixels overwriting.  The band stays on the device while the images
+        are accumulated into it and crosses PCIe once, into `out` (e.g. this rank's rows of a shared pinned
+        canvas) or into a new host array."""
+        import torch
         cw, ch, x0, yy0 = geom
-        band = np.zeros((band_h, cw, 3), np.uint8)
+        dev = torch.device("cuda", self.device)
+        band = torch.zeros((band_h, cw, 3), dtype=torch.uint8, device=dev)
+        dimgs = [im if _is_torch_cuda(im) else torch.from_numpy(np.ascontiguousarray(im)).to(dev) for im in images[:len(Hs)]]
+        torch.cuda.current_stream(dev).synchronize()
         for i, H in enumerate(Hs):
             M = np.array([[1, 0, x0], [0, 1, yy0], [0, 0, 1.0]]) if i == 0 else self.mul33(T, H)
-            im = _Img(images[i])
-            assert im.mem == MEM_HOST
+            im = _Img(dimgs[i])
             M = np.ascontiguousarray(M, np.float64)
-            self._check(self.lib.pano_warp_accumulate(self.ctx, im.ptr, im.w, im.h, C.c_size_t(im.stride), MEM_HOST,
-                                                      M.ctypes.data_as(C.c_void_p), band.ctypes.data_as(C.c_void_p),
-                                                      cw, ch, int(y0), int(band_h), C.c_size_t(band.strides[0])))
-        return band
+            self._check(self.lib.pano_warp_accumulate(self.ctx, im.ptr, im.w, im.h, C.c_size_t(im.stride), MEM_DEVICE,
+                                                      M.ctypes.data_as(C.c_void_p), C.c_void_p(band.data_ptr()),
+                                                      cw, ch, int(y0), int(band_h), C.c_size_t(band.stride(0))))
+        if out is None:
+            return band.cpu().numpy()
+        torch.from_numpy(out).copy_(band)
+        return out
 
     def stitchChain(self, images, harrisOpts=None, ransacOpts=None):
         """single-GPU chain mode: returns (panorama or None, [pair result dicts])"""

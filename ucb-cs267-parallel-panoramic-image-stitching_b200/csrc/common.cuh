@@ -77,6 +77,47 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   PANO_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
 }
 
+// ---- optional per-kernel timing (pano_set_profile): CUDA events recorded on the launching stream right around
+// selected launches, read after the call's final synchronisation.  bench.py's roofline numbers come from here, i.e.
+// they are measured live in the run that prints them, not copied from a profiler report.
+enum ProfId { PROF_HARRIS = 0, PROF_NMS_COMPACT, PROF_DESC, PROF_MATCH_TC, PROF_EMIT, PROF_REPLAY, PROF_DLT, PROF_SCORE,
+              PROF_WARP, PROF_N };
+struct Prof {
+  bool on = false;
+  struct Rec { int id; cudaEvent_t a, b; };
+  std::vector<Rec> pool;
+  size_t used = 0;
+  double ms[PROF_N] = {0};
+  int n[PROF_N] = {0};
+};
+extern thread_local Prof* t_prof;
+struct ProfScope {
+  Prof::Rec* r = nullptr;
+  cudaStream_t st;
+  ProfScope(int id, cudaStream_t s) : st(s) {
+    Prof* p = t_prof;
+    if (!p || !p->on) return;
+    if (p->used == p->pool.size()) {
+      Prof::Rec nr;
+      nr.id = id;
+      if (cudaEventCreate(&nr.a) != cudaSuccess || cudaEventCreate(&nr.b) != cudaSuccess) return;
+      p->pool.push_back(nr);
+    }
+    r = &p->pool[p->used++];
+    r->id = id;
+    cudaEventRecord(r->a, st);
+  }
+  ~ProfScope() { if (r) cudaEventRecord(r->b, st); }
+};
+// (call with every stream of the context idle)
+inline void prof_collect(Prof& p) {
+  for (size_t i = 0; i < p.used; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.pool[i].a, p.pool[i].b) == cudaSuccess) { p.ms[p.pool[i].id] += ms; p.n[p.pool[i].id]++; }
+  }
+  p.used = 0;
+}
+
 // every engine kernel launch goes through this: counts it and surfaces launch errors
 extern std::atomic<uint64_t> g_kernel_launches;
 #define PANO_LAUNCH_CHECK()            \
@@ -186,12 +227,18 @@ void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescript
                      unsigned long long* best, DevBuf& keybuf, int* errw);
 bool match_tc_available();
 void match_tc_disable();
+// 2-D byte tensor map (CUtensorMap, 128 bytes) over a pitched image for TMA tile loads; false if not describable
+bool make_tmap_bytes_2d(void* map_out, const void* base, size_t row_bytes, size_t rows, size_t pitch, uint32_t box_bytes,
+                        uint32_t box_rows);
 // turns best[] into pano_match records (ascending query order), applying maxSSD; returns count
 int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
                         const unsigned long long* best, double max_ssd, int offset, int patch,
                         MatchScratch& s, pano_dmatch* out_dev, PinnedBuf& pin, int* errw);
 
+struct MtStream;
 struct RansacScratch {
+  const MtStream* shared_mt = nullptr;       // read-only mt19937 stream generated by the parent context (batch slots share
+                                             // it instead of generating 96 private copies); used when long enough
   DevBuf pts, thr, cand_off, cand_samp, base, samples, Hs, valid, counts, result, mask, plan, pts_bits;
   std::shared_ptr<void> plan_cache;          // host-side replay plans of this context (ransac.cu), keyed by (M, iterations, ...)
   int* errw = nullptr;                       // the context's device error word (see PANO_ERRW_*)

@@ -13,6 +13,8 @@
 // Roofline: FP64-pipe bound (157 non-fusable FP64 ops per pixel against 3 B/px of input).
 #include "common.cuh"
 
+#include <cuda.h>  // CUtensorMap (type only)
+
 namespace pano {
 
 namespace {
@@ -116,6 +118,196 @@ harris_response_kernel(const uint8_t* __restrict__ img, int w, int h, size_t str
     if (cand != nullptr) {
       const unsigned bits = __ballot_sync(0xffffffffu, X < w && Y < h && r > thresh);
       if (tx == 0 && Y < h) cand[(size_t)Y * cand_stride + blockIdx.x] = bits;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1+K2 fused (round 2): response AND strict 3x3 NMS in one kernel; the FP64 response plane (66 MB per 4K image)
+// is never written.  A CTA computes the response of a 32 x 64 tile in shared memory and decides the inner
+// 30 x 62 pixels (tiles overlap by one response pixel on every side: +10 % FP64 work instead of a 66 MB write,
+// a second kernel and its re-read; under 24 concurrent lanes that plane did not fit the L2 and the detect stage
+// went from 0.34 to 2.7 ms per pair).  Data flow per CTA:
+//   TMA      one 2-D tile load (cp.async.bulk.tensor.2d) of 144 bytes x 70 rows of the interleaved BGR image
+//            (38 pixels = 32 + the 3-px halo on each side, starting at the 16-byte boundary below the first byte;
+//            out-of-image bytes are zero-filled by the TMA unit);
+//            images whose base / pitch are not 16-byte aligned take a plain-load fallback of the same tile
+//   phase 1  gray (15-bit fixed point) of 38 x 70 pixels
+//   phase 2  Sobel (integer) and the three products on 36 x 68
+//   phase 3  5x5 Gaussian in the reference's summation order, 8-row vertical strip per thread (each loaded
+//            product row feeds up to five outputs), response -> shared memory
+//   phase 4  threshold + strict NMS on the inner pixels, one ballot word per tile row, OR-ed into the 1-bit/px
+//            mask (keypoints are sparse: almost every word is zero and skipped) + per-row counts
+// Semantics: ref src/serial/main.cpp:119-180, bit-identical keypoints (the response values are the same doubles).
+// ---------------------------------------------------------------------------------------
+constexpr int FX = 32, FY = 64;           // response tile
+constexpr int FRPT = 8;                   // output rows per thread
+constexpr int FBY = FY / FRPT;            // 8 thread rows -> 256 threads
+constexpr int FPW = FX + 4, FPH = FY + 4; // product planes incl. Gaussian halo
+constexpr int FGW = FX + 6, FGH = FY + 6; // gray incl. Sobel halo
+constexpr int FRAW = 144;                 // bytes per raw tile row: 3 * FGW = 114 plus up to 15 bytes of alignment slack (the
+                                          // innermost TMA coordinate of a byte tensor must be a multiple of 16: measured, an
+                                          // unaligned one raises 'illegal instruction'; tools/_tma_probe.cu), multiple of 16
+
+struct FusedSmem {
+  double xx[FPH][FPW];
+  double yy[FPH][FPW];
+  double xy[FPH][FPW];
+  double resp[FY][FX + 1];
+  __align__(128) uint8_t raw[FGH][FRAW];
+  uint8_t gray[FGH][FGW + 2];
+  unsigned long long bar;
+};
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(FX* FBY, 2)
+harris_fused_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ img, int w, int h,
+                    size_t stride, double kparam, GaussTaps taps, double thresh, uint32_t* __restrict__ mask,
+                    int mask_stride, uint32_t* __restrict__ rowcnt) {
+  extern __shared__ __align__(128) uint8_t fused_smem_raw[];
+  FusedSmem& S = *reinterpret_cast<FusedSmem*>(fused_smem_raw);
+  const int tid = threadIdx.y * FX + threadIdx.x;
+  // response tile origin: the inner (decided) pixels are x0 + 1 .. x0 + FX - 2, y0 + 1 .. y0 + FY - 2
+  const int x0 = blockIdx.x * (FX - 2) - 1, y0 = blockIdx.y * (FY - 2) - 1;
+  const int braw = 3 * (x0 - 3);       // first image byte of the tile row (may be negative)
+  const int araw = braw & ~15;         // 16-byte boundary at or below it (floor, also for negative values)
+  const int boff = braw - araw;        // 0 .. 15: where pixel 0 of the tile sits inside a raw row
+
+  // ---- raw BGR tile: pixels x0 - 3 .. x0 - 3 + 37 inside 144 bytes from the aligned start, rows y0 - 3 .. y0 - 3 + 69
+  if (USE_TMA) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&S.bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(FRAW * FGH)) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(&S.raw[0][0])), "l"(reinterpret_cast<uint64_t>(&tmap)),
+            "r"(araw), "r"(y0 - 3), "r"(bar) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar) : "memory");
+    }
+  } else {
+    for (int i = tid; i < FGH * (FRAW / 4); i += FX * FBY) {
+      const int ry = i / (FRAW / 4), rw = i - ry * (FRAW / 4);
+      const int Y = y0 - 3 + ry;
+      uint32_t v = 0;
+      if (Y >= 0 && Y < h) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int B = araw + 4 * rw + b;
+          if (B >= 0 && B < 3 * w) v |= (uint32_t)img[(size_t)Y * stride + B] << (8 * b);
+        }
+      }
+      reinterpret_cast<uint32_t*>(&S.raw[ry][0])[rw] = v;
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 1: gray (values outside the image are zero bytes -> gray 0, never used by a decided pixel)
+  for (int i = tid; i < FGH * FGW; i += FX * FBY) {
+    const int gy = i / FGW, gx = i - gy * FGW;
+    const uint8_t* p = &S.raw[gy][boff + 3 * gx];
+    S.gray[gy][gx] = (uint8_t)gray_u8(p[0], p[1], p[2]);
+  }
+  __syncthreads();
+
+  // ---- phase 2: Sobel (integer, exact) and the three products on the tile + 2-px halo
+  for (int i = tid; i < FPH * FPW; i += FX * FBY) {
+    const int py = i / FPW, px = i - py * FPW;
+    const int X = x0 - 2 + px, Y = y0 - 2 + py;
+    int gx = 0, gy = 0;
+    if (X >= 1 && X <= w - 2 && Y >= 1 && Y <= h - 2) {
+      const int r = py + 1, c = px + 1;
+      const int a00 = S.gray[r - 1][c - 1], a01 = S.gray[r - 1][c], a02 = S.gray[r - 1][c + 1];
+      const int a10 = S.gray[r][c - 1], a12 = S.gray[r][c + 1];
+      const int a20 = S.gray[r + 1][c - 1], a21 = S.gray[r + 1][c], a22 = S.gray[r + 1][c + 1];
+      gx = (a02 - a00) + 2 * (a12 - a10) + (a22 - a20);
+      gy = (a20 - a00) + 2 * (a21 - a01) + (a22 - a02);
+    }
+    S.xx[py][px] = (double)(gx * gx);
+    S.yy[py][px] = (double)(gy * gy);
+    S.xy[py][px] = (double)(gx * gy);
+  }
+  __syncthreads();
+
+  // ---- phase 3: 5x5 Gaussian of the three planes for a vertical strip of FRPT pixels (input rows in increasing
+  // order, so every output accumulates its 25 terms in the reference's (row, column) order), response
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  {
+    double axx[FRPT], ayy[FRPT], axy[FRPT];
+#pragma unroll
+    for (int o = 0; o < FRPT; o++) axx[o] = ayy[o] = axy[o] = 0.0;
+#pragma unroll
+    for (int r = 0; r < FRPT + 4; r++) {
+      double vxx[5], vyy[5], vxy[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        vxx[j] = S.xx[ty * FRPT + r][tx + j];
+        vyy[j] = S.yy[ty * FRPT + r][tx + j];
+        vxy[j] = S.xy[ty * FRPT + r][tx + j];
+      }
+#pragma unroll
+      for (int o = 0; o < FRPT; o++) {
+        const int i = r - o;  // kernel row for output o
+        if (i >= 0 && i < 5) {
+#pragma unroll
+          for (int j = 0; j < 5; j++) {
+            const double g = taps.g[i * 5 + j];
+            axx[o] = __dadd_rn(axx[o], __dmul_rn(vxx[j], g));
+            ayy[o] = __dadd_rn(ayy[o], __dmul_rn(vyy[j], g));
+            axy[o] = __dadd_rn(axy[o], __dmul_rn(vxy[j], g));
+          }
+        }
+      }
+    }
+    const int X = x0 + tx;
+#pragma unroll
+    for (int o = 0; o < FRPT; o++) {
+      const int Y = y0 + ty * FRPT + o;
+      double r = 0.0;
+      if (X >= 2 && X <= w - 3 && Y >= 2 && Y <= h - 3) r = harris_resp(axx[o], ayy[o], axy[o], kparam);
+      S.resp[ty * FRPT + o][tx] = r;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 4: threshold + strict 3x3 NMS of the inner pixels (ref :157-180: y, x in [1, size - 2])
+  {
+    const int X = x0 + tx;
+    // word / shift of this tile row's 32 ballot bits inside the mask row (x0 may be -1)
+    const int wb = (x0 >= 0) ? (x0 >> 5) : -1;
+    const int sh = x0 - 32 * wb;
+#pragma unroll
+    for (int o = 0; o < FRPT; o++) {
+      const int ry = ty * FRPT + o, Y = y0 + ry;
+      bool keep = false;
+      if (tx >= 1 && tx <= FX - 2 && ry >= 1 && ry <= FY - 2 && X >= 1 && X <= w - 2 && Y >= 1 && Y <= h - 2) {
+        const double r = S.resp[ry][tx];
+        if (r > thresh) {
+          keep = r > S.resp[ry - 1][tx - 1] && r > S.resp[ry - 1][tx] && r > S.resp[ry - 1][tx + 1] &&
+                 r > S.resp[ry][tx - 1] && r > S.resp[ry][tx + 1] &&
+                 r > S.resp[ry + 1][tx - 1] && r > S.resp[ry + 1][tx] && r > S.resp[ry + 1][tx + 1];
+        }
+      }
+      const unsigned bits = __ballot_sync(0xffffffffu, keep);
+      if (bits != 0u && tx == 0) {
+        const unsigned long long v = (unsigned long long)bits << sh;
+        const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+        uint32_t* mrow = mask + (size_t)Y * mask_stride;
+        if (lo != 0u && wb >= 0) atomicOr(&mrow[wb], lo);
+        if (hi != 0u) atomicOr(&mrow[wb + 1], hi);
+        atomicAdd(&rowcnt[Y], (uint32_t)__popc(bits));
+      }
     }
   }
 }
@@ -328,16 +520,40 @@ int harris_detect_device(cudaStream_t st, const DevImage& img, const pano_harris
                          DevKeypoints& kp, PinnedBuf& pin) {
   const int w = img.w, h = img.h;
   const int mask_stride = (w + 31) / 32;
-  s.resp.reserve(sizeof(double) * (size_t)w * h);
   s.mask.reserve(sizeof(uint32_t) * (size_t)mask_stride * h);
   s.rowcnt.reserve(sizeof(uint32_t) * (size_t)h);
   s.rowoff.reserve(sizeof(uint32_t) * (size_t)h);
   s.total.reserve(sizeof(uint32_t));
   pin.reserve(64);
 
-  harris_response_device(st, img, o.k, s.resp.as<double>(), o.nms_thresh, s.mask.as<uint32_t>(), mask_stride);
+  static const bool fused_on = [] { const char* e = getenv("PANO_HARRIS_FUSED"); return !(e && atoi(e) == 0); }();
   PANO_CUDA(cudaMemsetAsync(s.rowcnt.p, 0, sizeof(uint32_t) * (size_t)h, st));
-  {
+  if (o.nms_neighborhood == 3 && fused_on) {
+    // fused response + NMS: no response plane (the reference's setting; other neighbourhoods take the two-kernel path)
+    static const GaussTaps taps = make_taps();
+    PANO_CUDA(cudaMemsetAsync(s.mask.p, 0, sizeof(uint32_t) * (size_t)mask_stride * h, st));
+    dim3 grid((w + (FX - 2) - 1) / (FX - 2), (h + (FY - 2) - 1) / (FY - 2)), block(FX, FBY);
+    const size_t smem = sizeof(FusedSmem);
+    static const bool attr = [&] {
+      PANO_CUDA(cudaFuncSetAttribute(harris_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PANO_CUDA(cudaFuncSetAttribute(harris_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      return true;
+    }();
+    (void)attr;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    ProfScope ps(PROF_HARRIS, st);
+    static const bool tma_on = [] { const char* e = getenv("PANO_HARRIS_TMA"); return !(e && atoi(e) == 0); }();
+    if (tma_on && make_tmap_bytes_2d(&tmap, img.p, (size_t)w * 3, (size_t)h, img.stride, FRAW, FGH))
+      harris_fused_kernel<true><<<grid, block, smem, st>>>(tmap, img.p, w, h, img.stride, o.k, taps, o.nms_thresh,
+                                                            s.mask.as<uint32_t>(), mask_stride, s.rowcnt.as<uint32_t>());
+    else
+      harris_fused_kernel<false><<<grid, block, smem, st>>>(tmap, img.p, w, h, img.stride, o.k, taps, o.nms_thresh,
+                                                             s.mask.as<uint32_t>(), mask_stride, s.rowcnt.as<uint32_t>());
+    PANO_LAUNCH_CHECK();
+  } else {
+    s.resp.reserve(sizeof(double) * (size_t)w * h);
+    harris_response_device(st, img, o.k, s.resp.as<double>(), o.nms_thresh, s.mask.as<uint32_t>(), mask_stride);
     dim3 block(32, 8), grid(mask_stride, (h + 7) / 8);
     if (o.nms_neighborhood == 3)
       nms_mask_kernel<1><<<grid, block, 0, st>>>(s.resp.as<double>(), w, h, o.nms_thresh, 1, s.mask.as<uint32_t>(),
@@ -347,7 +563,9 @@ int harris_detect_device(cudaStream_t st, const DevImage& img, const pano_harris
                                                  s.mask.as<uint32_t>(), mask_stride, s.rowcnt.as<uint32_t>());
     PANO_LAUNCH_CHECK();
   }
+  ProfScope* pc = new ProfScope(PROF_NMS_COMPACT, st);
   exclusive_scan_u32(st, s.rowcnt.as<uint32_t>(), s.rowoff.as<uint32_t>(), h, s.total.as<uint32_t>());
+  delete pc;
   PANO_CUDA(cudaMemcpyAsync(pin.p, s.total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   PANO_CUDA(stream_wait(st));
   int n = (int)*pin.as<uint32_t>();

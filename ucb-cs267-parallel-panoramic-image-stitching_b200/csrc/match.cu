@@ -137,6 +137,7 @@ int build_descriptors_device(cudaStream_t st, const DevImage& img, const int32_t
   s.cnt.reserve(sizeof(uint32_t));
   d.orig.reserve(sizeof(int32_t) * (size_t)n);
   pin.reserve(64);
+  ProfScope ps(PROF_DESC, st);
   border_flags_kernel<<<(n + 255) / 256, 256, 0, st>>>(xy, n, img.w, img.h, patch / 2, s.flags.as<uint8_t>());
   PANO_LAUNCH_CHECK();
   compact_flagged(st, s.flags.as<uint8_t>(), n, d.orig.as<int32_t>(), s.cnt.as<uint32_t>(), s.tmp);

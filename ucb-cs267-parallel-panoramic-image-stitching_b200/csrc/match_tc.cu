@@ -10,22 +10,27 @@
 // tiles are visited in train order with a strict '<', and CTAs that split the train range merge
 // through atomicMin on (ssd << 32 | j).
 //
-// Work split: the (query tile, train tile) grid is flattened query-major and every CTA takes one
-// contiguous, equally long run of tiles (a run that crosses a query-tile boundary reloads A and
-// flushes its rows' minima), so all SMs finish together.
-// Structure (one persistent CTA per SM, 320 threads):
-//   warps 0-3  epilogue warpgroup 0: drains TMEM accumulator 0 (even tiles)
-//   warps 4-7  epilogue warpgroup 1: drains TMEM accumulator 1 (odd tiles)
-//              (tcgen05.ld 32x32b.x32 -> registers, key/min, atomicMin)
-//   warp  8    producer: one lane issues TMA loads (cp.async.bulk.tensor.2d, 128B swizzle) of the
-//              descriptor tiles straight into the K-major layout the UMMA descriptors expect, and
-//              bulk copies (cp.async.bulk) of the tile's 256 precomputed column constants
-//   warp  9    one lane issues tcgen05.mma (4 K-steps of 32 bytes per 128x256 tile) and commits
-// Pipelines (mbarriers): B stages full/empty (5 deep, TMA complete_tx; the producer runs ahead of
-// the accumulators so the TMA latency is hidden), A buffer full/empty (2 deep), TMEM accumulators
-// full/empty (2 x 256 columns).  The per-tile column constants live in NCV = NSTAGE + 2 slots: the
-// producer reaches tile m only after the MMA of tile m - NSTAGE was issued, which needed the
-// epilogue of tile m - NSTAGE - 2 to have released its accumulator, so slot m % NCV is free.
+// Work unit = a SUPER-TILE: QT = 4 query tiles (4 x 128 rows) against one train tile of 128 rows.  The four
+// 128 x 128 s32 accumulators fill the CTA's 512 TMEM columns; one B tile (16 KB) brought in by TMA feeds all four,
+// so the train descriptors stream from L2 once per 512 query rows.  (Round 1 / early round 2 streamed a 32 KB B tile
+// per 128 x 256 tile: 122 MB of L2 reads per 11k x 11k match in 22 us = 5.5 TB/s, the L2 bandwidth - that, not
+// tensor-memory read bandwidth, was the bound; tools/microbench.cu measures ~900 B/clk/SM for tcgen05.ld from
+// 16 warps.)  The (super-row, train tile) grid is flattened super-row-major and every CTA takes one contiguous,
+// equally long run of units (a run that crosses a super-row boundary reloads A and flushes its rows' minima), so all
+// SMs finish together.
+// Structure (one persistent CTA per SM, 576 threads):
+//   warps 0-15 epilogue, four groups of four warps (a warp can only read its own 32-lane quarter of TMEM, so a
+//              group of four covers the 128 rows): group g drains accumulator g (query tile g of the super-row):
+//              tcgen05.ld 32x32b.x32 -> registers, key/min (1 IMAD + 1/2 VIMNMX3 per element), atomicMin.
+//   warp 16    producer: one lane issues TMA loads (cp.async.bulk.tensor.2d, 128B swizzle) of the descriptor
+//              tiles straight into the K-major layout the UMMA descriptors expect, and bulk copies
+//              (cp.async.bulk) of the train tile's 128 precomputed column constants
+//   warp 17    one lane issues tcgen05.mma (3 K-steps of 32 bytes per 128x128 accumulator) and commits
+// Pipelines (mbarriers): B stages full/empty (4 deep, TMA complete_tx), A super-rows full/empty (2 deep), one
+// full/empty pair per accumulator: the MMA of unit n + 1 into accumulator g starts as soon as group g has drained
+// unit n, while the other groups are still draining - the tensor pipe only idles when all four groups are behind.
+// The column constants live in NCV = NSTAGE + 2 slots: the producer reaches unit m only after the MMAs of unit
+// m - NSTAGE have completed, which needed every epilogue of unit m - NSTAGE - 1 to have released its accumulator.
 // Every wait is bounded: a bring-up bug raises an error flag instead of hanging the device.
 #include "common.cuh"
 
@@ -36,14 +41,16 @@ namespace pano {
 namespace {
 
 constexpr int TM = 128;            // query rows per tile (UMMA M)
-constexpr int TN = 256;            // train rows per tile (UMMA N)
+constexpr int TN = 128;            // train rows per tile (UMMA N)
+constexpr int QT = 4;              // query tiles per super-tile = TMEM accumulators (4 x 128 columns = 512)
 constexpr int KB = PANO_DESC_STRIDE;  // 128 bytes of K per row = one 128B swizzle atom
-constexpr int NSTAGE = 5;
+constexpr int NSTAGE = 4;
 constexpr int NCV = NSTAGE + 2;      // column-constant slots (see the header comment)
 constexpr int K_STEPS = 3;         // 3 x 32 = 96 >= 75 descriptor bytes; bytes 96..127 of a row are zero padding
 constexpr int A_BYTES = TM * KB;   // 16 KB
-constexpr int B_BYTES = TN * KB;   // 32 KB
-constexpr int TC_THREADS = 320;
+constexpr int B_BYTES = TN * KB;   // 16 KB
+constexpr int EPI_WARPS = 4 * QT;  // group g = warps 4g .. 4g + 3 drains accumulator g
+constexpr int TC_THREADS = 32 * (EPI_WARPS + 2);
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 // instruction descriptor, kind::i8: D = S32 (2 << 4), A = B = UINT8 (0), both K-major,
@@ -52,13 +59,13 @@ constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)
 
 struct Smem {
   // tiles first: 1024-byte aligned (SWIZZLE_128B requirement)
-  uint8_t A[2][A_BYTES];
+  uint8_t A[2][QT][A_BYTES];
   uint8_t B[NSTAGE][B_BYTES];
-  int cvec[NCV][TN];               // per tile in flight: |t_j|^2 * 256 + (j mod 256), INT_MAX for padding
+  int cvec[NCV][TN];               // per unit in flight: |t_j|^2 * 256 + (j mod 128), INT_MAX for padding
   unsigned long long b_full[NSTAGE], b_empty[NSTAGE];
   unsigned long long a_full[2], a_empty[2];
-  unsigned long long t_full[2], t_empty[2];
-  unsigned long long c_full[2];    // column constants of the tile in accumulator tb are visible (see MMA issuer)
+  unsigned long long t_full[QT], t_empty[QT];
+  unsigned long long c_full[QT];   // column constants of the unit in accumulator g are visible (see MMA issuer)
   uint32_t tmem_base;
   int abort_flag;
 };
@@ -162,20 +169,20 @@ __device__ __forceinline__ void chunk_min(const int4* __restrict__ cv, const uin
   }
 }
 
-// the CTA's next run of tiles inside one query tile: tiles [tile, tile + n) of the flattened grid
-struct Seg { int qt, t0, t1; };
-__device__ __forceinline__ Seg next_seg(int tile, int hi, int n_ttiles) {
+// the CTA's next run of units inside one super-row: units [unit, unit + n) of the flattened grid
+struct Seg { int sr, t0, t1; };
+__device__ __forceinline__ Seg next_seg(int unit, int hi, int n_ttiles) {
   Seg g;
-  g.qt = tile / n_ttiles;
-  g.t0 = tile - g.qt * n_ttiles;
-  g.t1 = min(n_ttiles, g.t0 + (hi - tile));
+  g.sr = unit / n_ttiles;
+  g.t0 = unit - g.sr * n_ttiles;
+  g.t1 = min(n_ttiles, g.t0 + (hi - unit));
   return g;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
-                const uint32_t* __restrict__ qn, int nq, const int* __restrict__ tkey, int nt, int n_ttiles,
-                int n_tiles, unsigned long long* __restrict__ best, int* __restrict__ err) {
+                const uint32_t* __restrict__ qn, int nq, const int* __restrict__ tkey, int nt, int n_qtiles, int n_ttiles,
+                int n_units, unsigned long long* __restrict__ best, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the pointer in the shared address space (LDS/STS, not generic loads)
   Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -184,15 +191,16 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; i++) { mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], 1); }
-    for (int i = 0; i < 2; i++) {
-      mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1);
-      mbar_init(&S.t_full[i], 1);   mbar_init(&S.t_empty[i], 128);
+    for (int i = 0; i < 2; i++) { mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1); }
+    for (int i = 0; i < QT; i++) {
+      mbar_init(&S.t_full[i], 1);
+      mbar_init(&S.t_empty[i], 128);   // the four warps of the accumulator's group
       mbar_init(&S.c_full[i], 1);
     }
     S.abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {  // TMEM: all 512 columns (two 128 x 256 s32 accumulators)
+  if (warp == EPI_WARPS + 1) {  // TMEM: all 512 columns (four 128 x 128 s32 accumulators)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
                  "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -202,48 +210,52 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
 
-  // this CTA's run of the flattened tile grid
-  const int lo = (int)((long long)n_tiles * blockIdx.x / gridDim.x);
-  const int hi = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+  // this CTA's run of the flattened (super-row, train tile) grid
+  const int lo = (int)((long long)n_units * blockIdx.x / gridDim.x);
+  const int hi = (int)((long long)n_units * (blockIdx.x + 1) / gridDim.x);
 
-  if (warp < 8) {
-    // ================= epilogue: warpgroup wg drains TMEM accumulator wg =================
-    const uint32_t wg = (uint32_t)warp >> 2;
-    uint32_t tile_ctr = 0;
+  if (warp < EPI_WARPS) {
+    // ================= epilogue: group g = warp >> 2 drains accumulator g (query tile 4 sr + g) =================
+    const int g = warp >> 2;
+    uint32_t unit_ctr = 0;   // units of this CTA so far (column-constant slot)
+    uint32_t use_ctr = 0;    // units in which accumulator g was used (its barriers' phase)
     bool ok = true;
-    for (int tile = lo; tile < hi && ok;) {
-      const Seg sg = next_seg(tile, hi, n_ttiles);
-      tile += sg.t1 - sg.t0;
-      const int qrow = sg.qt * TM + ((int)threadIdx.x & 127);
+    for (int unit = lo; unit < hi && ok;) {
+      const Seg sg = next_seg(unit, hi, n_ttiles);
+      const int n_seg = sg.t1 - sg.t0;
+      unit += n_seg;
+      const int qt = sg.sr * QT + g;
+      if (qt >= n_qtiles) { unit_ctr += (uint32_t)n_seg; continue; }   // this super-row has fewer than QT query tiles
+      const int qrow = qt * TM + ((int)threadIdx.x & 127);
       const int myqn = qrow < nq ? (int)qn[qrow] : 0;
       int best_ssd = 0x7fffffff, best_j = -1;
-      for (int tt = sg.t0; tt < sg.t1 && ok; tt++, tile_ctr++) {
-        const uint32_t tb = tile_ctr & 1u, ph = (tile_ctr >> 1) & 1u;
-        if (tb != wg) continue;   // the other warpgroup's tile
-        const uint32_t cs = tile_ctr % NCV;
-        // c_full: the producer's cvec writes are visible (relayed by the MMA thread, which acquired them
-        // through b_full; both barriers here advance in lockstep with the accumulator, so a waiter can
-        // never fall two phases behind); t_full: the accumulator is complete
-        ok = mbar_wait(&S.c_full[tb], ph, abort_flag) && mbar_wait(&S.t_full[tb], ph, abort_flag);
+      for (int tt = sg.t0; tt < sg.t1 && ok; tt++, unit_ctr++, use_ctr++) {
+        const uint32_t ph = use_ctr & 1u;
+        const uint32_t cs = unit_ctr % NCV;
+        // c_full: the producer's cvec writes are visible (relayed by the MMA thread, which acquired them through
+        // b_full; it advances in lockstep with the accumulator, so a waiter can never fall two phases behind);
+        // t_full: the accumulator is complete
+        ok = mbar_wait(&S.c_full[g], ph, abort_flag) && mbar_wait(&S.t_full[g], ph, abort_flag);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + tb * TN;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * TN);
+        const int4* cv = reinterpret_cast<const int4*>(&S.cvec[cs][0]);
         int km0 = 0x7fffffff, km1 = 0x7fffffff, km2 = 0x7fffffff, km3 = 0x7fffffff;
         // two register buffers: the tcgen05.ld of chunk c + 1 is in flight while chunk c is reduced
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
         tmem_ld_wait();
-#pragma unroll 1
+#pragma unroll
         for (int cb = 0; cb < TN / 32; cb += 2) {
           tmem_ld32(taddr + (cb + 1) * 32, rb);
-          chunk_min(reinterpret_cast<const int4*>(&S.cvec[cs][cb * 32]), ra, km0, km1, km2, km3);
+          chunk_min(cv + cb * 8, ra, km0, km1, km2, km3);
           tmem_ld_wait();
           if (cb + 2 < TN / 32) tmem_ld32(taddr + (cb + 2) * 32, ra);
-          chunk_min(reinterpret_cast<const int4*>(&S.cvec[cs][(cb + 1) * 32]), rb, km0, km1, km2, km3);
+          chunk_min(cv + (cb + 1) * 8, rb, km0, km1, km2, km3);
           tmem_ld_wait();
         }
         tc_fence_before();
-        mbar_arrive(&S.t_empty[tb]);
+        mbar_arrive(&S.t_empty[g]);
         const int kmin = min(min(km0, km1), min(km2, km3));
         const int v = kmin >> 8, jl = kmin & 255;
         const int ssd = v + myqn;
@@ -252,66 +264,78 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (ok && qrow < nq && best_j >= 0 && best_j < nt)
         atomicMin(&best[qrow], ((unsigned long long)(uint32_t)best_ssd << 32) | (uint32_t)best_j);
     }
-  } else if (warp == 8) {
+  } else if (warp == EPI_WARPS) {
     // ================= producer: TMA tile loads + bulk copies of the column constants =================
-    uint32_t tile_ctr = 0, seg_ctr = 0;
+    uint32_t unit_ctr = 0, seg_ctr = 0;
     bool ok = true;
-    for (int tile = lo; tile < hi && ok; seg_ctr++) {
-      const Seg sg = next_seg(tile, hi, n_ttiles);
-      tile += sg.t1 - sg.t0;
+    for (int unit = lo; unit < hi && ok; seg_ctr++) {
+      const Seg sg = next_seg(unit, hi, n_ttiles);
+      unit += sg.t1 - sg.t0;
       const uint32_t ab = seg_ctr & 1u, aph = (seg_ctr >> 1) & 1u;
       ok = mbar_wait(&S.a_empty[ab], aph ^ 1u, abort_flag);
       if (!ok) break;
+      const int nvalid = min(QT, n_qtiles - sg.sr * QT);
       if (lane == 0) {
-        mbar_arrive_expect_tx(&S.a_full[ab], A_BYTES);
-        tma_load_2d(S.A[ab], &tmap_q, 0, sg.qt * TM, &S.a_full[ab]);
+        mbar_arrive_expect_tx(&S.a_full[ab], (uint32_t)nvalid * A_BYTES);
+        for (int q = 0; q < nvalid; q++) tma_load_2d(S.A[ab][q], &tmap_q, 0, (sg.sr * QT + q) * TM, &S.a_full[ab]);
       }
-      for (int tt = sg.t0; tt < sg.t1; tt++, tile_ctr++) {
-        const uint32_t s = tile_ctr % NSTAGE, sph = (tile_ctr / NSTAGE) & 1u;
-        const uint32_t cs = tile_ctr % NCV;
+      for (int tt = sg.t0; tt < sg.t1; tt++, unit_ctr++) {
+        const uint32_t s = unit_ctr % NSTAGE, sph = (unit_ctr / NSTAGE) & 1u;
+        const uint32_t cs = unit_ctr % NCV;
         ok = mbar_wait(&S.b_empty[s], sph ^ 1u, abort_flag);
         if (!ok) break;
-        if (lane == 0) {   // descriptor tile (TMA) + the tile's 256 column constants (bulk copy), one barrier
+        if (lane == 0) {   // descriptor tile (TMA) + the tile's 128 column constants (bulk copy), one barrier
           mbar_arrive_expect_tx(&S.b_full[s], B_BYTES + TN * (uint32_t)sizeof(int));
           tma_load_2d(S.B[s], &tmap_t, 0, tt * TN, &S.b_full[s]);
           bulk_load_1d(S.cvec[cs], tkey + (size_t)tt * TN, TN * (uint32_t)sizeof(int), &S.b_full[s]);
         }
       }
     }
-  } else if (warp == 9 && lane == 0) {
+  } else if (warp == EPI_WARPS + 1 && lane == 0) {
     // ================= MMA issuer (one thread) =================
-    uint32_t tile_ctr = 0, seg_ctr = 0;
+    uint32_t unit_ctr = 0, seg_ctr = 0;
+    uint32_t use_ctr[QT] = {0u, 0u, 0u, 0u};
     bool ok = true;
-    for (int tile = lo; tile < hi && ok; seg_ctr++) {
-      const Seg sg = next_seg(tile, hi, n_ttiles);
-      tile += sg.t1 - sg.t0;
+    for (int unit = lo; unit < hi && ok; seg_ctr++) {
+      const Seg sg = next_seg(unit, hi, n_ttiles);
+      unit += sg.t1 - sg.t0;
       const uint32_t ab = seg_ctr & 1u, aph = (seg_ctr >> 1) & 1u;
       ok = mbar_wait(&S.a_full[ab], aph, abort_flag);
       if (!ok) break;
-      const uint64_t adesc = make_desc(smem_u32(S.A[ab]));
-      for (int tt = sg.t0; tt < sg.t1; tt++, tile_ctr++) {
-        const uint32_t s = tile_ctr % NSTAGE, sph = (tile_ctr / NSTAGE) & 1u;
-        const uint32_t tb = tile_ctr & 1u, tph = (tile_ctr >> 1) & 1u;
-        ok = mbar_wait(&S.b_full[s], sph, abort_flag) && mbar_wait(&S.t_empty[tb], tph ^ 1u, abort_flag);
+      const int nvalid = min(QT, n_qtiles - sg.sr * QT);
+      for (int tt = sg.t0; tt < sg.t1 && ok; tt++, unit_ctr++) {
+        const uint32_t s = unit_ctr % NSTAGE, sph = (unit_ctr / NSTAGE) & 1u;
+        ok = mbar_wait(&S.b_full[s], sph, abort_flag);
         if (!ok) break;
-        mbar_arrive(&S.c_full[tb]);  // release: passes the acquired cvec writes on to the epilogue
-        tc_fence_after();
         const uint64_t bdesc = make_desc(smem_u32(S.B[s]));
-        const uint32_t d_tmem = tmem_base + tb * TN;
 #pragma unroll
-        for (int ks = 0; ks < K_STEPS; ks++)  // 32 bytes of K per MMA: descriptor start advances 32 B
-          mma_i8(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), ks > 0 ? 1u : 0u);
+        for (int q = 0; q < QT; q++) {
+          if (q < nvalid && ok) {
+            ok = mbar_wait(&S.t_empty[q], (use_ctr[q] & 1u) ^ 1u, abort_flag);   // group q has drained the previous unit
+            if (ok) {
+              mbar_arrive(&S.c_full[q]);  // release: passes the acquired cvec writes on to the epilogue
+              tc_fence_after();
+              const uint64_t adesc = make_desc(smem_u32(S.A[ab][q]));
+              const uint32_t d_tmem = tmem_base + (uint32_t)(q * TN);
+#pragma unroll
+              for (int ks = 0; ks < K_STEPS; ks++)  // 32 bytes of K per MMA: descriptor start advances 32 B
+                mma_i8(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), ks > 0 ? 1u : 0u);
+              mma_commit(&S.t_full[q]);   // accumulator q ready for its group
+              use_ctr[q]++;
+            }
+          }
+        }
+        if (!ok) break;
         mma_commit(&S.b_empty[s]);   // smem stage reusable once these MMAs have read it
-        mma_commit(&S.t_full[tb]);   // accumulator ready for the epilogue
       }
-      mma_commit(&S.a_empty[ab]);    // A buffer reusable after the segment's last MMA
+      mma_commit(&S.a_empty[ab]);    // A super-row buffer reusable after the segment's last MMA
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0 && S.abort_flag) atomicOr(err, PANO_ERRW_TC_ABORT);
-  if (warp == 9) {
+  if (warp == EPI_WARPS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
 }
@@ -334,8 +358,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// descriptor matrix [rows][128 B] u8 -> 2-D tensor map, box = 128 bytes x box_rows, 128B swizzle
-void make_tmap(CUtensorMap* map, const void* base, size_t rows, uint32_t box_rows) {
+EncodeTiledFn tmap_encoder() {
   static EncodeTiledFn encode = [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -344,6 +367,12 @@ void make_tmap(CUtensorMap* map, const void* base, size_t rows, uint32_t box_row
       fn = nullptr;
     return (EncodeTiledFn)fn;
   }();
+  return encode;
+}
+
+// descriptor matrix [rows][128 B] u8 -> 2-D tensor map, box = 128 bytes x box_rows, 128B swizzle
+void make_tmap(CUtensorMap* map, const void* base, size_t rows, uint32_t box_rows) {
+  EncodeTiledFn encode = tmap_encoder();
   if (!encode) throw CudaError{cudaErrorNotSupported, "cuTensorMapEncodeTiled unavailable", __FILE__, __LINE__};
   const cuuint64_t dims[2] = {(cuuint64_t)KB, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)KB};
@@ -355,6 +384,23 @@ void make_tmap(CUtensorMap* map, const void* base, size_t rows, uint32_t box_row
   if (r != CUDA_SUCCESS) throw CudaError{cudaErrorInvalidValue, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__};
 }
 }  // namespace
+
+// plain (unswizzled) 2-D byte tensor map over a pitched image: [rows][row_bytes], box = box_bytes x box_rows.
+// Returns false when the layout cannot be described (base or pitch not 16-byte aligned, encoder unavailable).
+bool make_tmap_bytes_2d(void* map_out, const void* base, size_t row_bytes, size_t rows, size_t pitch, uint32_t box_bytes,
+                        uint32_t box_rows) {
+  EncodeTiledFn encode = tmap_encoder();
+  if (!encode || (reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (pitch & 15u) != 0 || row_bytes == 0 || rows == 0)
+    return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  const cuuint32_t box[2] = {box_bytes, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base),
+                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 
 void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t, unsigned long long* best,
                      DevBuf& keybuf, int* errw) {
@@ -373,9 +419,9 @@ void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescript
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
   }();
-  // flattened (query tile, train tile) grid split into equal contiguous runs, one per SM
-  const int n_tiles = n_qtiles * n_ttiles;
-  const int grid = n_tiles < sms ? n_tiles : sms;
+  // flattened (super-row of QT query tiles, train tile) grid split into equal contiguous runs, one per SM
+  const int n_units = ((n_qtiles + QT - 1) / QT) * n_ttiles;
+  const int grid = n_units < sms ? n_units : sms;
   const size_t smem = sizeof(Smem) + 1024;
   static const bool attr_set = [&] {
     PANO_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -388,8 +434,11 @@ void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescript
   make_tmap(&tmap_t, t.desc.p, ((size_t)t.count + 255) / 256 * 256, TN);
   // A CTA whose pipeline wait gives up ORs PANO_ERRW_TC_ABORT into the context's error word; the host sees it
   // with the next result it waits for (every call, not only the first), fails the call and disables this path.
-  match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_t, q.norm.as<uint32_t>(), q.count,
-                                                  tkey, t.count, n_ttiles, n_tiles, best, errw);
+  {
+    ProfScope ps(PROF_MATCH_TC, st);
+    match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_t, q.norm.as<uint32_t>(), q.count,
+                                                    tkey, t.count, n_qtiles, n_ttiles, n_units, best, errw);
+  }
   PANO_LAUNCH_CHECK();
   if (g_tc_state == 0) g_tc_state = 1;
 }

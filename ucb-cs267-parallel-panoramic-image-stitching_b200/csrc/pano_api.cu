@@ -8,11 +8,13 @@
 #include <algorithm>
 #include <exception>
 #include <new>
+#include <future>
 #include <mutex>
 #include <thread>
 
 namespace pano {
 thread_local int t_yield_wait = 0;
+thread_local Prof* t_prof = nullptr;
 // (The library does not touch the process environment.  Batch lanes are independent streams; with the default of 8
 // hardware work queues they alias, so callers that batch should export CUDA_DEVICE_MAX_CONNECTIONS=32 before the
 // CUDA context exists - bench.py and the executables do; see INTEGRATION.md.)
@@ -32,6 +34,7 @@ struct pano_ctx {
   bool owns_stream = true;
   std::string err;
   PinnedBuf pin;
+  Prof prof;     // per-kernel event timing (pano_set_profile)
   DevBuf errw;   // device error word (PANO_ERRW_* bits), read back with every result the host waits for
   DevBuf up[2];  // staging for host images
   // batch lanes with host buffers: the next pair's images are uploaded, and the previous canvas downloaded, on
@@ -53,7 +56,16 @@ struct pano_ctx {
   int cw = 0, ch = 0;
   size_t cstride = 0;
   bool has_canvas = false;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  struct Job {             // the pair between its stage A and its stage B (see pair_stage_a / pair_stage_b)
+    DevImage L, R;
+    int m = 0;
+    bool prelaunched = false;
+  } job;
+  std::vector<pano_ctx*> slots;  // a batch lane's pipeline slots (child contexts): pairs in flight between A and B
+  std::future<int> async_job;    // pano_stitch_pair_async: the pair running on the context's worker
+  cudaEvent_t ev_async = nullptr;
+  void* async_stream = nullptr;
   std::vector<pano_ctx*> lanes;  // child contexts (own stream + scratch) used by pano_stitch_batch
 };
 
@@ -68,6 +80,7 @@ int fail(pano_ctx* c, int code, const std::string& msg) {
 
 #define API_TRY(c)                                  \
   if (!(c)) return PANO_ERR_INVALID;                \
+  t_prof = &(c)->prof;                              \
   try {                                             \
     PANO_CUDA(cudaSetDevice((c)->device));
 
@@ -102,6 +115,18 @@ DevImage to_device(pano_ctx* c, const uint8_t* p, int w, int h, size_t stride, i
   d.p = c->up[slot].as<uint8_t>();
   d.stride = pitch;
   return d;
+}
+
+// 2-D image copy; one flat cudaMemcpyAsync when source and destination rows are contiguous and equally pitched
+// (3840 x 3 = 11520 bytes is already a multiple of the engine's 256-byte pitch), which spares the driver the
+// per-row descriptor work of cudaMemcpy2DAsync on the end-to-end path
+void copy_image_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, int rows,
+                      cudaMemcpyKind kind, cudaStream_t st) {
+  if (dpitch == spitch && rows > 0 && (spitch == row_bytes || rows == 1)) {
+    PANO_CUDA(cudaMemcpyAsync(dst, src, spitch * (size_t)(rows - 1) + row_bytes, kind, st));
+  } else {
+    PANO_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, kind, st));
+  }
 }
 
 const void* upload(pano_ctx* c, DevBuf& buf, const void* p, size_t bytes, int mem) {
@@ -212,19 +237,28 @@ void fill_canvas_info(const CanvasGeom& g, pano_canvas_info* info) {
   memcpy(info->TH, g.TH, sizeof g.TH);
 }
 
-// ref: src/serial/main.cpp:311-391.  left/right are device views.  On success the new
-// canvas is in c->canvas[c->cur].
-int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const pano_harris_opts& ho,
-                       const pano_ransac_opts& ro, pano_pair_result* res, bool homography_only = false) {
+// ref: src/serial/main.cpp:311-391, in two halves so that a batch lane can keep several pairs in flight:
+//   stage A  detection of both images, descriptors, matching - and, as soon as the right image's in-border keypoints
+//            are counted, the shuffle replay on the context's side stream (it depends on nothing but that count);
+//   stage B  joins the replay, solves (DLT, scoring, selection), reads H back, canvas geometry, warp + overlay.
+// A single pair runs A then B back to back (the replay then overlaps the left image's detection and the matching);
+// pano_stitch_batch runs B of an earlier pair after A of a later one, so a slow but cheap replay (the resident,
+// one-CTA formulation) is never waited for.  left/right are device views that must stay valid until B returns.
+// On success the new canvas is in c->canvas[c->cur].
+int pair_stage_a(pano_ctx* c, const DevImage& L, const DevImage& R, const pano_harris_opts& ho,
+                 const pano_ransac_opts& ro, pano_pair_result* res) {
   memset(res, 0, sizeof *res);
   res->best_iteration = -1;
   cudaStream_t st = c->st;
+  c->job.L = L;
+  c->job.R = R;
+  c->job.m = 0;
+  c->job.prelaunched = false;
   PANO_CUDA(cudaEventRecord(c->ev[0], st));
   // 1. corner detection (ref :316-317) and 2. matching: right = query, left = train (ref :320).  The right image
   // goes first: once its in-border keypoints are counted the number of matches M is known (every query keypoint
-  // gets its nearest neighbour; the max-SSD filter is vacuous at the reference's 1e8), and the shuffle replay -
-  // which depends on nothing but M - starts on its own stream underneath the left image's detection and the
-  // matching.  If the filter does remove matches the pre-launched replay is discarded and RANSAC runs in order.
+  // gets its nearest neighbour; the max-SSD filter is vacuous at the reference's 1e8).  If the filter does remove
+  // matches the pre-launched replay is discarded and RANSAC runs in order.
   res->n_kp_right = harris_detect_device(st, R, ho, c->hs, c->kpR, c->pin);
   bool prelaunched = false;
   int nqi = 0;
@@ -247,15 +281,31 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
     PANO_CUDA(cudaStreamWaitEvent(st, c->rs.ev_join, 0));
     prelaunched = false;
   }
+  c->job.m = m;
+  c->job.prelaunched = prelaunched;
+  return PANO_OK;
+}
+
+int pair_stage_b(pano_ctx* c, const pano_harris_opts& ho, const pano_ransac_opts& ro, pano_pair_result* res,
+                 bool homography_only) {
+  (void)ho;
+  cudaStream_t st = c->st;
+  const DevImage& L = c->job.L;
+  const DevImage& R = c->job.R;
+  const int m = c->job.m;
+  PANO_CUDA(cudaEventRecord(c->ev[5], st));
   auto finish = [&](int status) {
     int* ew_slot = reinterpret_cast<int*>(c->pin.as<char>() + 1024);
     PANO_CUDA(cudaMemcpyAsync(ew_slot, c->errw.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     PANO_CUDA(cudaEventRecord(c->ev[4], st));
     PANO_CUDA(cudaEventSynchronize(c->ev[4]));
     if (*ew_slot) status = fail_errw(c, *ew_slot);
+    float ta = 0, tb = 0;
     cudaEventElapsedTime(&res->ms_detect, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&res->ms_match, c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&res->ms_total, c->ev[0], c->ev[4]);
+    cudaEventElapsedTime(&ta, c->ev[0], c->ev[2]);
+    cudaEventElapsedTime(&tb, c->ev[5], c->ev[4]);
+    res->ms_total = ta + tb;     // (a batch lane runs other pairs' stages between A and B: not counted here)
     res->status = status;
     return status;
   };
@@ -264,12 +314,12 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
   c->rs.n1 = c->kpR.count;
   c->rs.n2 = c->kpL.count;
   RansacResult rr = ransac_retry(c, c->kpR.xy.as<int32_t>(), c->kpL.xy.as<int32_t>(), c->matches.as<pano_dmatch>(),
-                                 m, ro, nullptr, nullptr, nullptr, prelaunched);
+                                 m, ro, nullptr, nullptr, nullptr, c->job.prelaunched);
   PANO_CUDA(cudaEventRecord(c->ev[3], st));
   if (rr.errw) rr.status = fail_errw(c, rr.errw);
   if (rr.status != PANO_OK) {
     int s = finish(rr.status);
-    cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&res->ms_ransac, c->ev[5], c->ev[3]);
     return s;
   }
   memcpy(res->H, rr.H, sizeof rr.H);
@@ -281,12 +331,12 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
   fill_canvas_info(g, &res->canvas);
   if (homography_only) {  // chain mode: the canvas is composed later from all homographies
     int s = finish(PANO_OK);
-    cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&res->ms_ransac, c->ev[5], c->ev[3]);
     return s;
   }
   if (!g.ok) {
     int s = finish(PANO_ERR_ROI);
-    cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&res->ms_ransac, c->ev[5], c->ev[3]);
     return s;
   }
   int nxt = 1 - c->cur;
@@ -294,7 +344,7 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
   c->canvas[nxt].reserve(pitch * (size_t)g.ch);
   warp_overlay_device(st, L, R, g, c->canvas[nxt].as<uint8_t>(), pitch);
   if (int s = finish(PANO_OK)) return s;
-  cudaEventElapsedTime(&res->ms_ransac, c->ev[2], c->ev[3]);
+  cudaEventElapsedTime(&res->ms_ransac, c->ev[5], c->ev[3]);
   cudaEventElapsedTime(&res->ms_warp, c->ev[3], c->ev[4]);
   c->cur = nxt;
   c->cw = g.cw;
@@ -302,6 +352,13 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
   c->cstride = pitch;
   c->has_canvas = true;
   return PANO_OK;
+}
+
+int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const pano_harris_opts& ho,
+                       const pano_ransac_opts& ro, pano_pair_result* res, bool homography_only = false) {
+  int s = pair_stage_a(c, L, R, ho, ro, res);
+  if (s != PANO_OK) return s;
+  return pair_stage_b(c, ho, ro, res, homography_only);
 }
 
 }  // namespace
@@ -362,7 +419,12 @@ void pano_destroy(pano_ctx* c) {
   if (!c) return;
   for (pano_ctx* l : c->lanes) pano_destroy(l);
   c->lanes.clear();
+  for (pano_ctx* l : c->slots) pano_destroy(l);
+  c->slots.clear();
+  if (c->async_job.valid()) c->async_job.wait();
   cudaSetDevice(c->device);
+  if (c->ev_async) cudaEventDestroy(c->ev_async);
+  for (auto& r : c->prof.pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->st) cudaStreamSynchronize(c->st);
   if (c->rs.side) { cudaStreamSynchronize(c->rs.side); cudaStreamDestroy(c->rs.side); }
   if (c->rs.ev_fork) cudaEventDestroy(c->rs.ev_fork);
@@ -589,6 +651,51 @@ int pano_stitch_pair(pano_ctx* c, const uint8_t* left, int wl, int hl, size_t st
   API_CATCH(c)
 }
 
+int pano_stitch_pair_async(pano_ctx* c, const uint8_t* left, int wl, int hl, size_t stride_l, const uint8_t* right,
+                           int wr, int hr, size_t stride_r, int mem, const pano_harris_opts* hopts,
+                           const pano_ransac_opts* ropts, void* stream, pano_pair_result* res) {
+  API_TRY(c)
+  if (c->async_job.valid()) return PANO_ERR_BUSY;
+  if (!valid_image(left, wl, hl, stride_l) || !valid_image(right, wr, hr, stride_r) || !hopts || !ropts || !res)
+    return fail(c, PANO_ERR_INVALID, "pano_stitch_pair_async: bad argument");
+  if (int e = check_harris(*hopts)) return fail(c, e, "pano_stitch_pair_async: unsupported option");
+  if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
+  if (!c->ev_async) PANO_CUDA(cudaEventCreateWithFlags(&c->ev_async, cudaEventDisableTiming));
+  c->async_stream = stream;
+  if (stream) {   // the pair starts after what the caller has enqueued on its stream
+    PANO_CUDA(cudaEventRecord(c->ev_async, (cudaStream_t)stream));
+    PANO_CUDA(cudaStreamWaitEvent(c->st, c->ev_async, 0));
+  }
+  const pano_harris_opts ho = *hopts;
+  const pano_ransac_opts ro = *ropts;
+  c->async_job = std::async(std::launch::async, [=]() -> int {
+    return pano_stitch_pair(c, left, wl, hl, stride_l, right, wr, hr, stride_r, mem, &ho, &ro, res);
+  });
+  return PANO_OK;
+  API_CATCH(c)
+}
+
+static int async_finish(pano_ctx* c) {
+  const int s = c->async_job.get();
+  if (c->async_stream) {   // later work on the caller's stream is ordered after the pair (its kernels have completed)
+    cudaSetDevice(c->device);
+    cudaEventRecord(c->ev_async, c->st);
+    cudaStreamWaitEvent((cudaStream_t)c->async_stream, c->ev_async, 0);
+  }
+  return s;
+}
+
+int pano_pair_query(pano_ctx* c) {
+  if (!c || !c->async_job.valid()) return PANO_ERR_INVALID;
+  if (c->async_job.wait_for(std::chrono::seconds(0)) != std::future_status::ready) return PANO_ERR_BUSY;
+  return async_finish(c);
+}
+
+int pano_pair_wait(pano_ctx* c) {
+  if (!c || !c->async_job.valid()) return PANO_ERR_INVALID;
+  return async_finish(c);
+}
+
 int pano_canvas_device(pano_ctx* c, const uint8_t** ptr, size_t* stride, int* w, int* h) {
   if (!c || !c->has_canvas) return PANO_ERR_INVALID;
   if (ptr) *ptr = c->canvas[c->cur].as<uint8_t>();
@@ -650,6 +757,24 @@ int pano_stitch_fold(pano_ctx* c, const uint8_t* const* images, const int* ws, c
   PANO_CUDA(stream_wait(c->st));
   return PANO_OK;
   API_CATCH(c)
+}
+
+int pano_set_profile(pano_ctx* c, int on) {
+  if (!c) return PANO_ERR_INVALID;
+  c->prof.on = on != 0;
+  c->prof.used = 0;
+  for (int i = 0; i < PROF_N; i++) { c->prof.ms[i] = 0; c->prof.n[i] = 0; }
+  return PANO_OK;
+}
+
+int pano_get_profile(pano_ctx* c, double* ms_out, int* count_out, int cap) {
+  if (!c || !ms_out || !count_out) return PANO_ERR_INVALID;
+  cudaSetDevice(c->device);
+  if (c->st) cudaStreamSynchronize(c->st);
+  if (c->rs.side) cudaStreamSynchronize(c->rs.side);
+  prof_collect(c->prof);
+  for (int i = 0; i < cap && i < PROF_N; i++) { ms_out[i] = c->prof.ms[i]; count_out[i] = c->prof.n[i]; }
+  return PROF_N;
 }
 
 void* pano_stream(pano_ctx* c) { return c ? (void*)c->st : nullptr; }
@@ -751,7 +876,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
   // scratch and host thread) so that one pair's host synchronisations, copies and low-occupancy
   // kernels overlap with another pair's work.  PANO_BATCH_LANES (default 16, 1 = sequential); lanes beyond the
   // host cores poll-and-sleep instead of spinning inside the driver (t_yield_wait, set per lane thread).
-  int n_lanes = 16;
+  int n_lanes = 8;
   if (const char* e = getenv("PANO_BATCH_LANES")) n_lanes = atoi(e);
   if (n_lanes < 1) n_lanes = 1;
   if (n_lanes > 32) n_lanes = 32;
@@ -772,6 +897,12 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
     if (s != PANO_OK) return fail(c, s, "pano_stitch_batch: cannot create a lane context");
     c->lanes.push_back(l);
   }
+  // one mt19937 output stream for all slots: long enough for shuffles of up to 16 384 matches (longer ones make the
+  // slot generate its own)
+  if (ropts->num_iterations > 0) {
+    const uint64_t steps_cap = 8192;
+    mt_ensure(c->st, c->mt, c->seed, (uint64_t)ropts->num_iterations * (steps_cap + steps_cap / 32 + 256) + 65536, steps_cap + 4096);
+  }
   cudaEvent_t e0, e1;
   PANO_CUDA(cudaEventCreate(&e0));
   PANO_CUDA(cudaEventCreate(&e1));
@@ -779,84 +910,119 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
   PANO_CUDA(cudaEventRecord(e0, c->st));
   std::vector<int> lane_rc((size_t)n_lanes, PANO_OK);
   std::vector<std::string> lane_err((size_t)n_lanes);   // merged into c->err after the join (no shared writes)
+  // A lane is a software pipeline over N_SLOTS child contexts: stage A (detect, match, replay launched on the
+  // slot's side stream) of pair k, then stage B (solve, warp, download) of pair k - DEPTH.  With the resident
+  // replay (one CTA, ~20x less work than the chunked one but milliseconds long) nobody waits for a replay: it
+  // finishes while the lane's next DEPTH pairs go through stage A.  The upload of pair k + 1 is enqueued before
+  // stage A of pair k, so N_SLOTS = DEPTH + 2 slots are in use.
+  static const int DEPTH = [] { const char* e = getenv("PANO_BATCH_DEPTH"); int v = e ? atoi(e) : 2; return v < 0 ? 0 : (v > 6 ? 6 : v); }();
+  const int N_SLOTS = DEPTH + 2;
+  const bool host_io = mem != PANO_MEM_DEVICE;
+  std::mutex down_order;
+  if (host_io && !c->st_up) {
+    // ONE upload and ONE download stream per context: the copy engines serialise transfers anyway, and every extra
+    // stream costs one of the (at most 32) hardware work queues that the slots' compute streams need
+    PANO_CUDA(cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking));
+    PANO_CUDA(cudaStreamCreateWithFlags(&c->st_down, cudaStreamNonBlocking));
+  }
   auto work = [&](int li) {
     pano_ctx* l = c->lanes[li];
     t_yield_wait = yield_wait ? 1 : 0;
-    l->seed = c->seed;
-    l->matcher = c->matcher;
-    l->replay_target = n_lanes > 1 ? 4000.0 : 0.0;   // small chunks: least speculative work (19.9 k vs 17.8 k MP/s at 16000)
-    l->overlap_replay = false;   // (throughput mode overlaps across pairs; a second stream per lane only adds queue aliasing)
-    l->replay_mode = c->replay_mode;   // (resident = 1 pays off from ~32 lanes on: it trades latency for GPU time)
     try {
       PANO_CUDA(cudaSetDevice(l->device));
-      const bool host_io = mem != PANO_MEM_DEVICE;
-      if (host_io && !l->st_up) {
-        PANO_CUDA(cudaStreamCreateWithFlags(&l->st_up, cudaStreamNonBlocking));
-        PANO_CUDA(cudaStreamCreateWithFlags(&l->st_down, cudaStreamNonBlocking));
-        for (int q = 0; q < 2; q++) {
-          PANO_CUDA(cudaEventCreateWithFlags(&l->ev_up[q], cudaEventDisableTiming));
-          PANO_CUDA(cudaEventCreateWithFlags(&l->ev_down[q], cudaEventDisableTiming));
+      while ((int)l->slots.size() < N_SLOTS) {
+        pano_ctx* sl = nullptr;
+        if (pano_create(c->device, c->seed, &sl) != PANO_OK) throw CudaError{cudaErrorMemoryAllocation, "slot context", __FILE__, __LINE__};
+        l->slots.push_back(sl);
+      }
+      for (int q = 0; q < N_SLOTS; q++) {
+        pano_ctx* sl = l->slots[q];
+        sl->seed = c->seed;
+        sl->matcher = c->matcher;
+        sl->rs.shared_mt = &c->mt;
+        // replay: resident (mode 1) unless the caller forces the chunked one with PANO_BATCH_REPLAY=0; chunked replays
+        // use small chunks (least speculative work) and are not pre-launched when nothing can overlap them
+        static const int batch_replay = [] { const char* e = getenv("PANO_BATCH_REPLAY"); return e ? atoi(e) : 1; }();
+        sl->replay_mode = (DEPTH > 0 && n_lanes > 1) ? batch_replay : c->replay_mode;
+        sl->replay_target = n_lanes > 1 ? 4000.0 : 0.0;
+        sl->overlap_replay = DEPTH > 0;
+        if (host_io && !sl->ev_up[0]) {
+          PANO_CUDA(cudaEventCreateWithFlags(&sl->ev_up[0], cudaEventDisableTiming));
+          PANO_CUDA(cudaEventCreateWithFlags(&sl->ev_down[0], cudaEventDisableTiming));
         }
       }
-      DevImage Lq[2], Rq[2];
-      // both images of pair i -> upload slot q, on the lane's upload stream
-      auto enqueue_upload = [&](int i, int q) {
+      const int n_mine = li < n ? (n - li + n_lanes - 1) / n_lanes : 0;      // pairs li, li + n_lanes, ...
+      std::vector<DevImage> Ls((size_t)N_SLOTS), Rs((size_t)N_SLOTS);
+      std::vector<char> down_pending((size_t)N_SLOTS, 0);
+      // both images of pair i -> the slot's upload buffers, on the slot's upload stream
+      auto enqueue_upload = [&](int k) {
+        const int i = li + k * n_lanes, q = k % N_SLOTS;
+        pano_ctx* sl = l->slots[q];
         const size_t pl = align_up((size_t)wl * 3, 256), pr = align_up((size_t)wr * 3, 256);
-        l->upq[q][0].reserve(pl * hl);
-        l->upq[q][1].reserve(pr * hr);
+        sl->upq[0][0].reserve(pl * hl);
+        sl->upq[0][1].reserve(pr * hr);
         {
           // a pair needs both images: keep its two uploads adjacent in the copy engine's queue, otherwise the
           // lanes' copies interleave (all lefts, then all rights) and no lane can start until most have landed
           static std::mutex upload_order;
           std::lock_guard<std::mutex> lk(upload_order);
-          PANO_CUDA(cudaMemcpy2DAsync(l->upq[q][0].p, pl, lefts[i], stride_l, (size_t)wl * 3, hl, cudaMemcpyHostToDevice, l->st_up));
-          PANO_CUDA(cudaMemcpy2DAsync(l->upq[q][1].p, pr, rights[i], stride_r, (size_t)wr * 3, hr, cudaMemcpyHostToDevice, l->st_up));
+          copy_image_async(sl->upq[0][0].p, pl, lefts[i], stride_l, (size_t)wl * 3, hl, cudaMemcpyHostToDevice, c->st_up);
+          copy_image_async(sl->upq[0][1].p, pr, rights[i], stride_r, (size_t)wr * 3, hr, cudaMemcpyHostToDevice, c->st_up);
+          PANO_CUDA(cudaEventRecord(sl->ev_up[0], c->st_up));
         }
-        PANO_CUDA(cudaEventRecord(l->ev_up[q], l->st_up));
-        Lq[q].p = l->upq[q][0].as<uint8_t>(); Lq[q].w = wl; Lq[q].h = hl; Lq[q].stride = pl;
-        Rq[q].p = l->upq[q][1].as<uint8_t>(); Rq[q].w = wr; Rq[q].h = hr; Rq[q].stride = pr;
+        Ls[q].p = sl->upq[0][0].as<uint8_t>(); Ls[q].w = wl; Ls[q].h = hl; Ls[q].stride = pl;
+        Rs[q].p = sl->upq[0][1].as<uint8_t>(); Rs[q].w = wr; Rs[q].h = hr; Rs[q].stride = pr;
       };
-      if (host_io && li < n) enqueue_upload(li, 0);
-      int k = 0;   // pairs done by this lane
-      for (int i = li; i < n; i += n_lanes, k++) {
-        DevImage L, R;
-        if (host_io) {
-          const int q = k & 1;
-          // prefetch the lane's next pair into the other slot (its last user has finished: stitch_pair_device
-          // returns after the pair's last kernel)
-          if (i + n_lanes < n) enqueue_upload(i + n_lanes, q ^ 1);
-          PANO_CUDA(cudaStreamWaitEvent(l->st, l->ev_up[q], 0));
-          // this pair overwrites the canvas buffer that the download of pair k - 2 read
-          if (k >= 2 && canvases_out) PANO_CUDA(cudaStreamWaitEvent(l->st, l->ev_down[q], 0));
-          L = Lq[q]; R = Rq[q];
-        } else {
-          L = to_device(l, lefts[i], wl, hl, stride_l, mem, 0);
-          R = to_device(l, rights[i], wr, hr, stride_r, mem, 1);
-        }
-        int s = stitch_pair_device(l, L, R, *hopts, *ropts, &results[i]);
-        if (s == PANO_ERR_CUDA) { lane_rc[li] = s; lane_err[li] = l->err; t_yield_wait = 0; return; }
+      auto stage_b = [&](int k) -> bool {
+        const int i = li + k * n_lanes, q = k % N_SLOTS;
+        pano_ctx* sl = l->slots[q];
+        // this pair overwrites the canvas buffer that the download of the slot's previous pair read
+        if (host_io && down_pending[q]) PANO_CUDA(cudaStreamWaitEvent(sl->st, sl->ev_down[0], 0));
+        int s = pair_stage_b(sl, *hopts, *ropts, &results[i], false);
+        if (s == PANO_ERR_CUDA) { lane_rc[li] = s; lane_err[li] = sl->err; return false; }
         if (s == PANO_OK && canvases_out && canvases_out[i]) {
-          size_t row = (size_t)l->cw * 3;
-          if (row * (size_t)l->ch > canvas_cap_bytes) {
+          const size_t row = (size_t)sl->cw * 3;
+          if (row * (size_t)sl->ch > canvas_cap_bytes) {
             results[i].status = PANO_ERR_CAPACITY;
           } else if (host_io) {
             // (the pair's kernels have completed: no dependency to express)
-            PANO_CUDA(cudaMemcpy2DAsync(canvases_out[i], row, l->canvas[l->cur].p, l->cstride, row, l->ch,
-                                        cudaMemcpyDeviceToHost, l->st_down));
-            PANO_CUDA(cudaEventRecord(l->ev_down[k & 1], l->st_down));
+            // one download stream for the whole context: copies have no dependencies (the pair's kernels have
+            // completed), the D2H engine takes them in submission order
+            std::lock_guard<std::mutex> lk(down_order);
+            copy_image_async(canvases_out[i], row, sl->canvas[sl->cur].p, sl->cstride, row, sl->ch, cudaMemcpyDeviceToHost,
+                             c->st_down);
+            PANO_CUDA(cudaEventRecord(sl->ev_down[0], c->st_down));
+            down_pending[q] = 1;
           } else {
-            PANO_CUDA(cudaMemcpy2DAsync(canvases_out[i], row, l->canvas[l->cur].p, l->cstride, row, l->ch,
-                                        cudaMemcpyDeviceToDevice, l->st));
+            copy_image_async(canvases_out[i], row, sl->canvas[sl->cur].p, sl->cstride, row, sl->ch, cudaMemcpyDeviceToDevice,
+                             sl->st);
           }
-        } else if (host_io && canvases_out) {
-          PANO_CUDA(cudaEventRecord(l->ev_down[k & 1], l->st_down));   // keep the event chain defined
         }
+        return true;
+      };
+      if (host_io && n_mine > 0) enqueue_upload(0);
+      bool ok = true;
+      for (int k = 0; k < n_mine && ok; k++) {
+        const int i = li + k * n_lanes, q = k % N_SLOTS;
+        pano_ctx* sl = l->slots[q];
+        if (host_io) {
+          if (k + 1 < n_mine) enqueue_upload(k + 1);     // slot (k + 1) % N_SLOTS: its stage B (pair k + 1 - N_SLOTS) is done
+          PANO_CUDA(cudaStreamWaitEvent(sl->st, sl->ev_up[0], 0));
+        } else {
+          Ls[q] = to_device(sl, lefts[i], wl, hl, stride_l, mem, 0);
+          Rs[q] = to_device(sl, rights[i], wr, hr, stride_r, mem, 1);
+        }
+        int s = pair_stage_a(sl, Ls[q], Rs[q], *hopts, *ropts, &results[i]);
+        if (s == PANO_ERR_CUDA) { lane_rc[li] = s; lane_err[li] = sl->err; ok = false; break; }
+        if (k >= DEPTH) ok = stage_b(k - DEPTH);
       }
-      if (host_io) {
-        PANO_CUDA(stream_wait(l->st_up));
-        PANO_CUDA(stream_wait(l->st_down));
+      for (int k = std::max(0, n_mine - DEPTH); k < n_mine && ok; k++) ok = stage_b(k);
+      for (int q = 0; q < N_SLOTS; q++) {
+        pano_ctx* sl = l->slots[q];
+        if (sl->rs.side) PANO_CUDA(stream_wait(sl->rs.side));
+        PANO_CUDA(stream_wait(sl->st));
+        if (host_io && down_pending[q]) PANO_CUDA(cudaEventSynchronize(sl->ev_down[0]));
       }
-      PANO_CUDA(stream_wait(l->st));
     } catch (const CudaError& e) {
       char buf[512];
       snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e.e, cudaGetErrorString(e.e), e.file, e.line,

@@ -976,7 +976,12 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
 
   // ---- stream: everything the walks can touch, with margin ---------------------------------
   uint64_t need = plan.stream_need;
-  if (do_replay) mt_ensure(st, mt, seed, need, (uint64_t)steps + 4096);
+  MtStream* mtp = &mt;
+  if (s.shared_mt && s.shared_mt->valid && s.shared_mt->seed == seed && s.shared_mt->len >= need &&
+      s.shared_mt->guard >= (uint64_t)steps + 4096)
+    mtp = const_cast<MtStream*>(s.shared_mt);   // (never modified through this pointer)
+  else if (do_replay)
+    mt_ensure(st, mt, seed, need, (uint64_t)steps + 4096);
 
   // ---- buffers ---------------------------------------------------------------------------
   const int nseg = (int)((steps + PANO_SEG_STEPS - 1) / PANO_SEG_STEPS);
@@ -1022,6 +1027,7 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
     PANO_LAUNCH_CHECK();
   }
 
+  ProfScope* prep = do_replay ? new ProfScope(PROF_REPLAY, st) : nullptr;
   if (!do_replay) {
     // (samples were produced by an earlier phase-1 call)
   } else if (resident) {
@@ -1031,8 +1037,8 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
     PANO_CUDA(cudaMemcpyAsync(blk_dev, rplan.blk.data(), sizeof(ResBlock) * rplan.nkb, cudaMemcpyHostToDevice, st));
     PANO_CUDA(cudaMemcpyAsync(eoff_dev, rplan.seg_eoff.data(), sizeof(uint32_t) * (rplan.nseg + 1), cudaMemcpyHostToDevice, st));
     ResParams rp;
-    rp.X = mt.x.as<uint32_t>();
-    rp.x_limit = mt.len + mt.guard;
+    rp.X = mtp->x.as<uint32_t>();
+    rp.x_limit = mtp->len + mtp->guard;
     rp.rt = s.thr.as<RT>();
     rp.blk = blk_dev;
     rp.seg_eoff = eoff_dev;
@@ -1051,12 +1057,12 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
       dim3 grid((max_w + RW_THREADS - 1) / RW_THREADS, Gc);
       {
         long long warps = (long long)Gc * nkb;
-        launch_pdl(replay_cells_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, st, mt.x.as<uint32_t>(), steps,
-                   s.thr.as<RT>(), s.plan.as<WinEntry>(), Gc, nkb, plan.dextra, ctl, bits, mt.len + mt.guard - 64);
+        launch_pdl(replay_cells_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, st, mtp->x.as<uint32_t>(), steps,
+                   s.thr.as<RT>(), s.plan.as<WinEntry>(), Gc, nkb, plan.dextra, ctl, bits, mtp->len + mtp->guard - 64);
         PANO_LAUNCH_CHECK();
       }
       launch_pdl(replay_walk_bits_kernel, grid, dim3(RW_THREADS), 0, st, steps, s.plan.as<WinEntry>(), nkb, plan.dextra,
-                 ctl, bits, cand_end, seg_off, (int)n_cand, mt.len);
+                 ctl, bits, cand_end, seg_off, (int)n_cand, mtp->len);
       PANO_LAUNCH_CHECK();
       launch_pdl(replay_chain_kernel, dim3(1), dim3(1024), chain_smem, st, s.plan.as<WinEntry>(), Gc, steps, cand_end,
                  seg_off, (int)n_cand, nseg, ctl, seg_tab + (size_t)c * G * nseg);
@@ -1065,10 +1071,10 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
     {
       int nthr = iters * nseg;
       if (pairs)
-        launch_pdl(replay_segments_kernel<true>, dim3((nthr + 63) / 64), dim3(64), 0, st, mt.x.as<uint32_t>(), n, steps,
+        launch_pdl(replay_segments_kernel<true>, dim3((nthr + 63) / 64), dim3(64), 0, st, mtp->x.as<uint32_t>(), n, steps,
                    s.thr.as<RT>(), seg_tab, iters, nseg, ctl, seg_w);
       else
-        launch_pdl(replay_segments_kernel<false>, dim3((nthr + 63) / 64), dim3(64), 0, st, mt.x.as<uint32_t>(), n, steps,
+        launch_pdl(replay_segments_kernel<false>, dim3((nthr + 63) / 64), dim3(64), 0, st, mtp->x.as<uint32_t>(), n, steps,
                    s.thr.as<RT>(), seg_tab, iters, nseg, ctl, seg_w);
       PANO_LAUNCH_CHECK();
       launch_pdl(combine_samples_kernel, dim3((iters + 127) / 128), dim3(128), 0, st, seg_w, iters, nseg, samples_dev);
@@ -1076,15 +1082,22 @@ RansacResult ransac_device(cudaStream_t st, const int32_t* kp1_dev, const int32_
     }
   }
 
+  delete prep;
   if (!do_solve) {
     res.status = PANO_OK;
     return res;
   }
+  {
+    ProfScope ps(PROF_DLT, st);
   launch_pdl(dlt_kernel, dim3((iters + DLT_WARPS - 1) / DLT_WARPS), dim3(DLT_WARPS * 32), 0, st, s.pts.as<float4>(),
              s.samples.as<int4>(), iters, s.Hs.as<double>(), s.valid.as<int>());
+  }
   PANO_LAUNCH_CHECK();
+  {
+    ProfScope ps(PROF_SCORE, st);
   launch_pdl(score_kernel, dim3(iters), dim3(256), 0, st, s.pts.as<float4>(), m, s.Hs.as<double>(), s.valid.as<int>(),
              inlier_d2_limit(o.distance_threshold), s.counts.as<int>());
+  }
   PANO_LAUNCH_CHECK();
   select_kernel<<<1, 1024, 0, st>>>(s.counts.as<int>(), iters, s.Hs.as<double>(), s.result.as<SelectOut>());
   PANO_LAUNCH_CHECK();

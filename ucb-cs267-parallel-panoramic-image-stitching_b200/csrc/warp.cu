@@ -518,6 +518,7 @@ void warp_overlay_device(cudaStream_t st, const DevImage& left, const DevImage& 
   P.y0 = 0;
   P.src_bytes = (size_t)(right.h - 1) * right.stride + (size_t)right.w * 3;
   const bool box = footprint_box(g.TH, g.Minv, right.w, right.h, g.cw, g.ch, P);
+  ProfScope ps(PROF_WARP, st);
   if (fast_path_ok(P, right.p, right.stride, box) && warp_fast_enabled()) {
     launch_fast<1>(st, left.p, left.stride, right.p, right.stride, P, canvas, canvas_stride);
   } else {

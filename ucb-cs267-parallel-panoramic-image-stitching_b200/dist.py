@@ -5,6 +5,8 @@ no data crosses GPUs on the data path.  The only exchange is the all-gather of t
 results (3x3 homography, status, inlier count: 96 bytes per pair) so that every rank ends up with
 every homography — NCCL over NVLink on GPUs, gloo in the CPU tests.
 """
+import os
+
 import numpy as np
 
 RECORD = 12  # H[0..8], status, inliers, pair index
@@ -57,13 +59,54 @@ def band_rows(canvas_h, rank, world):
     return y0, base + (1 if rank < rem else 0)
 
 
+class SharedCanvas:
+    """A host canvas shared by all ranks of one node ("output bands are written straight to a pinned
+    host canvas; no NCCL bulk transfer").  POSIX shared memory under /dev/shm, created by rank 0, mapped by every
+    rank and - when a CUDA runtime is around - page-locked with cudaHostRegister so that a band's device -> host
+    copy lands in it directly.  Kept and reused across calls while it is large enough."""
+    _cache = {}
+
+    def __init__(self, nbytes, group=None):
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        cap = max(int(nbytes * 1.25), 1 << 20)
+        seq = SharedCanvas._cache.get("seq", 0) + 1
+        SharedCanvas._cache["seq"] = seq
+        self.path = "/dev/shm/pano_canvas_%s_%d" % (os.environ.get("MASTER_PORT", "0"), seq)
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(cap)
+        dist.barrier(group=group)
+        self.buf = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(cap,))
+        dist.barrier(group=group)
+        if rank == 0:
+            os.unlink(self.path)          # the mappings keep it alive
+        self.cap = cap
+        self.registered = False
+        try:
+            import torch
+            if torch.cuda.is_available():
+                rc = torch.cuda.cudart().cudaHostRegister(self.buf.ctypes.data, cap, 0)
+                self.registered = int(rc) == 0
+        except Exception:
+            self.registered = False
+
+    @classmethod
+    def get(cls, nbytes, group=None):
+        c = cls._cache.get(id(group))
+        if c is None or c.cap < nbytes:
+            c = cls(nbytes, group)
+            cls._cache[id(group)] = c
+        return c
+
+
 def stitch_chain_distributed(engine, images, device=None, group=None):
     """Chain-mode panorama over all ranks of the process group (SURVEY 8e2 + 8e3): adjacent pair
-    (i, i+1) is estimated on rank i mod W, the 96-byte records are all-gathered, every rank composes
-    the same H(0 <- i) and canvas geometry, renders its own band of canvas rows, and the bands are
-    gathered.  Every rank holds all input images (they come from the host).  Returns the panorama
-    (on every rank) or None, plus the gathered per-pair records."""
-    import torch
+    (i, i+1) is estimated on rank i mod W, the 96-byte records are all-gathered (the only collective), every
+    rank composes the same H(0 <- i) and canvas geometry and renders its own band of canvas rows straight into
+    a host canvas shared by the ranks of the node.  Every rank holds all input images (they come from the
+    host).  Returns the panorama (a view of the shared canvas, the same memory on every rank; copy it if it
+    has to outlive the next call) or None, plus the gathered per-pair records."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n_pairs = len(images) - 1
@@ -77,18 +120,10 @@ def stitch_chain_distributed(engine, images, device=None, group=None):
     if not ok:
         return None, allr
     cw, ch = geom[0], geom[1]
+    shared = SharedCanvas.get(ch * cw * 3, group)
+    canvas = shared.buf[:ch * cw * 3].reshape(ch, cw, 3)
     y0, bh = band_rows(ch, rank, world)
-    band = engine.renderChainBand(images, Hs, geom, T, y0, bh) if bh > 0 else np.zeros((0, cw, 3), np.uint8)
-    # gather the bands (padded to the tallest band)
-    maxh = (ch + world - 1) // world
-    buf = torch.zeros((maxh, cw, 3), dtype=torch.uint8)
-    buf[:bh] = torch.from_numpy(band)
-    if device is not None:
-        buf = buf.to(device)
-    parts = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(parts, buf, group=group)
-    rows = []
-    for r in range(world):
-        _, h_r = band_rows(ch, r, world)
-        rows.append(parts[r][:h_r].cpu().numpy())
-    return np.concatenate(rows, axis=0), allr
+    if bh > 0:
+        engine.renderChainBand(images, Hs, geom, T, y0, bh, out=canvas[y0:y0 + bh])
+    dist.barrier(group=group)            # every band has landed
+    return canvas, allr

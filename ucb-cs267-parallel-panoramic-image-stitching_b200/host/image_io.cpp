@@ -1,6 +1,8 @@
 // image_io.cpp — see image_io.hpp
 #include "image_io.hpp"
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <cctype>
 #include <cstdio>
@@ -290,6 +292,32 @@ bool write_jpeg_device(const std::string& path, const uint8_t* dev, int w, int h
 }
 #endif
 
+// JPEG (and anything else OpenCV reads) through the Python cv2 wheel when OpenCV C++ is absent: the pixels are then
+// exactly what the reference's cv::imread produces (same libjpeg-turbo build family), which nvJPEG's decoder does not
+// guarantee (tests/test_cli.py reports the per-pixel difference).  The helper converts to a binary PPM in a temporary
+// file.  PANO_JPEG=nvjpeg skips it (fast path, decode on the GPU); PANO_PYTHON overrides the interpreter.
+Image read_via_cv2_helper(const std::string& path) {
+  const char* py = getenv("PANO_PYTHON");
+  char tmpl[] = "/tmp/pano_imread_XXXXXX";
+  int fd = mkstemp(tmpl);
+  if (fd < 0) return Image();
+  close(fd);
+  std::string out = tmpl;
+  std::string q;                       // shell-quote the path
+  for (char ch : path) { if (ch == '\'') q += "'\\''"; else q += ch; }
+  std::string cmd = std::string(py ? py : "python3") +
+      " -c \"import sys,cv2; im=cv2.imread(sys.argv[1]); sys.exit(1) if im is None else None; "
+      "open(sys.argv[2],'wb').write(b'P6\\n%d %d\\n255\\n' % (im.shape[1], im.shape[0]) + im[:, :, ::-1].tobytes())\" '" +
+      q + "' '" + out + "' 2>/dev/null";
+  Image im;
+  if (system(cmd.c_str()) == 0) {
+    std::vector<uint8_t> d = slurp(out);
+    if (d.size() > 4 && d[0] == 'P' && d[1] == '6') im = read_pnm(d);
+  }
+  unlink(out.c_str());
+  return im;
+}
+
 }  // namespace
 
 Image read_image(const std::string& path) {
@@ -309,9 +337,17 @@ Image read_image(const std::string& path) {
 #ifdef PANO_WITH_ZLIB
   if (d[0] == 0x89 && d[1] == 'P') return read_png(d);
 #endif
+  if (d[0] == 0xff && d[1] == 0xd8) {
+    const char* mode = getenv("PANO_JPEG");
+    const bool want_nvjpeg = mode && std::string(mode) == "nvjpeg";
+    if (!want_nvjpeg) {
+      Image im = read_via_cv2_helper(path);   // the reference's decoder (cv2.imread), pixel for pixel
+      if (!im.empty()) return im;
+    }
 #ifdef PANO_WITH_NVJPEG
-  if (d[0] == 0xff && d[1] == 0xd8) return read_jpeg(d);
+    return read_jpeg(d);
 #endif
+  }
   return Image();
 #endif
 }

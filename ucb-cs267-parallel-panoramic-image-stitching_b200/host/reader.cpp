@@ -50,6 +50,10 @@ ImageReaderResult readImagesFromArgs(int argc, char** argv) {
       std::cerr << "Warning: Unable to open image file: " << fileName << std::endl;
       continue;
     }
+    if (const char* dump = std::getenv("PANO_DUMP_DECODED")) {   // test hook: the pixels the pipeline will see
+      const std::string out = std::string(dump) + "/decoded_" + std::to_string(result.images.size()) + ".ppm";
+      pano_io::write_image(out, img.bgr.data(), img.w, img.h, img.stride());
+    }
     result.images.push_back(std::move(img));
   }
   return result;

@@ -114,3 +114,60 @@ def make_strip(n=8, w=2000, h=1500, seed=267, stride_frac=0.6, rot_deg=0.2, nois
             v = v + rng.integers(-noise, noise + 1, v.shape)
         views.append(np.ascontiguousarray(np.clip(np.rint(v), 0, 255).astype(np.uint8)))
     return views
+
+
+# ----------------------------------------------------------------------------------------------------
+# The same generator with the heavy steps (upsampling, rectangle painting, bilinear resampling) on a torch
+# device: bench.py needs hundreds of distinct 4K pairs (BASELINE config 5: 256 pairs, seeds 1000..1255) and
+# the numpy version takes seconds per pair.  All random parameters come from the same numpy PCG64 draws as
+# make_world / make_pair, so a seed describes the same scene; pixel values can differ from the numpy version
+# in the last bit (float32 evaluation order), which is why fixtures and tests keep using make_pair.
+# ----------------------------------------------------------------------------------------------------
+def make_pair_torch(w=3840, h=2160, seed=267, overlap=0.5, rot_deg=0.3, persp=1e-6, noise=2, device="cuda"):
+    """Returns (left, right) uint8 torch tensors [h, w, 3] on `device` and H_true (numpy)."""
+    import torch
+    import torch.nn.functional as F
+    margin = max(16, h // 18)
+    shift = int(round(w * (1.0 - overlap)))
+    wh, ww = h + 2 * margin, w + shift + 2 * margin
+    rng = np.random.Generator(np.random.PCG64(seed))
+    img = torch.full((3, wh, ww), 96.0, dtype=torch.float32, device=device)
+    for s, amp in ((128, 40.0), (48, 24.0), (16, 10.0)):
+        g = rng.uniform(-1, 1, (wh // s + 3, ww // s + 3, 3)).astype(np.float32)
+        gt = torch.from_numpy(g).to(device).permute(2, 0, 1)[None]
+        # same sampling positions as _interp_matrix: linspace(0, n_in - 1.001, n_out)
+        ys = torch.linspace(0, g.shape[0] - 1.001, wh, device=device) / (g.shape[0] - 1) * 2 - 1
+        xs = torch.linspace(0, g.shape[1] - 1.001, ww, device=device) / (g.shape[1] - 1) * 2 - 1
+        grid = torch.stack(torch.meshgrid(xs, ys, indexing="xy"), -1)[None]
+        img += amp * F.grid_sample(gt, grid, mode="bilinear", align_corners=True)[0]
+    n_rect = int(wh * ww / 2600)
+    xs = rng.integers(0, ww, n_rect); ys = rng.integers(0, wh, n_rect)
+    ws = rng.integers(10, 70, n_rect); hs = rng.integers(10, 70, n_rect)
+    cols = torch.from_numpy(rng.uniform(0, 255, (n_rect, 3)).astype(np.float32)).to(device)
+    for i in range(n_rect):
+        img[:, ys[i]:ys[i] + hs[i], xs[i]:xs[i] + ws[i]] = cols[i][:, None, None]
+    world = img.clamp_(0, 255).to(torch.uint8).to(torch.float32)      # quantised world, as make_world returns uint8
+    left = world[:, margin:margin + h, margin:margin + w].permute(1, 2, 0).to(torch.uint8).contiguous()
+    th = np.deg2rad(rot_deg)
+    cx, cy = w / 2.0, h / 2.0
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    C0 = np.array([[1, 0, -cx], [0, 1, -cy], [0, 0, 1.0]])
+    C1 = np.array([[1, 0, cx], [0, 1, cy], [0, 0, 1.0]])
+    P = np.array([[1, 0, 0], [0, 1, 0], [persp, -persp, 1.0]])
+    T = np.array([[1, 0, margin + shift], [0, 1, margin], [0, 0, 1.0]])
+    A = T @ C1 @ R @ P @ C0
+    At = torch.from_numpy(A).to(device)
+    yy, xx = torch.meshgrid(torch.arange(h, device=device, dtype=torch.float64),
+                            torch.arange(w, device=device, dtype=torch.float64), indexing="ij")
+    den = At[2, 0] * xx + At[2, 1] * yy + At[2, 2]
+    X = ((At[0, 0] * xx + At[0, 1] * yy + At[0, 2]) / den).clamp_(0, ww - 1.001)
+    Y = ((At[1, 0] * xx + At[1, 1] * yy + At[1, 2]) / den).clamp_(0, wh - 1.001)
+    grid = torch.stack([X / (ww - 1) * 2 - 1, Y / (wh - 1) * 2 - 1], -1)[None].to(torch.float32)
+    right = F.grid_sample(world[None], grid, mode="bilinear", align_corners=True)[0]
+    if noise:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed + 1000003)
+        right = right + torch.randint(-noise, noise + 1, right.shape, generator=gen, device=device).to(torch.float32)
+    right = right.round_().clamp_(0, 255).to(torch.uint8).permute(1, 2, 0).contiguous()
+    H_true = np.array([[1, 0, -margin], [0, 1, -margin], [0, 0, 1.0]]) @ A
+    return left, right, H_true / H_true[2, 2]
