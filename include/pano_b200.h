@@ -201,6 +201,14 @@ int pano_stitch_fold(pano_ctx* ctx, const uint8_t* const* images, const int* ws,
                      const size_t* strides, int n, int mem, const pano_harris_opts* hopts,
                      const pano_ransac_opts* ropts, pano_pair_result* results);
 
+/* Fold restructuring (opt-in, behaviour changing).  mode 0 (default) = the reference's fold: every
+ * step re-detects keypoints on the whole grown panorama (ref: src/serial/main.cpp:400-409).  mode 1 = incremental:
+ * only the new image is detected; the panorama's keypoints are carried - the previous list shifted by the left
+ * image's offset in the new canvas, followed by the new image's keypoints mapped through T*H
+ * (cv::perspectiveTransform arithmetic, rounded to the nearest pixel) - and matched with patches taken from the
+ * current panorama.  Results differ from the reference's by design; a failed step keeps panorama and list. */
+int pano_set_fold_mode(pano_ctx* ctx, int mode);
+
 /* ---- chain mode (multi-image panoramas whose adjacent pairs are independent work items) ----
  * The reference folds images sequentially and re-detects on the growing panorama, which cannot
  * be sharded.  Chain mode instead estimates H(i <- i+1) for every adjacent pair

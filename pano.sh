@@ -57,7 +57,7 @@ case $COMMAND in
     done
     echo "=== Building project in $BUILD_DIR ==="
     mkdir -p "$BUILD_DIR" && cd "$BUILD_DIR" || { echo "Failed to enter build directory"; exit 1; }
-    CMAKE_ARGS=""; $NO_GPU && { CMAKE_ARGS="-DBUILD_GPU=OFF"; echo "Building without GPU support"; }
+    CMAKE_ARGS="-DBUILD_GPU=ON"; $NO_GPU && { CMAKE_ARGS="-DBUILD_GPU=OFF"; echo "Building without GPU support"; }
     # use the system compilers unless told otherwise (an inherited CXX may lack OpenMP support)
     export CXX="${PANO_CXX:-$(command -v g++)}" CC="${PANO_CC:-$(command -v gcc)}"
     cmake $CMAKE_ARGS "$SCRIPT_DIR" || { echo "CMake failed"; exit 1; }

@@ -473,3 +473,65 @@ def test_ransac_rejects_out_of_range_match_indices(engine, oracle, small_pair):
         assert ei.value.status == pkg.PANO_ERR_INVALID
     H = engine.computeHomography(kr, kl, m)
     assert np.array_equal(bits(H), bits(oracle.ransac(kr, kl, m, seed=12345)["H"]))
+
+
+def test_incremental_fold_matches_its_restatement(oracle):
+    """opt-in fold restructuring (pano_set_fold_mode(ctx, 1)): only the new image is detected, the
+    panorama's keypoints are carried (shifted / mapped through T*H).  Behaviour differs from the reference's fold by
+    design, so the engine is held to a restatement of the same rule built from the oracle's stage functions."""
+    pkg, synth = load_pkg(), load_synth()
+    views = synth.make_strip(n=4, w=520, h=300, seed=12)
+    eng = pkg.Engine(0, 12345)
+    eng.set_fold_mode(1)
+    pano, log = eng.stitchAllImages(views)
+    eng.set_fold_mode(0)
+    ref_pano, _ = eng.stitchAllImages(views)
+    eng.close()
+    O = oracle
+    P, K = views[0], O.detect(views[0])
+    for im, step in zip(views[1:], log):
+        kr = O.detect(im)
+        m = O.match(kr, K, im, P)
+        r = O.ransac(kr, K, m, seed=12345)
+        assert (step["kl"], step["kr"], step["m"], step["best"]) == (len(K), len(kr), len(m), r["best_count"])
+        assert r["ok"] and step["status"] == 0 and np.array_equal(bits(step["H"]), bits(r["H"]))
+        ok, (cw, ch, ox, oy), TH = O.canvas_geometry(P.shape[1], P.shape[0], im.shape[1], im.shape[0], r["H"])
+        assert ok
+        P = O.compose(P, im, r["H"])
+        moved = np.where(K[:, :1] < 0, -1, K + np.int32([ox, oy])).astype(np.int32)
+        q = np.rint(O.perspective_transform(kr.astype(np.float32), TH)).astype(np.int32)
+        inside = (q[:, 0] >= 0) & (q[:, 1] >= 0) & (q[:, 0] < cw) & (q[:, 1] < ch)
+        q[~inside] = -1
+        K = np.concatenate([moved, q]).astype(np.int32)
+    assert pano.shape == P.shape and np.array_equal(pano, P)
+    # it is a different algorithm from the reference's fold (which re-detects on the panorama), same kind of result
+    assert abs(pano.shape[1] - ref_pano.shape[1]) < 0.15 * ref_pano.shape[1], (pano.shape, ref_pano.shape)
+
+
+def test_async_pair_equals_blocking_pair(engine, oracle, small_pair):
+    """pano_stitch_pair_async + pano_pair_query / pano_pair_wait: same result as the blocking call; the
+    context refuses other work while the pair is in flight"""
+    pkg = load_pkg()
+    import torch
+    left, right, _ = small_pair
+    o = oracle.stitch_pair(left, right, seed=12345)
+    h = engine.stitchTwoImagesAsync(left, right)
+    res2 = pkg.PairResult()
+    ho, ro = pkg.HarrisCornerOptions(), pkg.RansacOptions()
+    L = pkg._Img(left)
+    import ctypes as C
+    busy = engine.lib.pano_stitch_pair_async(engine.ctx, L.ptr, L.w, L.h, C.c_size_t(L.stride), L.ptr, L.w, L.h,
+                                             C.c_size_t(L.stride), 0, C.byref(ho), C.byref(ro), None, C.byref(res2))
+    assert busy in (pkg.PANO_ERR_BUSY,)
+    r = h.result()
+    assert h.done() and r["status"] == 0 and np.array_equal(bits(r["H"]), bits(o["H"]))
+    assert np.array_equal(engine.getCanvas(), o["canvas"])
+    # stream-ordered, device-resident: work enqueued on the caller's stream after the wait sees the canvas
+    Ld, Rd = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+    s = torch.cuda.Stream()
+    h = engine.stitchTwoImagesAsync(Ld, Rd, stream_ptr=s.cuda_stream)
+    r = h.result()
+    with torch.cuda.stream(s):
+        c = engine.getCanvas(device=True)
+    s.synchronize()
+    assert r["status"] == 0 and np.array_equal(c.cpu().numpy(), o["canvas"])

@@ -93,6 +93,80 @@ __global__ void __launch_bounds__(512) tmem_ld_kernel(int reps, long long* cycle
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(512u));
 }
 
+// tcgen05.mma issue-to-completion rate: one thread issues `n_mma` MMAs of shape M128 x N x K32B (kind::i8, u8 x u8 -> s32)
+// or M128 x N x K16 (kind::f16, bf16 x bf16 -> f32) on zero-filled shared-memory operands (K-major, 128B swizzle, the
+// matcher's descriptors), commits, and waits for the commit's mbarrier.  cycles / n_mma is the tensor pipe's time per MMA.
+__device__ __forceinline__ uint64_t mk_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+template <int KIND, int N>   // KIND 0 = i8, 1 = bf16
+__global__ void __launch_bounds__(128) mma_rate_kernel(int n_mma, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  uint8_t* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
+  __shared__ uint32_t s_tmem;
+  __shared__ unsigned long long bar;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (128 + 256) * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x01010101u;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (threadIdx.x == 0) {
+    const uint64_t adesc = mk_desc(smem_u32(sm)), bdesc = mk_desc(smem_u32(sm + 128 * 128));
+    // instruction descriptor: D format bits [4,6) (1 = f32, 2 = s32), A/B format bits [7,10) / [10,13) (i8: 0 = u8; f16 kind: 1 = bf16)
+    const uint32_t idesc = KIND == 0 ? ((2u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24))
+                                     : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24));
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; i++) {
+      const uint32_t d = s_tmem + (uint32_t)((i & 1) * 256);
+      if (KIND == 0)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u) : "memory");
+      else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(512u));
+}
+
+template <int KIND, int N>
+static void run_mma(int sms, std::string& out, long long* d_cycles) {
+  const int n_mma = 2048;
+  const size_t smem = (128 + 256) * 128 + 1024;
+  CK(cudaFuncSetAttribute(mma_rate_kernel<KIND, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mma_rate_kernel<KIND, N><<<sms, 128, smem>>>(64, d_cycles);
+  CK(cudaDeviceSynchronize());
+  mma_rate_kernel<KIND, N><<<sms, 128, smem>>>(n_mma, d_cycles);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> cyc(sms);
+  CK(cudaMemcpy(cyc.data(), d_cycles, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+  double mean = 0;
+  for (long long c : cyc) mean += (double)c;
+  mean /= sms;
+  const double k_elems = KIND == 0 ? 32.0 : 16.0;
+  char buf[256];
+  snprintf(buf, sizeof buf, "%s{\"kind\": \"%s\", \"M\": 128, \"N\": %d, \"K\": %d, \"cycles_per_mma\": %.1f, \"mac_per_clk_per_sm\": %.0f}",
+           out.empty() ? "" : ", ", KIND == 0 ? "i8" : "bf16", N, (int)k_elems, mean / n_mma, 128.0 * N * k_elems / (mean / n_mma));
+  out += buf;
+}
+
 template <int OP>   // 0 DADD, 1 DMUL, 2 DFMA, 3 alternating DMUL + DADD (the stencil's mix)
 __global__ void __launch_bounds__(256) fp64_kernel(int reps, double seed, double* sink) {
   double a[8];
@@ -183,6 +257,12 @@ int main(int argc, char** argv) {
     run_tmem<64, 2>(warps, sms, tm, d_cycles, d_sink);
   }
 
+  std::string mm;
+  run_mma<0, 256>(sms, mm, d_cycles);
+  run_mma<0, 128>(sms, mm, d_cycles);
+  run_mma<1, 256>(sms, mm, d_cycles);
+  run_mma<1, 128>(sms, mm, d_cycles);
+
   // FP64 / integer issue rates: 8 resident blocks of 256 threads per SM, 8 independent chains per thread
   const int blocks = sms * 8, reps = 20000;
   double fp[4];
@@ -211,6 +291,7 @@ int main(int argc, char** argv) {
 
   std::string js = "{\"device_sms\": " + std::to_string(sms) + ", \"clock_khz_attr\": " + std::to_string(khz);
   js += ", \"tmem_ld\": [" + tm + "]";
+  js += ", \"tcgen05_mma\": [" + mm + "]";
   char buf[512];
   snprintf(buf, sizeof buf,
            ", \"fp64_instr_per_s\": {\"%s\": %.4e, \"%s\": %.4e, \"%s\": %.4e, \"%s\": %.4e}, \"replay_cells_per_s\": %.4e}",

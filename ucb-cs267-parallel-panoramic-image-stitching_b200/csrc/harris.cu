@@ -138,6 +138,10 @@ harris_response_kernel(const uint8_t* __restrict__ img, int w, int h, size_t str
 //            product row feeds up to five outputs), response -> shared memory
 //   phase 4  threshold + strict NMS on the inner pixels, one ballot word per tile row, OR-ed into the 1-bit/px
 //            mask (keypoints are sparse: almost every word is zero and skipped) + per-row counts
+// Tried and dropped (round 2): a persistent warp-specialised form (4 producer warps running TMA + gray + Sobel of tile
+// k + 1 while 8 consumer warps run the FP64 phase of tile k, one CTA per SM): 146.7 us per 4K image against 137.3 us
+// for this kernel - with one CTA per SM only two FP64 warps per scheduler remain, and the stencil's dependent
+// DADD chains need the four that two co-resident CTAs of this kernel provide (ncu: 26 % "wait" stalls).
 // Semantics: ref src/serial/main.cpp:119-180, bit-identical keypoints (the response values are the same doubles).
 // ---------------------------------------------------------------------------------------
 constexpr int FX = 32, FY = 64;           // response tile

@@ -127,7 +127,41 @@ __global__ void gather_matches_kernel(const pano_dmatch* __restrict__ in, const 
   if (i < n) out[i] = in[idx[i]];
 }
 
+// Incremental fold (opt-in): the panorama's keypoint list after a step = the old list shifted by the left
+// image's offset in the new canvas, followed by the new image's keypoints mapped through T*H
+// (cv::perspectiveTransform arithmetic, rounded to the nearest pixel, ties to even); points that leave the canvas
+// become (-1, -1), which the matcher's in-border test skips.
+struct Mat33 { double m[9]; };
+__global__ void update_pano_keypoints_kernel(const int32_t* __restrict__ old_xy, int n_old, int offx, int offy,
+                                             const int32_t* __restrict__ new_xy, int n_new, Mat33 TH, int cw, int ch,
+                                             int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_old) {
+    const int x = old_xy[2 * i], y = old_xy[2 * i + 1];
+    out[2 * i] = x < 0 ? -1 : x + offx;
+    out[2 * i + 1] = x < 0 ? -1 : y + offy;
+  } else if (i < n_old + n_new) {
+    const int j = i - n_old;
+    float px, py;
+    persp_point(TH.m, (float)new_xy[2 * j], (float)new_xy[2 * j + 1], &px, &py);
+    const int x = __float2int_rn(px), y = __float2int_rn(py);
+    const bool in = x >= 0 && y >= 0 && x < cw && y < ch;
+    out[2 * i] = in ? x : -1;
+    out[2 * i + 1] = in ? y : -1;
+  }
+}
+
 }  // namespace
+
+void update_pano_keypoints_device(cudaStream_t st, const int32_t* old_xy, int n_old, int offx, int offy, const int32_t* new_xy,
+                                  int n_new, const double* TH, int cw, int ch, int32_t* out) {
+  const int n = n_old + n_new;
+  if (n <= 0) return;
+  Mat33 m;
+  memcpy(m.m, TH, sizeof m.m);
+  update_pano_keypoints_kernel<<<(n + 255) / 256, 256, 0, st>>>(old_xy, n_old, offx, offy, new_xy, n_new, m, cw, ch, out);
+  PANO_LAUNCH_CHECK();
+}
 
 int build_descriptors_device(cudaStream_t st, const DevImage& img, const int32_t* xy, int n, int patch,
                              MatchScratch& s, DevDescriptors& d, PinnedBuf& pin) {

@@ -25,10 +25,11 @@
 //   warp 16    producer: one lane issues TMA loads (cp.async.bulk.tensor.2d, 128B swizzle) of the descriptor
 //              tiles straight into the K-major layout the UMMA descriptors expect, and bulk copies
 //              (cp.async.bulk) of the train tile's 128 precomputed column constants
-//   warp 17    one lane issues tcgen05.mma (3 K-steps of 32 bytes per 128x128 accumulator) and commits
-// Pipelines (mbarriers): B stages full/empty (4 deep, TMA complete_tx), A super-rows full/empty (2 deep), one
-// full/empty pair per accumulator: the MMA of unit n + 1 into accumulator g starts as soon as group g has drained
-// unit n, while the other groups are still draining - the tensor pipe only idles when all four groups are behind.
+//              The group's first lane also ISSUES its accumulator's tcgen05.mma (3 K-steps of 32 bytes) and commits:
+//              no cross-role hand-over sits on an accumulator's cycle (issue -> commit -> drain -> named barrier).
+//   warp 17    allocates / frees tensor memory
+// Pipelines (mbarriers): B stages full/empty (4 deep, TMA complete_tx; released by QT commits, one per group), A
+// super-rows full/empty (2 deep), one "full" barrier per accumulator; the four groups interleave on the tensor pipe.
 // The column constants live in NCV = NSTAGE + 2 slots: the producer reaches unit m only after the MMAs of unit
 // m - NSTAGE have completed, which needed every epilogue of unit m - NSTAGE - 1 to have released its accumulator.
 // Every wait is bounded: a bring-up bug raises an error flag instead of hanging the device.
@@ -51,7 +52,7 @@ constexpr int A_BYTES = TM * KB;   // 16 KB
 constexpr int B_BYTES = TN * KB;   // 16 KB
 constexpr int EPI_WARPS = 4 * QT;  // group g = warps 4g .. 4g + 3 drains accumulator g
 constexpr int TC_THREADS = 32 * (EPI_WARPS + 2);
-constexpr uint32_t SPIN_LIMIT = 1u << 26;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 // instruction descriptor, kind::i8: D = S32 (2 << 4), A = B = UINT8 (0), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24   (cute::UMMA::InstrDescriptor layout)
@@ -64,8 +65,7 @@ struct Smem {
   int cvec[NCV][TN];               // per unit in flight: |t_j|^2 * 256 + (j mod 128), INT_MAX for padding
   unsigned long long b_full[NSTAGE], b_empty[NSTAGE];
   unsigned long long a_full[2], a_empty[2];
-  unsigned long long t_full[QT], t_empty[QT];
-  unsigned long long c_full[QT];   // column constants of the unit in accumulator g are visible (see MMA issuer)
+  unsigned long long t_full[QT];   // accumulator g complete (tcgen05.commit of its group's issuing lane)
   uint32_t tmem_base;
   int abort_flag;
 };
@@ -78,21 +78,23 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded polling wait (test_wait never blocks, so the spin bound is a real time bound);
-// returns false if it gave up (or another role already aborted)
+// bounded wait; returns false if it gave up (or another role already aborted).  try_wait suspends the warp in
+// hardware until the phase completes or a short system time limit expires, so waiting warps do not compete for
+// issue slots with the warps that are draining accumulators (test_wait polling did: ncu showed 40 % of the issued
+// instructions in the poll loops).
 __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity, volatile int* abort_flag) {
   const uint32_t addr = smem_u32(bar);
   for (uint32_t spin = 0; spin < SPIN_LIMIT; spin++) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return true;
-    if ((spin & 1023u) == 1023u && *abort_flag) return false;
+    if ((spin & 63u) == 63u && *abort_flag) return false;
   }
   *abort_flag = 1;
   return false;
@@ -190,13 +192,10 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   volatile int* abort_flag = &S.abort_flag;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; i++) { mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], 1); }
-    for (int i = 0; i < QT; i++) {
-      mbar_init(&S.t_full[i], 1);
-      mbar_init(&S.t_empty[i], 128);   // the four warps of the accumulator's group
-      mbar_init(&S.c_full[i], 1);
-    }
+    // every group issues the MMAs of its own accumulator, so a B stage / an A super-row is released by QT arrivals
+    for (int i = 0; i < NSTAGE; i++) { mbar_init(&S.b_full[i], 1); mbar_init(&S.b_empty[i], QT); }
+    for (int i = 0; i < 2; i++) { mbar_init(&S.a_full[i], 1); mbar_init(&S.a_empty[i], QT); }
+    for (int i = 0; i < QT; i++) mbar_init(&S.t_full[i], 1);
     S.abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -215,27 +214,62 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int hi = (int)((long long)n_units * (blockIdx.x + 1) / gridDim.x);
 
   if (warp < EPI_WARPS) {
-    // ================= epilogue: group g = warp >> 2 drains accumulator g (query tile 4 sr + g) =================
+    // ===== group g = warp >> 2 owns accumulator g (query tile 4 sr + g): its first lane issues the MMAs, all four
+    // warps drain them.  (Round 2, first version: one MMA-issuing thread for all four accumulators; ncu showed the
+    // epilogue warps polling its hand-over barriers for most of the kernel - 4200 clk per unit against 768 clk of
+    // MMA - so the issue moved into the groups: no cross-role round trip is left on an accumulator's cycle.)
     const int g = warp >> 2;
-    uint32_t unit_ctr = 0;   // units of this CTA so far (column-constant slot)
-    uint32_t use_ctr = 0;    // units in which accumulator g was used (its barriers' phase)
+    const bool leader = (threadIdx.x & 127) == 0;
+    uint32_t unit_ctr = 0;   // units of this CTA so far (B stage / column-constant slot)
+    uint32_t use_ctr = 0;    // units in which accumulator g was used (t_full's phase)
+    uint32_t seg_ctr = 0;
     bool ok = true;
-    for (int unit = lo; unit < hi && ok;) {
+    for (int unit = lo; unit < hi && ok; seg_ctr++) {
       const Seg sg = next_seg(unit, hi, n_ttiles);
       const int n_seg = sg.t1 - sg.t0;
       unit += n_seg;
+      const uint32_t ab = seg_ctr & 1u, aph = (seg_ctr >> 1) & 1u;
       const int qt = sg.sr * QT + g;
-      if (qt >= n_qtiles) { unit_ctr += (uint32_t)n_seg; continue; }   // this super-row has fewer than QT query tiles
+      if (qt >= n_qtiles) {
+        // this super-row has fewer than QT query tiles: nothing to compute, but the producer counts QT releases
+        // (paced by the "full" barriers: one release per phase, never two of this group inside one phase)
+        if (leader) {
+          ok = mbar_wait(&S.a_full[ab], aph, abort_flag);
+          for (int i = 0; i < n_seg && ok; i++) {
+            const uint32_t uc = unit_ctr + (uint32_t)i;
+            ok = mbar_wait(&S.b_full[uc % NSTAGE], (uc / NSTAGE) & 1u, abort_flag);
+            if (ok) mbar_arrive(&S.b_empty[uc % NSTAGE]);
+          }
+          if (ok) mbar_arrive(&S.a_empty[ab]);
+        }
+        unit_ctr += (uint32_t)n_seg;
+        continue;
+      }
+      ok = mbar_wait(&S.a_full[ab], aph, abort_flag);
+      if (!ok) break;
+      const uint64_t adesc = make_desc(smem_u32(S.A[ab][g]));
       const int qrow = qt * TM + ((int)threadIdx.x & 127);
       const int myqn = qrow < nq ? (int)qn[qrow] : 0;
       int best_ssd = 0x7fffffff, best_j = -1;
       for (int tt = sg.t0; tt < sg.t1 && ok; tt++, unit_ctr++, use_ctr++) {
-        const uint32_t ph = use_ctr & 1u;
+        const uint32_t s = unit_ctr % NSTAGE, sph = (unit_ctr / NSTAGE) & 1u;
         const uint32_t cs = unit_ctr % NCV;
-        // c_full: the producer's cvec writes are visible (relayed by the MMA thread, which acquired them through
-        // b_full; it advances in lockstep with the accumulator, so a waiter can never fall two phases behind);
-        // t_full: the accumulator is complete
-        ok = mbar_wait(&S.c_full[g], ph, abort_flag) && mbar_wait(&S.t_full[g], ph, abort_flag);
+        // every thread acquires the stage (descriptor tile + column constants written by the async proxy)
+        ok = mbar_wait(&S.b_full[s], sph, abort_flag);
+        if (!ok) break;
+        if (leader) {
+          // accumulator g is free: the whole group passed the named barrier below after draining the previous unit
+          tc_fence_after();
+          const uint64_t bdesc = make_desc(smem_u32(S.B[s]));
+          const uint32_t d_tmem = tmem_base + (uint32_t)(g * TN);
+#pragma unroll
+          for (int ks = 0; ks < K_STEPS; ks++)  // 32 bytes of K per MMA: descriptor start advances 32 B
+            mma_i8(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), ks > 0 ? 1u : 0u);
+          mma_commit(&S.t_full[g]);    // accumulator ready
+          mma_commit(&S.b_empty[s]);   // this group's read of the stage is done once these MMAs have completed
+          if (tt + 1 == sg.t1) mma_commit(&S.a_empty[ab]);
+        }
+        ok = mbar_wait(&S.t_full[g], use_ctr & 1u, abort_flag);
         if (!ok) break;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * TN);
@@ -255,7 +289,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           tmem_ld_wait();
         }
         tc_fence_before();
-        mbar_arrive(&S.t_empty[g]);
+        // the group's 128 threads have read the accumulator: its leader may overwrite it (named barrier 1 + g)
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory");
         const int kmin = min(min(km0, km1), min(km2, km3));
         const int v = kmin >> 8, jl = kmin & 255;
         const int ssd = v + myqn;
@@ -290,45 +325,6 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           bulk_load_1d(S.cvec[cs], tkey + (size_t)tt * TN, TN * (uint32_t)sizeof(int), &S.b_full[s]);
         }
       }
-    }
-  } else if (warp == EPI_WARPS + 1 && lane == 0) {
-    // ================= MMA issuer (one thread) =================
-    uint32_t unit_ctr = 0, seg_ctr = 0;
-    uint32_t use_ctr[QT] = {0u, 0u, 0u, 0u};
-    bool ok = true;
-    for (int unit = lo; unit < hi && ok; seg_ctr++) {
-      const Seg sg = next_seg(unit, hi, n_ttiles);
-      unit += sg.t1 - sg.t0;
-      const uint32_t ab = seg_ctr & 1u, aph = (seg_ctr >> 1) & 1u;
-      ok = mbar_wait(&S.a_full[ab], aph, abort_flag);
-      if (!ok) break;
-      const int nvalid = min(QT, n_qtiles - sg.sr * QT);
-      for (int tt = sg.t0; tt < sg.t1 && ok; tt++, unit_ctr++) {
-        const uint32_t s = unit_ctr % NSTAGE, sph = (unit_ctr / NSTAGE) & 1u;
-        ok = mbar_wait(&S.b_full[s], sph, abort_flag);
-        if (!ok) break;
-        const uint64_t bdesc = make_desc(smem_u32(S.B[s]));
-#pragma unroll
-        for (int q = 0; q < QT; q++) {
-          if (q < nvalid && ok) {
-            ok = mbar_wait(&S.t_empty[q], (use_ctr[q] & 1u) ^ 1u, abort_flag);   // group q has drained the previous unit
-            if (ok) {
-              mbar_arrive(&S.c_full[q]);  // release: passes the acquired cvec writes on to the epilogue
-              tc_fence_after();
-              const uint64_t adesc = make_desc(smem_u32(S.A[ab][q]));
-              const uint32_t d_tmem = tmem_base + (uint32_t)(q * TN);
-#pragma unroll
-              for (int ks = 0; ks < K_STEPS; ks++)  // 32 bytes of K per MMA: descriptor start advances 32 B
-                mma_i8(d_tmem, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), ks > 0 ? 1u : 0u);
-              mma_commit(&S.t_full[q]);   // accumulator q ready for its group
-              use_ctr[q]++;
-            }
-          }
-        }
-        if (!ok) break;
-        mma_commit(&S.b_empty[s]);   // smem stage reusable once these MMAs have read it
-      }
-      mma_commit(&S.a_empty[ab]);    // A super-row buffer reusable after the segment's last MMA
     }
   }
 

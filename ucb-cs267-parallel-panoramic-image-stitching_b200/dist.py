@@ -111,11 +111,27 @@ def stitch_chain_distributed(engine, images, device=None, group=None):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n_pairs = len(images) - 1
     mine = shard_pairs(n_pairs, rank, world)
+    host_images = images
+    if device is not None and len({np.asarray(im).shape for im in images}) == 1:
+        # replicate the inputs over NVLink instead of PCIe: every rank uploads 1 / W of the images and
+        # one NCCL all-gather hands all of them to every GPU; on the 8-GPU boxes of this pool the host side moves
+        # ~105-130 GB/s in total, so 8 ranks uploading all images each would spend most of the step there
+        import torch
+        n = len(images)
+        per = (n + world - 1) // world
+        h, w = np.asarray(images[0]).shape[:2]
+        part = torch.zeros((per, h, w, 3), dtype=torch.uint8, device=device)
+        for slot, j in enumerate(range(rank, n, world)):
+            part[slot].copy_(torch.from_numpy(np.ascontiguousarray(images[j])), non_blocking=True)
+        allimg = torch.empty((world * per, h, w, 3), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allimg, part, group=group)
+        torch.cuda.current_stream().synchronize()
+        images = [allimg[(j % world) * per + j // world] for j in range(n)]
     res = [engine.pairHomography(images[i], images[i + 1]) for i in mine]
     allr = all_gather_results(pack_results(mine, res), n_pairs, device=device, group=group)
     pair_H = [allr[i, :9].reshape(3, 3).copy() if int(allr[i, 9]) == 0 else None for i in range(n_pairs)]
     Hs = engine.composeChain(pair_H)
-    sizes = [(np.asarray(im).shape[1], np.asarray(im).shape[0]) for im in images]
+    sizes = [(np.asarray(im).shape[1], np.asarray(im).shape[0]) for im in host_images]
     ok, geom, T = engine.chainGeometry(sizes, Hs)
     if not ok:
         return None, allr
