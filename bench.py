@@ -224,6 +224,11 @@ def copy_ceiling(torch, dist, world, Lh, Rh, Ch, canvas_bytes, Ld, Rd, reps=2):
 def run_engine(a):
     import torch
     rank, world, local = dist_env()
+    t_start = time.perf_counter()
+
+    def log(msg):      # progress on stderr (stdout carries the one JSON line)
+        if rank == 0:
+            print("[bench %6.1f s] %s" % (time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
     pkg = importlib.import_module(PKG)
     synth = importlib.import_module(PKG + ".synth")
     numa = importlib.import_module(PKG + ".numa").bind_to_gpu(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
@@ -251,6 +256,7 @@ def run_engine(a):
         Ld.append(l); Rd.append(r)
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
+    log("generated %d pairs per GPU on the device in %.1f s" % (P, t_gen))
 
     def barrier():
         if world > 1:
@@ -315,7 +321,10 @@ def run_engine(a):
     cap = max(canvas_bytes) + (1 << 20)
     per_pair = 2 * 3 * npx + cap
     budget = int(0.45 * mem_available_bytes() / max(world, 1))
-    Pe = max(8, min(P, budget // per_pair))           # pairs of the e2e leg (all P unless host memory is short)
+    # pairs of the e2e leg: all P on one GPU (unless host memory is short); with several ranks on one box the leg is
+    # bound by the box's shared host memory system, and 128 pairs per GPU already run for seconds per step
+    Pe = max(8, min(P if world == 1 else min(P, 128), budget // per_pair))
+    log("resident leg done (%.1f ms/step); pinning %.1f GB of host memory for %d e2e pairs" % (ms_dev / a.steps, Pe * per_pair / 1e9, Pe))
     t_pin = time.perf_counter()
     pool = pinned_bytes(torch, Pe * per_pair)
     t_pin = time.perf_counter() - t_pin
@@ -336,6 +345,7 @@ def run_engine(a):
     for _ in range(min(a.warmup, 2)):
         step_e2e()
     ms_e2e, _, res_e = timed(step_e2e, a.steps)
+    log("e2e leg done (%.1f ms/step)" % (ms_e2e / a.steps))
     res_e = dicts(res_e)
     d2h = sum(3 * r["canvas"][0] * r["canvas"][1] for r in res_e)
     h2d = Pe * 2 * 3 * npx
@@ -346,9 +356,9 @@ def run_engine(a):
         t = torch.tensor([ms_dev, ms_e2e, wall_ms, t_ceiling], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e, wall_ms, t_ceiling = [float(x) for x in t]
-        lt = torch.tensor([launches, len(bad)], device="cuda", dtype=torch.int64)
+        lt = torch.tensor([launches, len(bad), h2d, d2h], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt)
-        launches, nbad = int(lt[0]), int(lt[1])
+        launches, nbad, h2d, d2h = [int(x) for x in lt]      # (whole job, like `value`)
     else:
         nbad = len(bad)
     mp_pair = 2 * npx / 1e6
@@ -428,7 +438,11 @@ def run_engine(a):
         # the serial build is estimated from a sample of its stages) ---------------------------------
         cpu = None
         if not a.no_cpu and world == 1:
-            cpu = cpu_baseline(a, Ld[0].cpu().numpy(), Rd[0].cpu().numpy(), res[0])
+            log("kernel profile done; timing the reference's CPU code on one pair of the workload")
+            try:
+                cpu = cpu_baseline(a, Ld[0].cpu().numpy(), Rd[0].cpu().numpy(), res[0])
+            except Exception as e:      # the line is still worth printing
+                cpu = {"value": None, "unit": UNIT, "error": "%s: %s" % (type(e).__name__, e)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_dev / a.steps, "ms_per_pair": ms_dev / (a.steps * P), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",

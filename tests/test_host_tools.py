@@ -1,0 +1,46 @@
+"""CPU tier: host-side helpers of the bench / multi-GPU path (no GPU needed)."""
+import importlib
+import os
+
+import numpy as np
+
+from conftest import PKG, load_synth
+
+
+def test_numa_helpers_parse_and_degrade_gracefully():
+    numa = importlib.import_module(PKG + ".numa")
+    assert numa._parse_cpulist("0-3,8,10-11") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa._parse_cpulist("") == set() and numa._parse_cpulist(None) == set()
+    before = os.sched_getaffinity(0)
+    try:
+        info = numa.bind_to_gpu(0, 1)            # no GPU here: nothing to bind to, must not raise
+        assert info["gpu"] == 0 and info["allowed_cpus"] == len(before)
+        info2 = numa.bind_to_gpu(1, 2)           # two ranks, GPU node unknown: even split of the allowed CPUs
+        if len(before) >= 2:
+            assert info2.get("bound_cpus") == len(sorted(before)[1::2])
+    finally:
+        os.sched_setaffinity(0, before)
+
+
+def test_torch_generator_draws_the_same_scene_as_the_numpy_one():
+    """bench.py's device-side generator uses the numpy generator's random parameters: same left image up to the last
+    bit of float32 rounding, same kind of right image (its +-2 LSB noise comes from another RNG)"""
+    synth = load_synth()
+    l, r, H = synth.make_pair_torch(640, 360, seed=1003, device="cpu")
+    l2, r2, H2 = synth.make_pair(640, 360, seed=1003)
+    assert np.allclose(H, H2)
+    d = np.abs(l.numpy().astype(np.int16) - l2.astype(np.int16))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    assert np.abs(r.numpy().astype(np.int16) - r2.astype(np.int16)).mean() < 3.0
+
+
+def test_pair_result_numpy_view_matches_the_c_struct():
+    import ctypes as C
+    pkg = importlib.import_module(PKG)
+    arr = (pkg.PairResult * 3)()
+    arr[1].status = 5; arr[1].n_matches = 77; arr[1].best_inliers = 9; arr[1].H[4] = 2.5
+    arr[2].canvas.canvas_w = 123; arr[2].ms_total = 1.5
+    v = pkg.results_array(arr)
+    assert v.shape == (3,) and v["status"][1] == 5 and v["n_matches"][1] == 77 and v["best_inliers"][1] == 9
+    assert v["H"][1][4] == 2.5 and v["canvas"]["canvas_w"][2] == 123 and v["ms_total"][2] == 1.5
+    assert pkg.PAIR_DTYPE.itemsize == C.sizeof(pkg.PairResult)

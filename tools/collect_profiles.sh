@@ -12,6 +12,7 @@ python bench.py --steps 5 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_ben
 python bench.py --workload c3 > $OUT/${TAG%_final}_c3_pair.json 2> $OUT/c3.err; cut -c1-400 $OUT/${TAG%_final}_c3_pair.json
 python bench.py --workload c1 > $OUT/${TAG%_final}_c1_mountain.json 2> $OUT/c1.err; cut -c1-400 $OUT/${TAG%_final}_c1_mountain.json
 python bench.py --workload c2 > $OUT/${TAG%_final}_c2_oilseed.json 2> $OUT/c2.err; cut -c1-400 $OUT/${TAG%_final}_c2_oilseed.json
+python tools/cpu_o0.py > $OUT/${TAG%_final}_cpu_o0.json 2> $OUT/cpu_o0.err; cut -c1-300 $OUT/${TAG%_final}_cpu_o0.json
 # launch list of one pair (per-launch times are cold-cache and serialised: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python tools/profile_pair.py --reps 3 > $OUT/ncu_launches.log 2>&1

@@ -52,7 +52,7 @@ constexpr int A_BYTES = TM * KB;   // 16 KB
 constexpr int B_BYTES = TN * KB;   // 16 KB
 constexpr int EPI_WARPS = 4 * QT;  // group g = warps 4g .. 4g + 3 drains accumulator g
 constexpr int TC_THREADS = 32 * (EPI_WARPS + 2);
-constexpr uint32_t SPIN_LIMIT = 1u << 22;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 // instruction descriptor, kind::i8: D = S32 (2 << 4), A = B = UINT8 (0), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24   (cute::UMMA::InstrDescriptor layout)
@@ -78,23 +78,21 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded wait; returns false if it gave up (or another role already aborted).  try_wait suspends the warp in
-// hardware until the phase completes or a short system time limit expires, so waiting warps do not compete for
-// issue slots with the warps that are draining accumulators (test_wait polling did: ncu showed 40 % of the issued
-// instructions in the poll loops).
+// bounded polling wait (test_wait never blocks, so the spin bound is a real time bound);
+// returns false if it gave up (or another role already aborted)
 __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity, volatile int* abort_flag) {
   const uint32_t addr = smem_u32(bar);
   for (uint32_t spin = 0; spin < SPIN_LIMIT; spin++) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return true;
-    if ((spin & 63u) == 63u && *abort_flag) return false;
+    if ((spin & 1023u) == 1023u && *abort_flag) return false;
   }
   *abort_flag = 1;
   return false;
