@@ -151,7 +151,7 @@ constexpr int FPW = FX + 4, FPH = FY + 4; // product planes incl. Gaussian halo
 constexpr int FGW = FX + 6, FGH = FY + 6; // gray incl. Sobel halo
 constexpr int FRAW = 144;                 // bytes per raw tile row: 3 * FGW = 114 plus up to 15 bytes of alignment slack (the
                                           // innermost TMA coordinate of a byte tensor must be a multiple of 16: measured, an
-                                          // unaligned one raises 'illegal instruction'; tools/_tma_probe.cu), multiple of 16
+                                          // unaligned one raises 'illegal instruction'; tools/tma_probe.cu), multiple of 16
 
 struct FusedSmem {
   double xx[FPH][FPW];
