@@ -107,6 +107,11 @@ def _chain_worker(rank, world, port, out_dir):
     d = importlib.import_module(PKG + ".dist")
     synth = importlib.import_module(PKG + ".synth")
     views = synth.make_strip(n=4, w=320, h=200, seed=21)
+    # the NVLink replication of the inputs (upload 1 / W, all-gather) with CPU tensors: every rank must end up with
+    # every image, in order, also when the count is not a multiple of the world size
+    for k in (len(views), len(views) - 1):
+        rep = d.replicate_images(views[:k], "cpu")
+        assert len(rep) == k and all(np.array_equal(t.numpy(), v) for t, v in zip(rep, views[:k]))
     pano, allr = d.stitch_chain_distributed(_OracleEngine(), views)
     np.save(os.path.join(out_dir, "pano%d.npy" % rank), np.array(pano))
     dist.destroy_process_group()

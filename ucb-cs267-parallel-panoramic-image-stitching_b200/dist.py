@@ -100,33 +100,46 @@ class SharedCanvas:
         return c
 
 
-def stitch_chain_distributed(engine, images, device=None, group=None):
+def replicate_images(images, device, group=None):
+    """Hands all `images` (equal shapes, host arrays every rank holds) to every rank on `device` without every rank
+    pushing all of them through its own host link: rank r uploads images r, r + W, ... and one
+    all-gather (NCCL over NVLink on GPUs) completes the set.  On the 8-GPU boxes of this pool the host side moves
+    ~105-130 GB/s in total, so W ranks uploading all images each would spend most of the step there.
+    Returns one tensor view per image, in input order."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = len(images)
+    per = (n + world - 1) // world
+    h, w = np.asarray(images[0]).shape[:2]
+    part = torch.zeros((per, h, w, 3), dtype=torch.uint8, device=device)
+    for slot, j in enumerate(range(rank, n, world)):
+        part[slot].copy_(torch.from_numpy(np.ascontiguousarray(images[j])), non_blocking=True)
+    allimg = torch.empty((world * per, h, w, 3), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(allimg, part, group=group)
+    if allimg.is_cuda:
+        torch.cuda.current_stream().synchronize()     # the engine works on its own stream
+    return [allimg[(j % world) * per + j // world] for j in range(n)]
+
+
+def stitch_chain_distributed(engine, images, device=None, group=None, replicate=None):
     """Chain-mode panorama over all ranks of the process group (SURVEY 8e2 + 8e3): adjacent pair
     (i, i+1) is estimated on rank i mod W, the 96-byte records are all-gathered (the only collective), every
     rank composes the same H(0 <- i) and canvas geometry and renders its own band of canvas rows straight into
     a host canvas shared by the ranks of the node.  Every rank holds all input images (they come from the
     host).  Returns the panorama (a view of the shared canvas, the same memory on every rank; copy it if it
-    has to outlive the next call) or None, plus the gathered per-pair records."""
+    has to outlive the next call) or None, plus the gathered per-pair records.  With a CUDA `device` and equally
+    sized images the inputs are replicated over NVLink (replicate_images; `replicate=False` or PANO_CHAIN_NVLINK=0
+    makes every rank upload all images itself, the variant profiles/r02_chain_*gpu.json was measured with)."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if replicate is None:
+        replicate = os.environ.get("PANO_CHAIN_NVLINK", "1") != "0"
     n_pairs = len(images) - 1
     mine = shard_pairs(n_pairs, rank, world)
     host_images = images
-    if device is not None and len({np.asarray(im).shape for im in images}) == 1:
-        # replicate the inputs over NVLink instead of PCIe (SURVEY 8e3): every rank uploads 1 / W of the images and
-        # one NCCL all-gather hands all of them to every GPU; on the 8-GPU boxes of this pool the host side moves
-        # ~105-130 GB/s in total, so 8 ranks uploading all images each would spend most of the step there
-        import torch
-        n = len(images)
-        per = (n + world - 1) // world
-        h, w = np.asarray(images[0]).shape[:2]
-        part = torch.zeros((per, h, w, 3), dtype=torch.uint8, device=device)
-        for slot, j in enumerate(range(rank, n, world)):
-            part[slot].copy_(torch.from_numpy(np.ascontiguousarray(images[j])), non_blocking=True)
-        allimg = torch.empty((world * per, h, w, 3), dtype=torch.uint8, device=device)
-        dist.all_gather_into_tensor(allimg, part, group=group)
-        torch.cuda.current_stream().synchronize()
-        images = [allimg[(j % world) * per + j // world] for j in range(n)]
+    if device is not None and replicate and len({np.asarray(im).shape for im in images}) == 1:
+        images = replicate_images(images, device, group)
     res = [engine.pairHomography(images[i], images[i + 1]) for i in mine]
     allr = all_gather_results(pack_results(mine, res), n_pairs, device=device, group=group)
     pair_H = [allr[i, :9].reshape(3, 3).copy() if int(allr[i, 9]) == 0 else None for i in range(n_pairs)]
