@@ -351,14 +351,15 @@ def run_engine(a):
     h2d = Pe * 2 * 3 * npx
     # the e2e canvases are the same bytes the resident run produced (spot check: pair 0 against a fresh device canvas)
     t_ceiling = copy_ceiling(torch, dist, world, Lh, Rh, Ch, canvas_bytes[:Pe], Ld, Rd)
+    canvas_px = sum(canvas_bytes) // 3       # canvas pixels written per resident step on this rank
 
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e, wall_ms, t_ceiling], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e, wall_ms, t_ceiling = [float(x) for x in t]
-        lt = torch.tensor([launches, len(bad), h2d, d2h], device="cuda", dtype=torch.int64)
+        lt = torch.tensor([launches, len(bad), h2d, d2h, canvas_px], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt)
-        launches, nbad, h2d, d2h = [int(x) for x in lt]      # (whole job, like `value`)
+        launches, nbad, h2d, d2h, canvas_px = [int(x) for x in lt]      # (whole job, like `value`)
     else:
         nbad = len(bad)
     mp_pair = 2 * npx / 1e6
@@ -460,6 +461,7 @@ def run_engine(a):
                         "copy_ceiling": {"value": ceiling_val, "unit": UNIT, "frac": e2e_val / ceiling_val,
                                          "how": "the same H2D / D2H copies alone (both directions at once, all ranks "
                                                 "concurrently), best of 2"}},
+                "canvas_MP_per_s": canvas_px / 1e6 * a.steps / (ms_dev / 1000.0),
                 "latency": latency, "wall_ms_per_step": wall_ms / a.steps,
                 "collective": ("all_gather of %d x 96 B homography records per step (NCCL)" % n_total) if world > 1 else "none (single GPU)",
                 "roofline": roofline, "cpu_baseline": cpu}
@@ -495,6 +497,17 @@ def cpu_baseline(a, l, r, eng_res):
            "sample": "1 full pair of the workload (pair 0), the reference's OpenMP pipeline (src/openmp/main.cpp, "
                      "unmodified, -O2 -fopenmp, cvshim), %.2f s" % dt,
            "stage_ms": s["times_ms"]}
+    try:    # what the reference's own CMake flags produce (no build type = -O0; ref: CMakeLists.txt), same pair, same threads
+        if refmod.available("omp_O0"):
+            R0 = refmod.Reference("omp_O0")
+            t0 = time.perf_counter()
+            s0 = R0.stitch_pair(l, r, seed=SEED)
+            dt0 = time.perf_counter() - t0
+            out["reference_O0_build"] = {"value": mp / dt0, "unit": UNIT, "cores": R0.num_threads(), "status": s0["status"],
+                                         "sample": "the same pair, src/openmp/main.cpp compiled -O0 -fopenmp (the reference's "
+                                                   "default build), %.2f s" % dt0}
+    except Exception as e:
+        out["reference_O0_build"] = {"error": str(e)}
     try:
         S = refmod.Reference("")
         t0 = time.perf_counter(); kl = S.detect(l); kr = S.detect(r); t_det = time.perf_counter() - t0
