@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-from conftest import PKG, load_synth
+from conftest import PKG, ROOT, load_synth
 
 
 def test_numa_helpers_parse_and_degrade_gracefully():
@@ -44,3 +44,22 @@ def test_pair_result_numpy_view_matches_the_c_struct():
     assert v.shape == (3,) and v["status"][1] == 5 and v["n_matches"][1] == 77 and v["best_inliers"][1] == 9
     assert v["H"][1][4] == 2.5 and v["canvas"]["canvas_w"][2] == 123 and v["ms_total"][2] == 1.5
     assert pkg.PAIR_DTYPE.itemsize == C.sizeof(pkg.PairResult)
+
+
+def test_stall_summary_tool_reads_the_committed_source_pages():
+    """tools/ncu_stalls.py on the committed per-instruction pages: totals are consistent and the kernels'
+    signature instructions are where DESIGN.md says they are"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ncu_stalls", os.path.join(ROOT, "tools", "ncu_stalls.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    d = os.path.join(ROOT, "profiles", "r02_ncu_csv")
+    m = mod.summarise(os.path.join(d, "r02_match_tc_kernel.source_sass.csv"))
+    assert "match_tc_kernel" in m["kernel"] and m["samples"] > 500
+    assert m["opcode_executed"].get("IMAD", 0) > 0 and sum(m["stall_reason_pct"].values()) <= 100.5
+    w = mod.summarise(os.path.join(d, "r02_warp_quad_kernel.source_sass.csv"))
+    assert "warp_quad_kernel" in w["kernel"] and w["opcode_executed"].get("IDP", 0) > 0        # DP4A bilinear
+    assert w["hottest"][0]["stall"] == "stall_long_sb"                                       # tap-load latency
+    h = mod.summarise(os.path.join(d, "r02_harris_fused_kernel.source_sass.csv"))
+    assert h["opcode_executed"]["DMUL"] > 2e7 and h["opcode_executed"]["DADD"] > 2e7           # separately rounded: no DFMA
+    assert h["opcode_executed"].get("DFMA", 0) == 0
