@@ -936,7 +936,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
   if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
   // Pairs are independent: run them on several lanes (child contexts, each with its own stream,
   // scratch and host thread) so that one pair's host synchronisations, copies and low-occupancy
-  // kernels overlap with another pair's work.  PANO_BATCH_LANES (default 16, 1 = sequential); lanes beyond the
+  // kernels overlap with another pair's work.  PANO_BATCH_LANES (default 10, 1 = sequential); lanes beyond the
   // host cores poll-and-sleep instead of spinning inside the driver (t_yield_wait, set per lane thread).
   int n_lanes = 10;
   if (const char* e = getenv("PANO_BATCH_LANES")) n_lanes = atoi(e);
@@ -1097,6 +1097,9 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
                e.what);
       lane_err[li] = buf;
       cudaGetLastError();
+      lane_rc[li] = PANO_ERR_CUDA;
+    } catch (const std::exception& e) {   // (an exception leaving a std::thread would terminate the host process)
+      lane_err[li] = std::string("lane failed: ") + e.what();
       lane_rc[li] = PANO_ERR_CUDA;
     }
     t_yield_wait = 0;
