@@ -7,6 +7,9 @@ import os
 import subprocess
 import sys
 
+# ncu prints every value in a unit of its own choosing (byte / Kbyte / Mbyte, ns / us / ms): normalised to bytes and ns here
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9,
+         "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9}
 WANT = {"gpu__time_duration.sum": "duration_ns", "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor_pipe_active_pct",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "fp64_pipe_pct_active",
@@ -32,12 +35,14 @@ def main():
             for k, short in WANT.items():
                 if k in d and d[k] != "":
                     try:
-                        e[short] = float(d[k].replace(",", ""))
-                        e[short + "_unit"] = units[hdr.index(k)]
+                        unit = units[hdr.index(k)]
+                        e[short] = float(d[k].replace(",", "")) * SCALE.get(unit, 1.0)
+                        e[short + "_unit"] = {"byte": "byte", "ns": "ns"}.get(
+                            "byte" if unit.endswith("byte") else ("ns" if unit.endswith("s") and unit in SCALE else unit), unit)
                     except ValueError:
                         pass
             if "dram_read" in e and "dram_write" in e:
-                e["dram_bytes"] = e["dram_read"] + e["dram_write"]   # (units in *_unit)
+                e["dram_bytes"] = e["dram_read"] + e["dram_write"]
             e["report"] = os.path.basename(rep)
             out[name] = e
     json.dump(out, open(os.path.join("profiles", tag + "_ncu_metrics.json"), "w"), indent=1)
