@@ -81,6 +81,29 @@ def main():
                 fail("ransac status")
             if Ho is not None and not np.array_equal(np.asarray(Ho, np.float64).view(np.uint64), Hr.view(np.uint64)):
                 fail("homography bits")
+        if rng.random() < 0.25:     # other detector / matcher options (ref: HarrisCornerOptions)
+            k, th, nb, patch = (float(rng.choice([0.04, 0.06, 0.1])), float(rng.choice([1e5, 1e6, 1e7])),
+                                int(rng.choice([3, 5, 7])), int(rng.choice([1, 3, 5])))
+            ko, kq = O.detect(l, k=k, thresh=th, nbhd=nb), O.detect(r, k=k, thresh=th, nbhd=nb)
+            if not (np.array_equal(ko, R.detect(l, k=k, thresh=th, nbhd=nb)) and np.array_equal(kq, R.detect(r, k=k, thresh=th, nbhd=nb))):
+                fail("keypoints with options k=%g thresh=%g nbhd=%d" % (k, th, nb))
+            mo, mq = O.match(kq, ko, r, l, patch=patch), R.match(kq, ko, r, l, patch=patch)
+            if not (np.array_equal(mo["queryIdx"], mq["queryIdx"]) and np.array_equal(mo["trainIdx"], mq["trainIdx"])
+                    and np.array_equal(mo["distance"], mq["distance"])):
+                fail("matches with patch=%d" % patch)
+            stats["option_cases"] = stats.get("option_cases", 0) + 1
+        if kind == "pair" and rng.random() < 0.2:     # a three-image fold (ref: stitchAllImages)
+            views = synth.make_strip(n=3, w=int(rng.integers(120, 260)), h=int(rng.integers(90, 180)), seed=int(rng.integers(1, 1 << 30)))
+            po, flog = O.stitch_fold(views, seed=rs)
+            pr = R.stitch_all(views, seed=rs)
+            # (-1 = a garbage homography blew the canvas past this harness's buffer on either side: nothing to compare)
+            oversize = pr["status"] == -1 or any(f["status"] == -1 for f in flog)
+            if oversize:
+                stats["folds_oversize"] = stats.get("folds_oversize", 0) + 1
+            elif pr["status"] != 1 or not np.array_equal(po, pr["canvas"]):
+                np.savez(os.path.join(ROOT, "gpurun_out", "fuzz_fail_fold.npz"), v0=views[0], v1=views[1], v2=views[2], seed=rs)
+                fail("fold of 3 (reference status %s, shapes %s vs %s)" % (pr["status"], po.shape, None if pr["canvas"] is None else pr["canvas"].shape))
+            stats["folds"] = stats.get("folds", 0) + 1
         so, sr = O.stitch_pair(l, r, seed=rs), R.stitch_pair(l, r, seed=rs)
         if (so["status"] == 1) != (sr["status"] == 1):
             fail("stitch status %s vs %s" % (so["status"], sr["status"]))
