@@ -137,6 +137,31 @@ int pano_match(pano_ctx* ctx, const int32_t* kp_query, int n_query, const int32_
                const uint8_t* img_train, int wt, int ht, size_t stride_t, int mem,
                const pano_harris_opts* opts, int offset, pano_dmatch* out, int cap, int* count);
 
+/* ---- 2-nearest-neighbour matching with Lowe's ratio test (north star item (c)); opt-in -----------------
+ * NOT the reference's matcher and never used by pano_stitch_*: the reference keeps the single nearest patch
+ * under a fixed SSD threshold (pano_match above).  Same candidates (in-border keypoints of both sides), same
+ * tie rule extended to the runner-up: neighbours are ordered by (distance, position in the train list).
+ *  PANO_KNN_PATCH_SSD  the path's raw BGR patch; distance = exact SSD (what pano_match reports); tensor-core
+ *                      distance GEMM with a fused top-2 epilogue (tcgen05), or the SIMT kernel under
+ *                      pano_set_matcher(ctx, 1).  Test on L2 distances: ssd1 < ratio^2 * ssd2.
+ *  PANO_KNN_BINARY     256-bit intensity-comparison descriptor of the 5 x 5 gray patch (bit k compares the two
+ *                      positions of pair number 37 k mod 300 of the 300 position pairs); distance = Hamming
+ *                      (XOR + popcount, warp-shuffle reduction).  Test: h1 < ratio * h2.
+ * A query whose train side offers fewer than two candidates yields no match. */
+enum { PANO_KNN_PATCH_SSD = 0, PANO_KNN_BINARY = 1 };
+typedef struct {
+  int patch_size;           /* 5 (patch descriptor: 1, 3 or 5; binary descriptor: 5 only) */
+  int descriptor;           /* PANO_KNN_PATCH_SSD */
+  double ratio;             /* 0.75 (0 < ratio <= 1) */
+} pano_knn_opts;
+void pano_default_knn_opts(pano_knn_opts* o);
+/* Writes min(*count, cap) matches in ascending query order: (query_idx, train_idx of the nearest neighbour,
+ * its distance); second_out (may be NULL) receives the runner-up's distance of each written match. */
+int pano_match_knn(pano_ctx* ctx, const int32_t* kp_query, int n_query, const int32_t* kp_train,
+                   int n_train, const uint8_t* img_query, int wq, int hq, size_t stride_q,
+                   const uint8_t* img_train, int wt, int ht, size_t stride_t, int mem,
+                   const pano_knn_opts* opts, pano_dmatch* out, float* second_out, int cap, int* count);
+
 /* ref: GpuRansacHomographyCalculator::computeHomography(kp1, kp2, matches)
  *      (src/gpu/ransac.cuh:8-36) with the semantics of
  *      SeqRansacHomographyCalculator::computeHomography (src/serial/main.cpp:247-307).

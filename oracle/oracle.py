@@ -104,6 +104,28 @@ class Oracle:
                                patch, C.c_double(max_ssd), offset, out.ctypes.data_as(C.c_void_p), len(out))
         return out[:n]
 
+    def match_knn(self, kq, kt, imq, imt, patch=5, descriptor=0, ratio=0.75):
+        """checker of the engine's opt-in pano_match_knn (2-NN + Lowe's ratio; NOT a reference function).
+        Returns (matches, runner-up distances)."""
+        imq, imt = self._img(imq), self._img(imt)
+        kq = np.ascontiguousarray(kq, np.int32).reshape(-1, 2)
+        kt = np.ascontiguousarray(kt, np.int32).reshape(-1, 2)
+        out = np.empty(max(len(kq), 1), MATCH_DTYPE)
+        second = np.empty(max(len(kq), 1), np.float32)
+        self.lib.orc_match_knn.restype = C.c_int
+        n = self.lib.orc_match_knn(_p(kq, C.c_int32), len(kq), _p(kt, C.c_int32), len(kt),
+                                   _p(imq, C.c_uint8), imq.shape[1], imq.shape[0], C.c_size_t(imq.strides[0]),
+                                   _p(imt, C.c_uint8), imt.shape[1], imt.shape[0], C.c_size_t(imt.strides[0]),
+                                   patch, descriptor, C.c_double(ratio), out.ctypes.data_as(C.c_void_p),
+                                   _p(second, C.c_float), len(out))
+        return out[:n], second[:n]
+
+    def knn_binary_descriptor(self, img, x, y):
+        img = self._img(img)
+        bits = np.zeros(8, np.uint32)
+        self.lib.orc_knn_binary_descriptor(_p(img, C.c_uint8), C.c_size_t(img.strides[0]), int(x), int(y), _p(bits, C.c_uint32))
+        return bits
+
     def find_homography4(self, src, dst):
         src = np.ascontiguousarray(src, np.float32).reshape(4, 2)
         dst = np.ascontiguousarray(dst, np.float32).reshape(4, 2)

@@ -195,6 +195,88 @@ void match_keypoints(const int32_t* kq, int nq, const int32_t* kt, int nt,
 }
 
 
+// ---- NOT the reference: checker of the engine's opt-in pano_match_knn (north star item (c)) ----------------------
+// The published algorithm it restates is OpenCV's BFMatcher::knnMatch(k = 2) followed by Lowe's ratio test
+// (Lowe 2004; the OpenCV feature-matching tutorial), on the candidates and with the tie rule of the reference's
+// matcher above: in-border keypoints only, neighbours ordered by (distance, position in the train list).
+// descriptor 0: the reference's patch, distance = SSD (exact), test  (double)ssd1 < (ratio * ratio) * (double)ssd2,
+//              i.e. d1 < ratio * d2 on the L2 distances.
+// descriptor 1: 256-bit intensity-comparison descriptor of the 5 x 5 gray patch (gray = cvtColor's formula): bit k =
+//              gray[a] < gray[b] for pair number (37 k mod 300) of the lexicographic list of the 300 position pairs
+//              a < b (positions row-major); distance = Hamming; test  (double)h1 < ratio * (double)h2.
+// Pinned against real cv2.BFMatcher (NORM_L2SQR / NORM_HAMMING) in tests/test_knn.py.
+struct KnnMatch { int32_t queryIdx, trainIdx; float distance, second; };
+
+void knn_binary_descriptor(const uint8_t* im, size_t stride, int x, int y, uint32_t* bits) {
+  static std::vector<std::pair<int, int>> pairs;
+  if (pairs.empty())
+    for (int a = 0; a < 25; a++)
+      for (int b = a + 1; b < 25; b++) pairs.push_back({a, b});
+  int g[25];
+  for (int dy = -2; dy <= 2; dy++)
+    for (int dx = -2; dx <= 2; dx++) {
+      const uint8_t* p = im + (size_t)(y + dy) * stride + 3 * (size_t)(x + dx);
+      g[(dy + 2) * 5 + dx + 2] = (p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15;
+    }
+  for (int w = 0; w < 8; w++) bits[w] = 0;
+  for (int k = 0; k < 256; k++) {
+    const std::pair<int, int>& pr = pairs[(size_t)((37 * k) % 300)];
+    if (g[pr.first] < g[pr.second]) bits[k >> 5] |= 1u << (k & 31);
+  }
+}
+
+void match_knn(const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8_t* imq, int wq, int hq, size_t sq,
+               const uint8_t* imt, int wt, int ht, size_t st, int patch, int descriptor, double ratio,
+               std::vector<KnnMatch>& out) {
+  const int border = patch / 2, plen = patch * patch * 3;
+  const int dlen = descriptor == 1 ? 32 : plen;   // bytes per descriptor
+  auto describe = [&](const uint8_t* im, size_t stride, int x, int y, uint8_t* d) {
+    if (descriptor == 1) {
+      uint32_t bits[8];
+      knn_binary_descriptor(im, stride, x, y, bits);
+      memcpy(d, bits, 32);
+    } else {
+      for (int dy = -border; dy <= border; dy++)
+        for (int dx = -border; dx <= border; dx++)
+          for (int c = 0; c < 3; c++) *d++ = im[(size_t)(y + dy) * stride + 3 * (x + dx) + c];
+    }
+  };
+  auto distance = [&](const uint8_t* a, const uint8_t* b) -> uint32_t {
+    uint32_t s = 0;
+    if (descriptor == 1) {
+      for (int e = 0; e < 32; e++) s += (uint32_t)__builtin_popcount((unsigned)(a[e] ^ b[e]));
+    } else {
+      for (int e = 0; e < plen; e++) { const int d = (int)a[e] - (int)b[e]; s += (uint32_t)(d * d); }
+    }
+    return s;
+  };
+  std::vector<int> tj;
+  std::vector<uint8_t> tp;
+  for (int j = 0; j < nt; j++) {
+    const int x = kt[2 * j], y = kt[2 * j + 1];
+    if (x < border || y < border || x + border >= wt || y + border >= ht) continue;
+    tj.push_back(j);
+    tp.resize(tp.size() + dlen);
+    describe(imt, st, x, y, &tp[tp.size() - dlen]);
+  }
+  const double factor = descriptor == 1 ? ratio : ratio * ratio;
+  std::vector<uint8_t> qp((size_t)dlen);
+  for (int i = 0; i < nq; i++) {
+    const int x = kq[2 * i], y = kq[2 * i + 1];
+    if (x < border || y < border || x + border >= wq || y + border >= hq) continue;
+    describe(imq, sq, x, y, qp.data());
+    int j1 = -1, j2 = -1;
+    uint32_t d1 = 0, d2 = 0;
+    for (size_t jj = 0; jj < tj.size(); jj++) {   // strict '<' twice: the earlier train keypoint keeps its rank on ties
+      const uint32_t d = distance(qp.data(), &tp[jj * dlen]);
+      if (j1 < 0 || d < d1) { j2 = j1; d2 = d1; j1 = (int)jj; d1 = d; }
+      else if (j2 < 0 || d < d2) { j2 = (int)jj; d2 = d; }
+    }
+    if (j2 < 0) continue;   // fewer than two candidates: no runner-up, no match
+    if ((double)d1 < factor * (double)d2) out.push_back(KnnMatch{i, tj[(size_t)j1], (float)d1, (float)d2});
+  }
+}
+
 // Inlier predicate of ref: src/serial/main.cpp:285-293.
 //   pt2Transformed = H * (x, y, 1)      -> gemm small path, (h0*x + h1*y) + h2*1
 //   pt2Transformed /= w                  -> Mat::convertTo(-1, 1./w): multiply by reciprocal
@@ -390,6 +472,25 @@ int orc_match(const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8_
   int n = (int)v.size();
   if (out) memcpy(out, v.data(), sizeof(Match) * (size_t)std::min(n, cap));
   return n;
+}
+
+// checker of pano_match_knn (not a reference function; see match_knn above).  second[] = runner-up distances.
+int orc_match_knn(const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8_t* imq, int wq, int hq, size_t sq,
+                  const uint8_t* imt, int wt, int ht, size_t st, int patch, int descriptor, double ratio,
+                  orc_dmatch* out, float* second, int cap) {
+  std::vector<KnnMatch> v;
+  match_knn(kq, nq, kt, nt, imq, wq, hq, sq, imt, wt, ht, st, patch, descriptor, ratio, v);
+  const int n = (int)v.size();
+  for (int i = 0; i < std::min(n, cap); i++) {
+    if (out) out[i] = orc_dmatch{v[(size_t)i].queryIdx, v[(size_t)i].trainIdx, v[(size_t)i].distance};
+    if (second) second[i] = v[(size_t)i].second;
+  }
+  return n;
+}
+
+// the 256-bit descriptor of one keypoint (8 words), for the descriptor-level tests
+void orc_knn_binary_descriptor(const uint8_t* im, size_t stride, int x, int y, uint32_t* bits) {
+  knn_binary_descriptor(im, stride, x, y, bits);
 }
 
 // cv::eigen(A symmetric n x n) -> W (descending), V (rows).  A is not modified.

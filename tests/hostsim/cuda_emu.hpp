@@ -1,0 +1,247 @@
+// cuda_emu.hpp — a small CPU emulation of the CUDA execution model, for the no-GPU test tier.
+//
+// TEST INFRASTRUCTURE ONLY (never linked into the product).  It lets g++ compile a header of real __global__
+// kernels (csrc/knn_kernels.cuh) unchanged and run them block by block on the host:
+//   * every CUDA thread of a block is a fiber (ucontext) with its own stack; threadIdx / blockIdx / blockDim /
+//     gridDim are globals that the scheduler sets whenever it resumes a fiber;
+//   * __syncthreads() and the warp collectives (__shfl_sync, __shfl_xor_sync, __shfl_down_sync, __ballot_sync,
+//     __syncwarp) are REAL rendezvous points: a fiber yields until every live participant has arrived, values are
+//     exchanged through per-warp slots.  A barrier that can never complete (divergent participants) is reported as
+//     an error instead of hanging;
+//   * __shared__ becomes `static` (blocks run one after another); a thread that returns early counts as "exited"
+//     for later barriers, as on the hardware;
+//   * atomics are plain read-modify-write (one fiber runs at a time); blocks of a grid run in the order given by
+//     emu::Launch::block_order (forward, reverse or shuffled) so that order-dependent results show up.
+// What it cannot show: data races between threads of a warp that the hardware runs in lockstep, memory-model
+// effects, launch-configuration limits (registers, shared memory) - ptxas -v and the GPU tier cover those.
+#pragma once
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#define PANO_CUDA_EMU 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+
+struct uint4 {
+  uint32_t x, y, z, w;
+} __attribute__((aligned(16)));
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+struct int4 {
+  int x, y, z, w;
+} __attribute__((aligned(16)));
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct emu_idx {
+  unsigned x, y, z;
+};
+inline emu_idx threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+
+using std::max;
+using std::min;
+
+namespace emu {
+
+struct Fiber {
+  ucontext_t ctx;
+  std::vector<char> stack;
+  bool done = false;
+  unsigned tid = 0;
+};
+
+struct Warp {
+  unsigned arrived = 0;   // lanes waiting at the current warp rendezvous
+  unsigned gen = 0;
+  unsigned alive = 0;
+  uint64_t slot[32];
+};
+
+struct State {
+  ucontext_t sched;
+  std::vector<Fiber> fibers;
+  std::vector<Warp> warps;
+  Fiber* cur = nullptr;
+  unsigned block_arrived = 0, block_gen = 0, live = 0;
+  std::function<void()> body;
+  const char* error = nullptr;
+  uint64_t progress = 0;
+};
+inline State* S = nullptr;
+
+inline void yield() { swapcontext(&S->cur->ctx, &S->sched); }
+
+inline void trampoline() {
+  S->body();
+  Fiber* f = S->cur;
+  f->done = true;
+  S->live--;
+  S->warps[f->tid >> 5].alive &= ~(1u << (f->tid & 31));
+  S->progress++;
+  swapcontext(&f->ctx, &S->sched);
+}
+
+inline void sync_block() {
+  State& s = *S;
+  const unsigned gen = s.block_gen;
+  s.block_arrived++;
+  s.progress++;
+  // (exited threads no longer count: the barrier completes when every live thread has arrived)
+  while (s.block_gen == gen) {
+    if (s.block_arrived >= s.live) { s.block_arrived = 0; s.block_gen++; s.progress++; break; }
+    yield();
+  }
+}
+
+inline void sync_warp(unsigned mask) {
+  State& s = *S;
+  Warp& w = s.warps[s.cur->tid >> 5];
+  const unsigned lane = s.cur->tid & 31;
+  const unsigned gen = w.gen;
+  w.arrived |= 1u << lane;
+  s.progress++;
+  while (w.gen == gen) {
+    if ((w.arrived & mask) == (mask & w.alive)) { w.arrived &= ~mask; w.gen++; s.progress++; break; }
+    yield();
+  }
+}
+
+template <typename T>
+inline T exchange(unsigned mask, T v, unsigned src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+  State& s = *S;
+  Warp& w = s.warps[s.cur->tid >> 5];
+  const unsigned lane = s.cur->tid & 31;
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  w.slot[lane] = raw;
+  sync_warp(mask);
+  // a source lane outside the mask / already exited returns the caller's own value (undefined on hardware)
+  uint64_t got = ((mask >> (src_lane & 31)) & 1u) && ((w.alive >> (src_lane & 31)) & 1u) ? w.slot[src_lane & 31] : raw;
+  sync_warp(mask);   // nobody overwrites a slot before everyone has read
+  T out;
+  memcpy(&out, &got, sizeof(T));
+  return out;
+}
+
+enum Order { FORWARD = 0, REVERSE = 1, SHUFFLED = 2 };
+
+// runs `body` (a call of a __global__ function) for every thread of every block of the grid
+inline const char* launch(dim3 grid, dim3 block, const std::function<void()>& body, int order = FORWARD,
+                          size_t stack_bytes = 256 * 1024) {
+  const unsigned nthreads = block.x * block.y * block.z;
+  State st;
+  S = &st;
+  st.body = body;
+  gridDim = grid;
+  blockDim = block;
+  std::vector<unsigned> blocks(grid.x * grid.y * grid.z);
+  for (unsigned i = 0; i < blocks.size(); i++) blocks[i] = i;
+  if (order == REVERSE) std::reverse(blocks.begin(), blocks.end());
+  if (order == SHUFFLED) {
+    uint32_t x = 2463534242u;
+    for (size_t i = blocks.size(); i > 1; i--) {
+      x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+      std::swap(blocks[i - 1], blocks[x % i]);
+    }
+  }
+  st.fibers.resize(nthreads);
+  for (auto& f : st.fibers) f.stack.resize(stack_bytes);
+  for (unsigned b : blocks) {
+    const emu_idx bi = {b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y)};
+    st.warps.assign((nthreads + 31) / 32, Warp());
+    st.block_arrived = 0;
+    st.live = nthreads;
+    for (unsigned t = 0; t < nthreads; t++) {
+      Fiber& f = st.fibers[t];
+      f.done = false;
+      f.tid = t;
+      st.warps[t >> 5].alive |= 1u << (t & 31);
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = f.stack.data();
+      f.ctx.uc_stack.ss_size = f.stack.size();
+      f.ctx.uc_link = &st.sched;
+      makecontext(&f.ctx, (void (*)())trampoline, 0);
+    }
+    while (st.live > 0) {
+      const uint64_t before = st.progress;
+      for (unsigned t = 0; t < nthreads; t++) {
+        Fiber& f = st.fibers[t];
+        if (f.done) continue;
+        st.cur = &f;
+        threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+        blockIdx = bi;
+        swapcontext(&st.sched, &f.ctx);
+      }
+      if (st.progress == before && st.live > 0) {   // a full round in which nobody moved: a barrier cannot complete
+        st.error = "deadlock: a barrier / warp collective is waiting for threads that never arrive";
+        S = nullptr;
+        return st.error;
+      }
+    }
+  }
+  S = nullptr;
+  return nullptr;
+}
+
+}  // namespace emu
+
+// ---- the CUDA device API surface the kernels use -----------------------------------------------------------------
+inline void __syncthreads() { emu::sync_block(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::sync_warp(mask); }
+template <typename T>
+inline T __shfl_sync(unsigned mask, T v, int src_lane) { return emu::exchange(mask, v, (unsigned)src_lane); }
+template <typename T>
+inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) {
+  return emu::exchange(mask, v, (emu::S->cur->tid & 31) ^ (unsigned)lane_mask);
+}
+template <typename T>
+inline T __shfl_down_sync(unsigned mask, T v, unsigned delta) {
+  const unsigned lane = emu::S->cur->tid & 31;
+  return emu::exchange(mask, v, lane + delta < 32 ? lane + delta : lane);
+}
+inline unsigned __ballot_sync(unsigned mask, int pred) {
+  unsigned r = 0;
+  for (unsigned l = 0; l < 32; l++) {   // 32 exchanges: slow and simple
+    const int p = emu::exchange(mask, pred, l);
+    if (((mask >> l) & 1u) && p) r |= 1u << l;
+  }
+  return r;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __vabsdiffu4(unsigned a, unsigned b) {
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++) {
+    const int x = (a >> (8 * i)) & 255, y = (b >> (8 * i)) & 255;
+    r |= (unsigned)(x > y ? x - y : y - x) << (8 * i);
+  }
+  return r;
+}
+inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+  for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 255) * ((b >> (8 * i)) & 255);
+  return c;
+}
+inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
+  const unsigned long long old = *p;
+  if (v < old) *p = v;
+  return old;
+}
+inline int atomicOr(int* p, int v) {
+  const int old = *p;
+  *p = old | v;
+  return old;
+}

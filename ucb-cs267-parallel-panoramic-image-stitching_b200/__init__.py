@@ -46,7 +46,19 @@ EXPORTED_SYMBOLS = [
     "pano_stitch_fold", "pano_stitch_batch", "pano_stream", "pano_pair_homography", "pano_mul33",
     "pano_chain_geometry", "pano_warp_accumulate", "pano_set_stream", "pano_set_replay_mode",
     "pano_set_fold_mode", "pano_stitch_pair_async", "pano_pair_query", "pano_pair_wait", "pano_set_profile", "pano_get_profile",
+    "pano_default_knn_opts", "pano_match_knn",
 ]
+
+
+KNN_PATCH_SSD, KNN_BINARY = 0, 1
+
+
+class KnnOptions(C.Structure):
+    """pano_knn_opts (opt-in 2-NN / Lowe-ratio matcher; include/pano_b200.h)"""
+    _fields_ = [("patchSize_", C.c_int), ("descriptor_", C.c_int), ("ratio_", C.c_double)]
+
+    def __init__(self, patchSize_=5, descriptor_=0, ratio_=0.75):
+        super().__init__(patchSize_, descriptor_, ratio_)
 
 
 class HarrisCornerOptions(C.Structure):
@@ -245,6 +257,24 @@ class Engine:
                                         C.byref(opts), int(offset), out.ctypes.data_as(C.c_void_p), len(out),
                                         C.byref(count)))
         return out[:count.value]
+
+    def matchKnn(self, keypointsQ, keypointsT, imageQ, imageT, patchSize=5, descriptor=KNN_PATCH_SSD, ratio=0.75):
+        """Opt-in 2-nearest-neighbour matching with Lowe's ratio test (north star item (c); NOT the reference's
+        matcher, which is gpuHarrisMatchKeyPoints).  Returns (matches, runner-up distances)."""
+        kq = np.ascontiguousarray(keypointsQ, np.int32).reshape(-1, 2)
+        kt = np.ascontiguousarray(keypointsT, np.int32).reshape(-1, 2)
+        iq, it = _Img(imageQ), _Img(imageT)
+        assert iq.mem == MEM_HOST and it.mem == MEM_HOST
+        opts = KnnOptions(patchSize_=patchSize, descriptor_=descriptor, ratio_=ratio)
+        out = np.empty(max(len(kq), 1), MATCH_DTYPE)
+        second = np.empty(max(len(kq), 1), np.float32)
+        count = C.c_int(0)
+        self._check(self.lib.pano_match_knn(self.ctx, kq.ctypes.data_as(C.c_void_p), len(kq),
+                                            kt.ctypes.data_as(C.c_void_p), len(kt), iq.ptr, iq.w, iq.h,
+                                            C.c_size_t(iq.stride), it.ptr, it.w, it.h, C.c_size_t(it.stride), MEM_HOST,
+                                            C.byref(opts), out.ctypes.data_as(C.c_void_p),
+                                            second.ctypes.data_as(C.c_void_p), len(out), C.byref(count)))
+        return out[:count.value], second[:count.value]
 
     def computeHomography(self, keypoints1, keypoints2, matches, options=None, details=False):
         """GpuRansacHomographyCalculator::computeHomography.  Returns H (3x3) or None (the

@@ -223,8 +223,9 @@ int build_descriptors_device(cudaStream_t st, const DevImage& img, const int32_t
 // best[i] = (ssd << 32 | j) over all train descriptors, lowest j on ties
 void match_simt_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
                        unsigned long long* best);
+// best2 != nullptr: the top-2 variant (pano_match_knn) - nearest neighbour in best, runner-up in best2
 void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
-                     unsigned long long* best, DevBuf& keybuf, int* errw);
+                     unsigned long long* best, DevBuf& keybuf, int* errw, unsigned long long* best2 = nullptr);
 bool match_tc_available();
 void match_tc_disable();
 // 2-D byte tensor map (CUtensorMap, 128 bytes) over a pitched image for TMA tile loads; false if not describable
@@ -234,6 +235,15 @@ bool make_tmap_bytes_2d(void* map_out, const void* base, size_t row_bytes, size_
 int emit_matches_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t,
                         const unsigned long long* best, double max_ssd, int offset, int patch,
                         MatchScratch& s, pano_dmatch* out_dev, PinnedBuf& pin, int* errw);
+
+// opt-in 2-NN / Lowe-ratio matcher (knn.cu; semantics in knn_core.cuh)
+struct KnnScratch {
+  DevBuf best2, qbits, tbits, rec, second, out, out2, flags, idx, cnt, tmp;
+};
+// matches (ascending query order) are left in ks.out (records) / ks.out2 (runner-up distances); returns the count
+int match_knn_device(cudaStream_t st, const DevImage& iq, const DevImage& it, const int32_t* kq, const int32_t* kt,
+                     const DevDescriptors& q, const DevDescriptors& t, const pano_knn_opts& o, bool use_tc,
+                     MatchScratch& ms, DevBuf& best1, KnnScratch& ks, PinnedBuf& pin, int* errw);
 
 struct MtStream;
 void update_pano_keypoints_device(cudaStream_t st, const int32_t* old_xy, int n_old, int offx, int offy, const int32_t* new_xy,

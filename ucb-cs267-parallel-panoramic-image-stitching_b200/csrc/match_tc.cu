@@ -34,6 +34,7 @@
 // m - NSTAGE have completed, which needed every epilogue of unit m - NSTAGE - 1 to have released its accumulator.
 // Every wait is bounded: a bring-up bug raises an error flag instead of hanging the device.
 #include "common.cuh"
+#include "knn_core.cuh"
 
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 
@@ -169,6 +170,18 @@ __device__ __forceinline__ void chunk_min(const int4* __restrict__ cv, const uin
   }
 }
 
+// the same with the runner-up of each chain (top-2 epilogue of pano_match_knn): 1 IMAD + 3 VIMNMX per element
+__device__ __forceinline__ void chunk_min2(const int4* __restrict__ cv, const uint32_t (&acc)[32], int (&km)[4], int (&ks)[4]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int4 c4 = cv[i];
+    top2_insert_i32(km[0], ks[0], (int)((uint32_t)c4.x - 512u * acc[4 * i]));
+    top2_insert_i32(km[1], ks[1], (int)((uint32_t)c4.y - 512u * acc[4 * i + 1]));
+    top2_insert_i32(km[2], ks[2], (int)((uint32_t)c4.z - 512u * acc[4 * i + 2]));
+    top2_insert_i32(km[3], ks[3], (int)((uint32_t)c4.w - 512u * acc[4 * i + 3]));
+  }
+}
+
 // the CTA's next run of units inside one super-row: units [unit, unit + n) of the flattened grid
 struct Seg { int sr, t0, t1; };
 __device__ __forceinline__ Seg next_seg(int unit, int hi, int n_ttiles) {
@@ -179,10 +192,14 @@ __device__ __forceinline__ Seg next_seg(int unit, int hi, int n_ttiles) {
   return g;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
-                const uint32_t* __restrict__ qn, int nq, const int* __restrict__ tkey, int nt, int n_qtiles, int n_ttiles,
-                int n_units, unsigned long long* __restrict__ best, int* __restrict__ err) {
+// TOP2 = false: the reference's matcher (nearest neighbour only; `best2` unused).  TOP2 = true: pano_match_knn's
+// variant - the epilogue also keeps the runner-up of every query row and publishes both (knn_publish).  Pipeline,
+// barriers and tensor-memory traffic are the same; only the per-element reduction and the final atomics differ.
+template <bool TOP2>
+__device__ __forceinline__ void match_tc_body(const CUtensorMap& tmap_q, const CUtensorMap& tmap_t,
+                                              const uint32_t* __restrict__ qn, int nq, const int* __restrict__ tkey, int nt,
+                                              int n_qtiles, int n_ttiles, int n_units, unsigned long long* __restrict__ best,
+                                              unsigned long long* __restrict__ best2, int* __restrict__ err) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // keep the pointer in the shared address space (LDS/STS, not generic loads)
   Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -249,6 +266,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int qrow = qt * TM + ((int)threadIdx.x & 127);
       const int myqn = qrow < nq ? (int)qn[qrow] : 0;
       int best_ssd = 0x7fffffff, best_j = -1;
+      Top2 top = top2_empty();   // (TOP2 only)
       for (int tt = sg.t0; tt < sg.t1 && ok; tt++, unit_ctr++, use_ctr++) {
         const uint32_t s = unit_ctr % NSTAGE, sph = (unit_ctr / NSTAGE) & 1u;
         const uint32_t cs = unit_ctr % NCV;
@@ -273,6 +291,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * TN);
         const int4* cv = reinterpret_cast<const int4*>(&S.cvec[cs][0]);
         int km0 = 0x7fffffff, km1 = 0x7fffffff, km2 = 0x7fffffff, km3 = 0x7fffffff;
+        int km[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff}, ks[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
         // two register buffers: the tcgen05.ld of chunk c + 1 is in flight while chunk c is reduced
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
@@ -280,22 +299,35 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int cb = 0; cb < TN / 32; cb += 2) {
           tmem_ld32(taddr + (cb + 1) * 32, rb);
-          chunk_min(cv + cb * 8, ra, km0, km1, km2, km3);
+          if constexpr (TOP2) chunk_min2(cv + cb * 8, ra, km, ks);
+          else chunk_min(cv + cb * 8, ra, km0, km1, km2, km3);
           tmem_ld_wait();
           if (cb + 2 < TN / 32) tmem_ld32(taddr + (cb + 2) * 32, ra);
-          chunk_min(cv + (cb + 1) * 8, rb, km0, km1, km2, km3);
+          if constexpr (TOP2) chunk_min2(cv + (cb + 1) * 8, rb, km, ks);
+          else chunk_min(cv + (cb + 1) * 8, rb, km0, km1, km2, km3);
           tmem_ld_wait();
         }
         tc_fence_before();
         // the group's 128 threads have read the accumulator: its leader may overwrite it (named barrier 1 + g)
         asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory");
-        const int kmin = min(min(km0, km1), min(km2, km3));
-        const int v = kmin >> 8, jl = kmin & 255;
-        const int ssd = v + myqn;
-        if (kmin != 0x7fffffff && ssd < best_ssd) { best_ssd = ssd; best_j = tt * TN + jl; }
+        if constexpr (TOP2) {
+          // the tile's two smallest keys out of the four chains' (valid keys of a tile are distinct: the column sits
+          // in their low bits; 0x7fffffff = padding column / nothing), then into the row's running pair in
+          // (SSD, train index) order - tiles come in train order, so earlier columns win ties as in the reference
+          knn_fold_tile(top, km, ks, myqn, tt * TN);
+        } else {
+          const int kmin = min(min(km0, km1), min(km2, km3));
+          const int v = kmin >> 8, jl = kmin & 255;
+          const int ssd = v + myqn;
+          if (kmin != 0x7fffffff && ssd < best_ssd) { best_ssd = ssd; best_j = tt * TN + jl; }
+        }
       }
-      if (ok && qrow < nq && best_j >= 0 && best_j < nt)
-        atomicMin(&best[qrow], ((unsigned long long)(uint32_t)best_ssd << 32) | (uint32_t)best_j);
+      if constexpr (TOP2) {
+        if (ok && qrow < nq) knn_publish(best, best2, qrow, top);
+      } else {
+        if (ok && qrow < nq && best_j >= 0 && best_j < nt)
+          atomicMin(&best[qrow], ((unsigned long long)(uint32_t)best_ssd << 32) | (uint32_t)best_j);
+      }
     }
   } else if (warp == EPI_WARPS) {
     // ================= producer: TMA tile loads + bulk copies of the column constants =================
@@ -332,6 +364,22 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == EPI_WARPS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+match_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
+                const uint32_t* __restrict__ qn, int nq, const int* __restrict__ tkey, int nt, int n_qtiles, int n_ttiles,
+                int n_units, unsigned long long* __restrict__ best, int* __restrict__ err) {
+  match_tc_body<false>(tmap_q, tmap_t, qn, nq, tkey, nt, n_qtiles, n_ttiles, n_units, best, nullptr, err);
+}
+
+// pano_match_knn: nearest neighbour and runner-up of every query row (keys (ssd << 32 | j) in best / best2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
+match_tc_top2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t,
+                     const uint32_t* __restrict__ qn, int nq, const int* __restrict__ tkey, int nt, int n_qtiles,
+                     int n_ttiles, int n_units, unsigned long long* __restrict__ best,
+                     unsigned long long* __restrict__ best2, int* __restrict__ err) {
+  match_tc_body<true>(tmap_q, tmap_t, qn, nq, tkey, nt, n_qtiles, n_ttiles, n_units, best, best2, err);
 }
 
 // column constants of the train side: |t_j|^2 * 256 + (j mod 256); INT_MAX for the padding columns
@@ -397,8 +445,9 @@ bool make_tmap_bytes_2d(void* map_out, const void* base, size_t row_bytes, size_
 }
 
 void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescriptors& t, unsigned long long* best,
-                     DevBuf& keybuf, int* errw) {
+                     DevBuf& keybuf, int* errw, unsigned long long* best2) {
   PANO_CUDA(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * (size_t)q.count, st));
+  if (best2) PANO_CUDA(cudaMemsetAsync(best2, 0xff, sizeof(unsigned long long) * (size_t)q.count, st));
   if (q.count == 0 || t.count == 0) return;
   const int n_qtiles = (q.count + TM - 1) / TM;
   const int n_ttiles = (t.count + TN - 1) / TN;
@@ -428,7 +477,15 @@ void match_tc_device(cudaStream_t st, const DevDescriptors& q, const DevDescript
   make_tmap(&tmap_t, t.desc.p, ((size_t)t.count + 255) / 256 * 256, TN);
   // A CTA whose pipeline wait gives up ORs PANO_ERRW_TC_ABORT into the context's error word; the host sees it
   // with the next result it waits for (every call, not only the first), fails the call and disables this path.
-  {
+  if (best2) {
+    static const bool attr2_set = [&] {   // (kept apart from the default kernel's set-up: the opt-in variant cannot fail it)
+      PANO_CUDA(cudaFuncSetAttribute(match_tc_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      return true;
+    }();
+    (void)attr2_set;
+    match_tc_top2_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_t, q.norm.as<uint32_t>(), q.count, tkey, t.count,
+                                                         n_qtiles, n_ttiles, n_units, best, best2, errw);
+  } else {
     ProfScope ps(PROF_MATCH_TC, st);
     match_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmap_q, tmap_t, q.norm.as<uint32_t>(), q.count,
                                                     tkey, t.count, n_qtiles, n_ttiles, n_units, best, errw);

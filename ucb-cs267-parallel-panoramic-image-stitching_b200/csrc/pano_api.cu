@@ -46,6 +46,7 @@ struct pano_ctx {
   HarrisScratch hs;
   DevKeypoints kpL, kpR;
   MatchScratch ms;
+  KnnScratch ks;     // pano_match_knn only
   DevDescriptors dQ, dT;
   DevBuf best, matches;
   RansacScratch rs;
@@ -396,6 +397,12 @@ void pano_default_harris_opts(pano_harris_opts* o) {
   o->max_ssd_thresh = 1e8;
 }
 
+void pano_default_knn_opts(pano_knn_opts* o) {
+  o->patch_size = 5;
+  o->descriptor = PANO_KNN_PATCH_SSD;
+  o->ratio = 0.75;
+}
+
 void pano_default_ransac_opts(pano_ransac_opts* o) {
   o->num_iterations = 1000;
   o->num_samples = 4;
@@ -466,7 +473,8 @@ void pano_destroy(pano_ctx* c) {
                     &c->dT.desc, &c->dT.norm, &c->dT.orig, &c->best, &c->matches, &c->rs.pts, &c->rs.thr,
                     &c->rs.cand_off, &c->rs.cand_samp, &c->rs.base, &c->rs.samples, &c->rs.Hs, &c->rs.valid,
                     &c->rs.counts, &c->rs.result, &c->rs.mask, &c->rs.plan, &c->rs.pts_bits, &c->mt.x, &c->mt.state, &c->tmp[0],
-                    &c->tmp[1], &c->tmp[2], &c->canvas[0], &c->canvas[1], &c->tight};
+                    &c->tmp[1], &c->tmp[2], &c->canvas[0], &c->canvas[1], &c->tight, &c->ks.best2, &c->ks.qbits, &c->ks.tbits,
+                    &c->ks.rec, &c->ks.second, &c->ks.out, &c->ks.out2, &c->ks.flags, &c->ks.idx, &c->ks.cnt, &c->ks.tmp};
   for (DevBuf* b : bufs) b->release();
   c->pin.release();
   for (auto& e : c->ev)
@@ -578,6 +586,43 @@ int pano_match(pano_ctx* c, const int32_t* kp_query, int n_query, const int32_t*
   if (out && ncopy > 0)
     PANO_CUDA(cudaMemcpyAsync(out, c->matches.p, sizeof(pano_dmatch) * (size_t)ncopy,
                               mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->st));
+  if (int ew = wait_errw(c)) return fail_errw(c, ew);
+  return (out && m > cap) ? PANO_ERR_CAPACITY : PANO_OK;
+  API_CATCH(c)
+}
+
+// north star item (c), opt-in: 2 nearest neighbours + Lowe's ratio test (knn.cu).  Not the reference's matcher.
+int pano_match_knn(pano_ctx* c, const int32_t* kp_query, int n_query, const int32_t* kp_train, int n_train,
+                   const uint8_t* img_query, int wq, int hq, size_t stride_q, const uint8_t* img_train, int wt, int ht,
+                   size_t stride_t, int mem, const pano_knn_opts* opts, pano_dmatch* out, float* second_out, int cap,
+                   int* count) {
+  API_TRY(c)
+  if (!valid_image(img_query, wq, hq, stride_q) || !valid_image(img_train, wt, ht, stride_t) || !opts || !count ||
+      n_query < 0 || n_train < 0 || (n_query > 0 && !kp_query) || (n_train > 0 && !kp_train) || cap < 0)
+    return fail(c, PANO_ERR_INVALID, "pano_match_knn: bad argument");
+  if (!(opts->ratio > 0.0) || opts->ratio > 1.0) return fail(c, PANO_ERR_INVALID, "pano_match_knn: ratio outside (0, 1]");
+  if (opts->descriptor != PANO_KNN_PATCH_SSD && opts->descriptor != PANO_KNN_BINARY)
+    return fail(c, PANO_ERR_UNSUPPORTED, "pano_match_knn: unknown descriptor");
+  if ((opts->patch_size != 1 && opts->patch_size != 3 && opts->patch_size != 5) ||
+      (opts->descriptor == PANO_KNN_BINARY && opts->patch_size != 5))
+    return fail(c, PANO_ERR_UNSUPPORTED, "pano_match_knn: unsupported patch size");
+  *count = 0;
+  DevImage iq = to_device(c, img_query, wq, hq, stride_q, mem, 0);
+  DevImage it = to_device(c, img_train, wt, ht, stride_t, mem, 1);
+  const int32_t* kq = (const int32_t*)upload(c, c->kpup[0], kp_query, sizeof(int32_t) * 2 * (size_t)n_query, mem);
+  const int32_t* kt = (const int32_t*)upload(c, c->kpup[1], kp_train, sizeof(int32_t) * 2 * (size_t)n_train, mem);
+  // the candidates of both sides: in-border keypoints and their patch descriptors, exactly as in pano_match
+  const int nqi = build_descriptors_device(c->st, iq, kq, n_query, opts->patch_size, c->ms, c->dQ, c->pin);
+  const int nti = build_descriptors_device(c->st, it, kt, n_train, opts->patch_size, c->ms, c->dT, c->pin);
+  int m = 0;
+  if (nqi > 0 && nti > 0)
+    m = match_knn_device(c->st, iq, it, kq, kt, c->dQ, c->dT, *opts, c->matcher == 0 && match_tc_available(), c->ms, c->best,
+                         c->ks, c->pin, c->errw.as<int>());
+  *count = m;
+  const int ncopy = std::min(m, cap);
+  const cudaMemcpyKind kind = mem == PANO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (out && ncopy > 0) PANO_CUDA(cudaMemcpyAsync(out, c->ks.out.p, sizeof(pano_dmatch) * (size_t)ncopy, kind, c->st));
+  if (second_out && ncopy > 0) PANO_CUDA(cudaMemcpyAsync(second_out, c->ks.out2.p, sizeof(float) * (size_t)ncopy, kind, c->st));
   if (int ew = wait_errw(c)) return fail_errw(c, ew);
   return (out && m > cap) ? PANO_ERR_CAPACITY : PANO_OK;
   API_CATCH(c)
