@@ -4,6 +4,7 @@
 // check, without a GPU, that the shim marshals the reference's C++ types correctly and that the reference's GPU
 // executable then produces what its serial one produces.  It is never built into or loaded by the product.
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +22,10 @@ int orc_match(const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8_
 int orc_ransac(const int32_t* kp1, const int32_t* kp2, const orc_dmatch* matches, int m, int iters, int nsamples,
                double thr, uint32_t seed, int div_mode, double* H, int* best_count, int32_t* samples, int32_t* counts,
                uint8_t* inlier_mask, uint64_t* draws, int* best_iter);
+void orc_mul33(const double* a, const double* b, double* d);
+void orc_perspective_transform(const float* pts, int n, const double* H, float* out);
+void orc_warp_perspective(const uint8_t* src, int sw, int sh, size_t sstride, const double* M, uint8_t* dst, int dw, int dh,
+                          size_t dstride);
 }
 
 struct pano_ctx { uint32_t seed; std::string err; };
@@ -57,6 +62,60 @@ int pano_ransac(pano_ctx* c, const int32_t* kp1, int, const int32_t* kp2, int, c
 
 int pano_convolve_f64(pano_ctx*, const double* in, int w, int h, const double* k, int ksize, int, double* out) {
   orc_convolve(in, w, h, k, ksize, out);
+  return PANO_OK;
+}
+// ---- chain mode (host/chain_multi_gpu.hpp on the CPU tier: tests/hostsim/chain_host.cpp) --------------------------
+// "device" memory is host memory here; the device ordinal is ignored.
+int pano_pair_homography(pano_ctx* c, const uint8_t* left, int wl, int hl, size_t sl, const uint8_t* right, int wr, int hr,
+                         size_t sr, int, const pano_harris_opts* ho, const pano_ransac_opts* ro, pano_pair_result* res) {
+  std::vector<int32_t> kl(2 * (size_t)wl * hl / 4 + 16), kr(2 * (size_t)wr * hr / 4 + 16);
+  const int nl = orc_detect(left, wl, hl, sl, ho->k, ho->nms_thresh, ho->nms_neighborhood, kl.data(), (int)kl.size() / 2);
+  const int nr = orc_detect(right, wr, hr, sr, ho->k, ho->nms_thresh, ho->nms_neighborhood, kr.data(), (int)kr.size() / 2);
+  std::vector<orc_dmatch> m((size_t)std::max(nr, 1));
+  const int nm = orc_match(kr.data(), nr, kl.data(), nl, right, wr, hr, sr, left, wl, hl, sl, ho->patch_size,
+                           ho->max_ssd_thresh, 0, m.data(), (int)m.size());
+  memset(res, 0, sizeof *res);
+  res->n_kp_left = nl; res->n_kp_right = nr; res->n_matches = nm; res->best_iteration = -1;
+  if (nm == 0) return res->status = PANO_ERR_NO_MATCHES;
+  if (nm < ro->num_samples) return res->status = PANO_ERR_TOO_FEW_MATCHES;
+  const int ok = orc_ransac(kr.data(), kl.data(), m.data(), nm, ro->num_iterations, ro->num_samples, ro->distance_threshold,
+                            c->seed, 0, res->H, &res->best_inliers, nullptr, nullptr, nullptr, nullptr, &res->best_iteration);
+  return res->status = (ok == 1 ? PANO_OK : PANO_ERR_NO_HOMOGRAPHY);
+}
+
+void pano_mul33(const double A[9], const double B[9], double out[9]) { orc_mul33(A, B, out); }
+
+// ref: src/serial/main.cpp:335-369 with every image i >= 1 in the role of "right" (float min / max, ceil in float)
+int pano_chain_geometry(int n, const int* ws, const int* hs, const double* Hs, pano_canvas_info* out) {
+  float minX = 0, minY = 0, maxX = (float)ws[0], maxY = (float)hs[0];
+  for (int i = 1; i < n; i++) {
+    const float pts[8] = {0.f, 0.f, (float)ws[i], 0.f, (float)ws[i], (float)hs[i], 0.f, (float)hs[i]};
+    float q[8];
+    orc_perspective_transform(pts, 4, Hs + 9 * (size_t)i, q);
+    for (int k = 0; k < 4; k++) {
+      minX = std::min(minX, q[2 * k]); maxX = std::max(maxX, q[2 * k]);
+      minY = std::min(minY, q[2 * k + 1]); maxY = std::max(maxY, q[2 * k + 1]);
+    }
+  }
+  const double T[9] = {1, 0, (double)(-minX), 0, 1, (double)(-minY), 0, 0, 1};
+  memcpy(out->TH, T, sizeof T);
+  out->canvas_w = (int)std::ceil(maxX - minX);
+  out->canvas_h = (int)std::ceil(maxY - minY);
+  out->left_x = (int)(-minX);
+  out->left_y = (int)(-minY);
+  return out->canvas_w > 0 && out->canvas_h > 0 ? PANO_OK : PANO_ERR_ROI;
+}
+
+// cv::warpPerspective of the whole canvas, then the reference's overlay rule (ref: :380-386) on rows [y0, y0 + band_h)
+int pano_warp_accumulate(pano_ctx*, const uint8_t* src, int w, int h, size_t stride, int, const double M[9], uint8_t* band,
+                         int canvas_w, int canvas_h, int y0, int band_h, size_t band_stride) {
+  std::vector<uint8_t> full((size_t)canvas_w * 3 * canvas_h);
+  orc_warp_perspective(src, w, h, stride, M, full.data(), canvas_w, canvas_h, (size_t)canvas_w * 3);
+  for (int y = 0; y < band_h; y++)
+    for (int x = 0; x < canvas_w; x++) {
+      const uint8_t* p = &full[((size_t)(y0 + y) * canvas_w + x) * 3];
+      if (p[0] | p[1] | p[2]) memcpy(band + (size_t)y * band_stride + 3 * (size_t)x, p, 3);
+    }
   return PANO_OK;
 }
 }

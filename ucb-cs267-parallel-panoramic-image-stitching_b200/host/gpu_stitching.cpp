@@ -6,15 +6,21 @@
 //
 // Environment: PANO_DEVICE (GPU ordinal, default 0), PANO_SEED (RANSAC seed, default 12345; the
 // reference seeds from std::random_device).
+// Opt-in, behaviour changing: PANO_MODE=chain stitches in chain mode (adjacent pairs estimated independently, SURVEY
+// 8e2) over PANO_GPUS devices of this box (default: all visible) inside this one process - pairs sharded over the
+// devices, canvas bands rendered per device (host/chain_multi_gpu.hpp).  The default is the reference's fold.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <iomanip>
 #include <iostream>
+#include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
 #include "../../include/pano_b200.h"
+#include "chain_multi_gpu.hpp"
 #include "reader.hpp"
 
 namespace {
@@ -30,6 +36,73 @@ class Timer {
 
 void line(const char* what, double ms) {
   std::cout << what << std::fixed << std::setprecision(3) << ms << " ms" << std::endl;
+}
+
+struct CudaMem {   // device memory for host/chain_multi_gpu.hpp
+  static void set_device(int d) { cudaSetDevice(d); }
+  static void* alloc(size_t n) { void* p = nullptr; return cudaMalloc(&p, n) == cudaSuccess ? p : nullptr; }
+  static void free(void* p) { if (p) cudaFree(p); }
+  static bool zero(void* p, size_t n) { return cudaMemset(p, 0, n) == cudaSuccess; }
+  static void sync() { cudaDeviceSynchronize(); }
+  static bool h2d_2d(void* d, size_t dp, const void* s, size_t sp, size_t row_bytes, int rows) {
+    return cudaMemcpy2D(d, dp, s, sp, row_bytes, (size_t)rows, cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  static bool d2h_2d(void* d, size_t dp, const void* s, size_t sp, size_t row_bytes, int rows) {
+    return cudaMemcpy2D(d, dp, s, sp, row_bytes, (size_t)rows, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+};
+
+// PANO_MODE=chain: one process, PANO_GPUS devices
+int run_chain(const ImageReaderResult& rr, uint32_t seed, const pano_harris_opts& harrisOpts, const pano_ransac_opts& ransacOpts,
+              const Timer& totalTimer) {
+  int visible = 0;
+  if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1) {
+    std::cerr << "gpu_stitching: no CUDA device: an sm_100 GPU is required, there is no CPU path" << std::endl;
+    return -1;
+  }
+  const char* ng = std::getenv("PANO_GPUS");
+  int D = ng ? std::atoi(ng) : visible;
+  if (D < 1) D = 1;
+  if (D > visible) D = visible;
+  const int n = (int)rr.images.size();
+  if (D > n - 1) D = n - 1;          // at most one device per adjacent pair
+  std::vector<int> devices;
+  for (int d = 0; d < D; d++) devices.push_back(d);
+  std::vector<pano_host::ImageView> views;
+  for (const pano_io::Image& im : rr.images) views.push_back({im.bgr.data(), im.w, im.h, im.stride()});
+  std::cout << "Chain mode: " << n << " images, adjacent pairs sharded over " << D << " GPU(s)" << std::endl;
+  Timer foldTimer;
+  pano_host::ChainOutput out;
+  const int st = pano_host::stitch_chain_multi_gpu<CudaMem>(views, devices, seed, harrisOpts, ransacOpts, &out);
+  for (size_t i = 0; i < out.pairs.size(); i++) {
+    const pano_pair_result& r = out.pairs[i];
+    std::cout << "Stitching image " << i + 2 << " of " << n << "... (GPU " << out.pair_device[i] << ")" << std::endl;
+    line("Harris Corner Detection (GPU): ", r.ms_detect);
+    line("Harris Corner Matching (GPU): ", r.ms_match);
+    if (r.status == PANO_ERR_NO_MATCHES) {
+      std::cerr << "Not enough matched corners for stitching!" << std::endl;
+    } else {
+      line("RANSAC Homography Estimation (GPU): ", r.ms_ransac);
+      if (r.status == PANO_ERR_TOO_FEW_MATCHES || r.status == PANO_ERR_NO_HOMOGRAPHY)
+        std::cerr << "RANSAC failed to estimate a homography matrix!" << std::endl;
+    }
+    if (r.status != PANO_OK) std::cerr << "Failed to stitch image " << i + 1 << "!" << std::endl;
+  }
+  line("Image Stitching: ", foldTimer.elapsed());
+  line("Total Stitching Process: ", foldTimer.elapsed());
+  if (st != PANO_OK || out.w <= 0 || out.h <= 0) {
+    std::cerr << "Panoramic stitching failed! (status " << st << ") " << out.error << std::endl;
+    return -1;
+  }
+  if (out.n_used < n)
+    std::cerr << "Chain broken after image " << out.n_used << ": the panorama covers images 1.." << out.n_used << std::endl;
+  if (!pano_io::write_image(rr.outputFile, out.canvas.data(), out.w, out.h, (size_t)out.w * 3)) {
+    std::cerr << "Failed to write " << rr.outputFile << std::endl;
+    return -1;
+  }
+  std::cout << "Stitched result saved to " << rr.outputFile << std::endl;
+  std::cout << "\nTotal Execution Time: " << std::fixed << std::setprecision(3) << totalTimer.elapsed() << " ms" << std::endl;
+  return 0;
 }
 }  // namespace
 
@@ -51,6 +124,8 @@ int main(int argc, char** argv) {
   const char* sd = std::getenv("PANO_SEED");
   int device = dv ? std::atoi(dv) : 0;
   uint32_t seed = sd ? (uint32_t)std::strtoul(sd, nullptr, 10) : 12345u;
+  if (const char* mode = std::getenv("PANO_MODE"))
+    if (std::string(mode) == "chain") return run_chain(rr, seed, harrisOpts, ransacOpts, totalTimer);
   pano_ctx* ctx = nullptr;
   int st = pano_create(device, seed, &ctx);
   if (st != PANO_OK) {
