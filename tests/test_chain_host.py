@@ -3,7 +3,7 @@
 host memory and linked against a CPU stand-in of the C ABI (tests/hostsim/abi_standin.cpp, on the oracle): pair
 sharding over the worker threads, composition of the homographies, canvas geometry and band tiling must give the
 oracle's chain panorama for every device count; a pair that fails ends the chain.  The same executable on a real B200
-is checked in tests/test_zz_chain_cli_gpu.py."""
+is checked in tests/test_zz2_chain_cli_gpu.py."""
 import ctypes as C
 import os
 import subprocess

@@ -4,7 +4,7 @@ UNMODIFIED from /root/reference - with its four .cu stage files replaced by the 
 test-only stand-in on the CPU oracle (tests/hostsim/abi_standin.cpp), so what is tested is the shim's marshalling of the
 reference's C++ types and the reference main's flow on top of it: the panorama must be the one the reference's serial
 code produces for the same seed.  The same executable linked against the real libpano_b200.so is
-oracle/_ref/gpu_stitching_refmain (GPU tier: tests/test_zz_reference_gpu_main.py)."""
+oracle/_ref/gpu_stitching_refmain (GPU tier: tests/test_zz1_reference_gpu_main.py)."""
 import os
 import subprocess
 
