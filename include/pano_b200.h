@@ -213,6 +213,36 @@ int pano_stitch_pair_async(pano_ctx* ctx, const uint8_t* left, int wl, int hl, s
 int pano_pair_query(pano_ctx* ctx);
 int pano_pair_wait(pano_ctx* ctx);
 
+/* Asynchronous forms of the stage, fold and batch calls ("each with an explicit cudaStream_t-carrying
+ * async variant").  Same contract as pano_stitch_pair_async: the call returns at once; the work runs on the context's
+ * worker, ordered after everything already enqueued on `stream` (may be NULL); every pointer argument (inputs,
+ * outputs, *count, results) must stay valid until completion; one pending call per context (PANO_ERR_BUSY
+ * otherwise); pano_pair_query / pano_pair_wait report completion and return the status the blocking call would have
+ * returned (argument errors included). */
+int pano_detect_async(pano_ctx* ctx, const uint8_t* bgr, int w, int h, size_t stride, int mem,
+                      const pano_harris_opts* opts, int32_t* xy_out, int cap, int* count, void* stream);
+int pano_match_async(pano_ctx* ctx, const int32_t* kp_query, int n_query, const int32_t* kp_train,
+                     int n_train, const uint8_t* img_query, int wq, int hq, size_t stride_q,
+                     const uint8_t* img_train, int wt, int ht, size_t stride_t, int mem,
+                     const pano_harris_opts* opts, int offset, pano_dmatch* out, int cap, int* count,
+                     void* stream);
+int pano_ransac_async(pano_ctx* ctx, const int32_t* kp1, int n1, const int32_t* kp2, int n2,
+                      const pano_dmatch* matches, int n_matches, int mem, const pano_ransac_opts* opts,
+                      double H_out[9], int* best_inliers, int* best_iteration, int32_t* samples_out,
+                      int32_t* counts_out, uint8_t* inlier_mask_out, void* stream);
+int pano_warp_overlay_async(pano_ctx* ctx, const uint8_t* left, int wl, int hl, size_t stride_l,
+                            const uint8_t* right, int wr, int hr, size_t stride_r, int mem,
+                            const double H[9], uint8_t* canvas_out, size_t canvas_stride,
+                            size_t canvas_cap_bytes, pano_canvas_info* info, void* stream);
+int pano_stitch_fold_async(pano_ctx* ctx, const uint8_t* const* images, const int* ws, const int* hs,
+                           const size_t* strides, int n, int mem, const pano_harris_opts* hopts,
+                           const pano_ransac_opts* ropts, pano_pair_result* results, void* stream);
+int pano_stitch_batch_async(pano_ctx* ctx, int n, const uint8_t* const* lefts, const uint8_t* const* rights,
+                            int wl, int hl, size_t stride_l, int wr, int hr, size_t stride_r, int mem,
+                            const pano_harris_opts* hopts, const pano_ransac_opts* ropts,
+                            pano_pair_result* results, uint8_t* const* canvases_out,
+                            size_t canvas_cap_bytes, float* ms_batch, void* stream);
+
 /* Copies the context's current canvas (result of the last successful pair / fold step). */
 int pano_get_canvas(pano_ctx* ctx, uint8_t* out, size_t out_stride, size_t cap_bytes, int mem,
                     int* w, int* h);

@@ -8,7 +8,7 @@
    bit for bit, for every split of the train range and every block order (the two-slot atomic publication).
 3. The arithmetic of the tensor-core matcher's top-2 epilogue (tile keys, chains, fold, publication) replayed on the
    host gives the same (nearest, runner-up) keys as the brute force.
-The GPU tier (tests/test_zz3_knn_gpu.py) runs the same comparisons through the C ABI."""
+The GPU tier (tests/test_zz4_knn_gpu.py) runs the same comparisons through the C ABI."""
 import ctypes as C
 import itertools
 

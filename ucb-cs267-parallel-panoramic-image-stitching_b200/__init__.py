@@ -47,6 +47,8 @@ EXPORTED_SYMBOLS = [
     "pano_chain_geometry", "pano_warp_accumulate", "pano_set_stream", "pano_set_replay_mode",
     "pano_set_fold_mode", "pano_stitch_pair_async", "pano_pair_query", "pano_pair_wait", "pano_set_profile", "pano_get_profile",
     "pano_default_knn_opts", "pano_match_knn",
+    "pano_detect_async", "pano_match_async", "pano_ransac_async", "pano_warp_overlay_async", "pano_stitch_fold_async",
+    "pano_stitch_batch_async",
 ]
 
 
@@ -385,6 +387,74 @@ class Engine:
                                                PANO_ERR_ROI))
                 return res.as_dict()
         return Handle()
+
+    # ---- asynchronous forms of the stage calls (pano_*_async; completion through pano_pair_query / pano_pair_wait) ----
+    def _async_handle(self, keep, finish, allow=()):
+        eng = self
+
+        class Handle:
+            status = None
+
+            def done(self):
+                if self.status is None:
+                    s = eng.lib.pano_pair_query(eng.ctx)
+                    if s == PANO_ERR_BUSY:
+                        return False
+                    self.status = s
+                return True
+
+            def result(self):
+                if self.status is None:
+                    self.status = eng.lib.pano_pair_wait(eng.ctx)
+                eng._check(self.status, allow=allow)
+                return finish(self.status)
+        h = Handle()
+        h.keep = keep
+        return h
+
+    def gpuHarrisCornerDetectorDetectAsync(self, image, k=0.04, nmsThresh=1e6, nmsNeighborhood=3, cap=1 << 18, stream_ptr=None):
+        """pano_detect_async: handle whose .result() is the keypoint array (cap = output capacity in keypoints)"""
+        im = _Img(image)
+        assert im.mem == MEM_HOST
+        opts = HarrisCornerOptions(k, nmsThresh, nmsNeighborhood)
+        xy = np.empty((cap, 2), np.int32)
+        count = C.c_int(0)
+        self._check(self.lib.pano_detect_async(self.ctx, im.ptr, im.w, im.h, C.c_size_t(im.stride), im.mem, C.byref(opts),
+                                               xy.ctypes.data_as(C.c_void_p), cap, C.byref(count),
+                                               C.c_void_p(stream_ptr) if stream_ptr else None))
+        return self._async_handle((im, opts, xy, count), lambda st: xy[:count.value])
+
+    def gpuHarrisMatchKeyPointsAsync(self, keypointsL, keypointsR, image1, image2, patchSize=5, maxSSDThresh=1e8, offset=0,
+                                     stream_ptr=None):
+        kq = np.ascontiguousarray(keypointsL, np.int32).reshape(-1, 2)
+        kt = np.ascontiguousarray(keypointsR, np.int32).reshape(-1, 2)
+        iq, it = _Img(image1), _Img(image2)
+        assert iq.mem == MEM_HOST and it.mem == MEM_HOST
+        opts = HarrisCornerOptions(patchSize_=patchSize, maxSSDThresh_=maxSSDThresh)
+        out = np.empty(max(len(kq), 1), MATCH_DTYPE)
+        count = C.c_int(0)
+        self._check(self.lib.pano_match_async(self.ctx, kq.ctypes.data_as(C.c_void_p), len(kq), kt.ctypes.data_as(C.c_void_p),
+                                              len(kt), iq.ptr, iq.w, iq.h, C.c_size_t(iq.stride), it.ptr, it.w, it.h,
+                                              C.c_size_t(it.stride), MEM_HOST, C.byref(opts), int(offset),
+                                              out.ctypes.data_as(C.c_void_p), len(out), C.byref(count),
+                                              C.c_void_p(stream_ptr) if stream_ptr else None))
+        return self._async_handle((kq, kt, iq, it, opts, out, count), lambda st: out[:count.value])
+
+    def computeHomographyAsync(self, keypoints1, keypoints2, matches, options=None, stream_ptr=None):
+        """pano_ransac_async: .result() is (H or None, best inlier count, best iteration)"""
+        o = options or RansacOptions()
+        k1 = np.ascontiguousarray(keypoints1, np.int32).reshape(-1, 2)
+        k2 = np.ascontiguousarray(keypoints2, np.int32).reshape(-1, 2)
+        m = np.ascontiguousarray(matches, MATCH_DTYPE)
+        H = np.zeros((3, 3), np.float64)
+        best, best_iter = C.c_int(0), C.c_int(-1)
+        self._check(self.lib.pano_ransac_async(self.ctx, k1.ctypes.data_as(C.c_void_p), len(k1), k2.ctypes.data_as(C.c_void_p),
+                                               len(k2), m.ctypes.data_as(C.c_void_p), len(m), MEM_HOST, C.byref(o),
+                                               H.ctypes.data_as(C.c_void_p), C.byref(best), C.byref(best_iter), None, None, None,
+                                               C.c_void_p(stream_ptr) if stream_ptr else None))
+        return self._async_handle((k1, k2, m, o, H, best, best_iter),
+                                  lambda st: (H if st == PANO_OK else None, best.value, best_iter.value),
+                                  allow=(PANO_ERR_TOO_FEW_MATCHES, PANO_ERR_NO_HOMOGRAPHY))
 
     def set_profile(self, on=True):
         self._check(self.lib.pano_set_profile(self.ctx, 1 if on else 0))

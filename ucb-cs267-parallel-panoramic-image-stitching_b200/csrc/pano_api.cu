@@ -4,6 +4,7 @@
 // interfaces of ref src/gpu/*.cuh.  No CPU fallback anywhere: without an sm_100 device
 // pano_create fails and nothing else can be called.
 #include "common.cuh"
+#include <array>
 
 #include <algorithm>
 #include <exception>
@@ -387,6 +388,24 @@ int stitch_pair_device(pano_ctx* c, const DevImage& L, const DevImage& R, const 
 
 }  // namespace
 
+// worker launch shared by the asynchronous forms of the stage / fold / batch calls (below)
+namespace {
+template <class F>
+int start_async(pano_ctx* c, void* stream, F fn) {
+  API_TRY(c)
+  if (c->async_job.valid()) return PANO_ERR_BUSY;
+  if (!c->ev_async) PANO_CUDA(cudaEventCreateWithFlags(&c->ev_async, cudaEventDisableTiming));
+  c->async_stream = stream;
+  if (stream) {
+    PANO_CUDA(cudaEventRecord(c->ev_async, (cudaStream_t)stream));
+    PANO_CUDA(cudaStreamWaitEvent(c->st, c->ev_async, 0));
+  }
+  c->async_job = std::async(std::launch::async, fn);
+  return PANO_OK;
+  API_CATCH(c)
+}
+}  // namespace
+
 extern "C" {
 
 void pano_default_harris_opts(pano_harris_opts* o) {
@@ -768,6 +787,77 @@ int pano_pair_query(pano_ctx* c) {
 int pano_pair_wait(pano_ctx* c) {
   if (!c || !c->async_job.valid()) return PANO_ERR_INVALID;
   return async_finish(c);
+}
+
+// ---- asynchronous forms of the stage / fold / batch calls ------------------------------------------
+// Same mechanism and contract as pano_stitch_pair_async: the blocking call runs on a worker owned by the context
+// (its stage synchronisations happen there), its device work is ordered after what the caller has enqueued on
+// `stream`, completion and status come from pano_pair_query / pano_pair_wait.  Argument errors of the underlying call
+// are therefore reported at completion.
+
+int pano_detect_async(pano_ctx* c, const uint8_t* bgr, int w, int h, size_t stride, int mem, const pano_harris_opts* opts,
+                      int32_t* xy_out, int cap, int* count, void* stream) {
+  if (!c || !opts) return PANO_ERR_INVALID;
+  const pano_harris_opts o = *opts;
+  return start_async(c, stream, [=]() -> int { return pano_detect(c, bgr, w, h, stride, mem, &o, xy_out, cap, count); });
+}
+
+int pano_match_async(pano_ctx* c, const int32_t* kp_query, int n_query, const int32_t* kp_train, int n_train,
+                     const uint8_t* img_query, int wq, int hq, size_t stride_q, const uint8_t* img_train, int wt, int ht,
+                     size_t stride_t, int mem, const pano_harris_opts* opts, int offset, pano_dmatch* out, int cap,
+                     int* count, void* stream) {
+  if (!c || !opts) return PANO_ERR_INVALID;
+  const pano_harris_opts o = *opts;
+  return start_async(c, stream, [=]() -> int {
+    return pano_match(c, kp_query, n_query, kp_train, n_train, img_query, wq, hq, stride_q, img_train, wt, ht, stride_t, mem,
+                      &o, offset, out, cap, count);
+  });
+}
+
+int pano_ransac_async(pano_ctx* c, const int32_t* kp1, int n1, const int32_t* kp2, int n2, const pano_dmatch* matches,
+                      int n_matches, int mem, const pano_ransac_opts* opts, double H_out[9], int* best_inliers,
+                      int* best_iteration, int32_t* samples_out, int32_t* counts_out, uint8_t* inlier_mask_out,
+                      void* stream) {
+  if (!c || !opts) return PANO_ERR_INVALID;
+  const pano_ransac_opts o = *opts;
+  return start_async(c, stream, [=]() -> int {
+    return pano_ransac(c, kp1, n1, kp2, n2, matches, n_matches, mem, &o, H_out, best_inliers, best_iteration, samples_out,
+                       counts_out, inlier_mask_out);
+  });
+}
+
+int pano_warp_overlay_async(pano_ctx* c, const uint8_t* left, int wl, int hl, size_t stride_l, const uint8_t* right, int wr,
+                            int hr, size_t stride_r, int mem, const double H[9], uint8_t* canvas_out, size_t canvas_stride,
+                            size_t canvas_cap_bytes, pano_canvas_info* info, void* stream) {
+  if (!c || !H) return PANO_ERR_INVALID;
+  std::array<double, 9> h9;
+  memcpy(h9.data(), H, sizeof(double) * 9);
+  return start_async(c, stream, [=]() -> int {
+    return pano_warp_overlay(c, left, wl, hl, stride_l, right, wr, hr, stride_r, mem, h9.data(), canvas_out, canvas_stride,
+                             canvas_cap_bytes, info);
+  });
+}
+
+int pano_stitch_fold_async(pano_ctx* c, const uint8_t* const* images, const int* ws, const int* hs, const size_t* strides,
+                           int n, int mem, const pano_harris_opts* hopts, const pano_ransac_opts* ropts,
+                           pano_pair_result* results, void* stream) {
+  if (!c || !hopts || !ropts) return PANO_ERR_INVALID;
+  const pano_harris_opts ho = *hopts;
+  const pano_ransac_opts ro = *ropts;
+  return start_async(c, stream, [=]() -> int { return pano_stitch_fold(c, images, ws, hs, strides, n, mem, &ho, &ro, results); });
+}
+
+int pano_stitch_batch_async(pano_ctx* c, int n, const uint8_t* const* lefts, const uint8_t* const* rights, int wl, int hl,
+                            size_t stride_l, int wr, int hr, size_t stride_r, int mem, const pano_harris_opts* hopts,
+                            const pano_ransac_opts* ropts, pano_pair_result* results, uint8_t* const* canvases_out,
+                            size_t canvas_cap_bytes, float* ms_batch, void* stream) {
+  if (!c || !hopts || !ropts) return PANO_ERR_INVALID;
+  const pano_harris_opts ho = *hopts;
+  const pano_ransac_opts ro = *ropts;
+  return start_async(c, stream, [=]() -> int {
+    return pano_stitch_batch(c, n, lefts, rights, wl, hl, stride_l, wr, hr, stride_r, mem, &ho, &ro, results, canvases_out,
+                             canvas_cap_bytes, ms_batch);
+  });
 }
 
 int pano_canvas_device(pano_ctx* c, const uint8_t** ptr, size_t* stride, int* w, int* h) {
