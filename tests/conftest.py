@@ -60,6 +60,22 @@ def knn_emu():
 
 
 @pytest.fixture(scope="session")
+def harris_emu():
+    """the detector's device code (csrc/harris_kernels.cuh, incl. the production fused kernel) compiled by g++ on the CPU
+    emulation of the CUDA execution model (tests/hostsim/cuda_emu.hpp)"""
+    d = os.path.join(ROOT, "tests", "hostsim")
+    so = os.path.join(d, "libharris_emu.so")
+    srcs = [os.path.join(d, "harris_emu.cpp"), os.path.join(d, "cuda_emu.hpp")]
+    srcs += [os.path.join(ROOT, PKG, "csrc", f) for f in ("harris_kernels.cuh", "pano_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                               "-o", so, srcs[0]])
+    lib = ctypes.CDLL(so)
+    lib.hemu_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+@pytest.fixture(scope="session")
 def pins():
     return np.load(os.path.join(GOLDEN, "opencv_pins.npz"))
 

@@ -33,6 +33,8 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) alignas(n)
+#define __grid_constant__
 
 struct uint4 {
   uint32_t x, y, z, w;
@@ -80,8 +82,16 @@ struct State {
   std::function<void()> body;
   const char* error = nullptr;
   uint64_t progress = 0;
+  std::vector<uint8_t> dyn;      // the launch's dynamic shared memory (one block at a time)
+  int count_acc = 0;             // __syncthreads_count accumulator
 };
 inline State* S = nullptr;
+
+// the dynamic shared memory of the running block (128-byte aligned like the kernels ask for)
+inline uint8_t* dyn_smem() {
+  uintptr_t a = reinterpret_cast<uintptr_t>(S->dyn.data());
+  return reinterpret_cast<uint8_t*>((a + 127) & ~uintptr_t(127));
+}
 
 inline void yield() { swapcontext(&S->cur->ctx, &S->sched); }
 
@@ -142,11 +152,12 @@ enum Order { FORWARD = 0, REVERSE = 1, SHUFFLED = 2 };
 
 // runs `body` (a call of a __global__ function) for every thread of every block of the grid
 inline const char* launch(dim3 grid, dim3 block, const std::function<void()>& body, int order = FORWARD,
-                          size_t stack_bytes = 256 * 1024) {
+                          size_t dyn_smem_bytes = 0, size_t stack_bytes = 256 * 1024) {
   const unsigned nthreads = block.x * block.y * block.z;
   State st;
   S = &st;
   st.body = body;
+  st.dyn.assign(dyn_smem_bytes + 256, 0xCD);   // (not zero: shared memory is uninitialised on the device)
   gridDim = grid;
   blockDim = block;
   std::vector<unsigned> blocks(grid.x * grid.y * grid.z);
@@ -214,15 +225,41 @@ inline T __shfl_down_sync(unsigned mask, T v, unsigned delta) {
   const unsigned lane = emu::S->cur->tid & 31;
   return emu::exchange(mask, v, lane + delta < 32 ? lane + delta : lane);
 }
+// every lane of the mask contributes its predicate; one exchange round (the slots hold the predicates)
 inline unsigned __ballot_sync(unsigned mask, int pred) {
+  emu::State& s = *emu::S;
+  emu::Warp& w = s.warps[s.cur->tid >> 5];
+  const unsigned lane = s.cur->tid & 31;
+  w.slot[lane] = pred ? 1u : 0u;
+  emu::sync_warp(mask);
   unsigned r = 0;
-  for (unsigned l = 0; l < 32; l++) {   // 32 exchanges: slow and simple
-    const int p = emu::exchange(mask, pred, l);
-    if (((mask >> l) & 1u) && p) r |= 1u << l;
-  }
+  for (unsigned l = 0; l < 32; l++)
+    if (((mask >> l) & 1u) && ((w.alive >> l) & 1u) && w.slot[l]) r |= 1u << l;
+  emu::sync_warp(mask);
+  return r;
+}
+template <typename T>
+inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
+  const unsigned lane = emu::S->cur->tid & 31;
+  return emu::exchange(mask, v, lane >= delta ? lane - delta : lane);
+}
+// number of threads of the block whose predicate is non-zero (a barrier like __syncthreads)
+inline int __syncthreads_count(int pred) {
+  emu::State& s = *emu::S;
+  if (pred) s.count_acc++;
+  emu::sync_block();                       // every live thread has added its predicate
+  const int r = s.count_acc;
+  emu::sync_block();                       // every thread has read the sum
+  s.count_acc = 0;                         // (idempotent; nobody adds again before the third barrier)
+  emu::sync_block();
   return r;
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+// separately rounded FP64 operations (this translation unit is built with -ffp-contract=off: no FMA is formed)
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
 inline unsigned __vabsdiffu4(unsigned a, unsigned b) {
   unsigned r = 0;
   for (int i = 0; i < 4; i++) {
@@ -245,3 +282,33 @@ inline int atomicOr(int* p, int v) {
   *p = old | v;
   return old;
 }
+inline uint32_t atomicOr(uint32_t* p, uint32_t v) {
+  const uint32_t old = *p;
+  *p = old | v;
+  return old;
+}
+inline uint32_t atomicAdd(uint32_t* p, uint32_t v) {
+  const uint32_t old = *p;
+  *p = old + v;
+  return old;
+}
+
+// ---- a model of the TMA unit's 2-D byte-tensor tile load (cp.async.bulk.tensor.2d, no swizzle) --------------------
+// CUtensorMap here is the host-side description the real encoder would be given: the tile is box_bytes x box_rows
+// from (byte coordinate c0, row coordinate r0); elements outside [0, row_bytes) x [0, rows) are zero-filled, as the
+// hardware does for out-of-bounds coordinates (negative ones included).
+struct CUtensorMap {
+  const uint8_t* base;
+  uint64_t row_bytes, rows, pitch;
+};
+namespace emu {
+inline void tma_tile_load_2d(uint8_t* dst, const CUtensorMap& m, int c0, int r0, int box_bytes, int box_rows) {
+  for (int r = 0; r < box_rows; r++)
+    for (int c = 0; c < box_bytes; c++) {
+      const long long R = (long long)r0 + r, Cc = (long long)c0 + c;
+      uint8_t v = 0;
+      if (R >= 0 && R < (long long)m.rows && Cc >= 0 && Cc < (long long)m.row_bytes) v = m.base[(size_t)R * m.pitch + (size_t)Cc];
+      dst[(size_t)r * box_bytes + c] = v;
+    }
+}
+}  // namespace emu
