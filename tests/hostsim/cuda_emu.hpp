@@ -312,3 +312,12 @@ inline void tma_tile_load_2d(uint8_t* dst, const CUtensorMap& m, int c0, int r0,
     }
 }
 }  // namespace emu
+
+// ---- further device intrinsics (warp kernels) -----------------------------------------------------------------------
+#include <cmath>
+// low 32 bits of (hi:lo) >> (shift mod 32)
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+  const unsigned s = shift & 31u;
+  return s ? (lo >> s) | (hi << (32u - s)) : lo;
+}
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
