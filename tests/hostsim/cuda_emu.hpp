@@ -321,3 +321,4 @@ inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
   return s ? (lo >> s) | (hi << (32u - s)) : lo;
 }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+inline int __float2int_rn(float v) { return (int)lrintf(v); }   // round to nearest even (default rounding mode)
