@@ -108,6 +108,22 @@ def match_emu():
 
 
 @pytest.fixture(scope="session")
+def ransac_emu():
+    """the RANSAC stage's device code (csrc/ransac_kernels.cuh: shuffle replay, DLT, scoring ...) compiled by g++ on the
+    CPU emulation of the CUDA execution model (tests/hostsim/cuda_emu.hpp)"""
+    d = os.path.join(ROOT, "tests", "hostsim")
+    so = os.path.join(d, "libransac_emu.so")
+    srcs = [os.path.join(d, "ransac_emu.cpp"), os.path.join(d, "cuda_emu.hpp")]
+    srcs += [os.path.join(ROOT, PKG, "csrc", f) for f in ("ransac_kernels.cuh", "replay_plan.hpp", "pano_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                               "-Wno-unused-function", "-o", so, srcs[0]])
+    lib = ctypes.CDLL(so)
+    lib.remu_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+@pytest.fixture(scope="session")
 def pins():
     return np.load(os.path.join(GOLDEN, "opencv_pins.npz"))
 

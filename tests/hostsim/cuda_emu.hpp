@@ -33,7 +33,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __grid_constant__
 
 struct uint4 {
@@ -43,6 +43,16 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 struct int4 {
   int x, y, z, w;
 } __attribute__((aligned(16)));
+
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+struct int2 {
+  int x, y;
+} __attribute__((aligned(8)));
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+struct float4 {
+  float x, y, z, w;
+} __attribute__((aligned(16)));
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 struct dim3 {
   unsigned x, y, z;
@@ -59,9 +69,45 @@ using std::min;
 
 namespace emu {
 
+// Context switch between fibers.  On x86-64 a dozen instructions (callee-saved registers + stack pointer; the
+// kernels neither change the FP control state nor throw), because a block of 1024 threads meeting at a few thousand
+// barriers switches millions of times and ucontext's swapcontext costs a system call each; ucontext elsewhere.
+#if defined(__x86_64__)
+#define PANO_EMU_FAST_SWITCH 1
+extern "C" void pano_emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.p2align 4
+.globl pano_emu_switch
+.type pano_emu_switch,@function
+pano_emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size pano_emu_switch,.-pano_emu_switch
+)");
+#endif
+
 struct Fiber {
+#ifdef PANO_EMU_FAST_SWITCH
+  void* sp = nullptr;
+#else
   ucontext_t ctx;
-  std::vector<char> stack;
+#endif
+  char* stack = nullptr;       // (malloc'ed, not zero-filled: 1024 threads x 256 KB would cost more than the kernel)
+  size_t stack_size = 0;
   bool done = false;
   unsigned tid = 0;
 };
@@ -74,7 +120,11 @@ struct Warp {
 };
 
 struct State {
+#ifdef PANO_EMU_FAST_SWITCH
+  void* sched_sp = nullptr;
+#else
   ucontext_t sched;
+#endif
   std::vector<Fiber> fibers;
   std::vector<Warp> warps;
   Fiber* cur = nullptr;
@@ -93,7 +143,14 @@ inline uint8_t* dyn_smem() {
   return reinterpret_cast<uint8_t*>((a + 127) & ~uintptr_t(127));
 }
 
-inline void yield() { swapcontext(&S->cur->ctx, &S->sched); }
+#ifdef PANO_EMU_FAST_SWITCH
+inline void to_scheduler(Fiber* f) { pano_emu_switch(&f->sp, S->sched_sp); }
+inline void to_fiber(Fiber* f) { pano_emu_switch(&S->sched_sp, f->sp); }
+#else
+inline void to_scheduler(Fiber* f) { swapcontext(&f->ctx, &S->sched); }
+inline void to_fiber(Fiber* f) { swapcontext(&S->sched, &f->ctx); }
+#endif
+inline void yield() { to_scheduler(S->cur); }
 
 inline void trampoline() {
   S->body();
@@ -102,7 +159,26 @@ inline void trampoline() {
   S->live--;
   S->warps[f->tid >> 5].alive &= ~(1u << (f->tid & 31));
   S->progress++;
-  swapcontext(&f->ctx, &S->sched);
+  to_scheduler(f);   // never resumed
+}
+
+inline void prepare_fiber(Fiber& f) {
+#ifdef PANO_EMU_FAST_SWITCH
+  // initial frame: six callee-saved registers, the entry point as return address, a null return address above it
+  // (the entry never returns); the stack pointer is 8 modulo 16 when the entry starts, as after a call
+  uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack) + f.stack_size) & ~uintptr_t(15);
+  void** sp = reinterpret_cast<void**>(top);
+  *--sp = nullptr;
+  *--sp = reinterpret_cast<void*>(&trampoline);
+  for (int i = 0; i < 6; i++) *--sp = nullptr;
+  f.sp = sp;
+#else
+  getcontext(&f.ctx);
+  f.ctx.uc_stack.ss_sp = f.stack;
+  f.ctx.uc_stack.ss_size = f.stack_size;
+  f.ctx.uc_link = &S->sched;
+  makecontext(&f.ctx, (void (*)())trampoline, 0);
+#endif
 }
 
 inline void sync_block() {
@@ -171,7 +247,8 @@ inline const char* launch(dim3 grid, dim3 block, const std::function<void()>& bo
     }
   }
   st.fibers.resize(nthreads);
-  for (auto& f : st.fibers) f.stack.resize(stack_bytes);
+  char* stacks = static_cast<char*>(malloc((size_t)nthreads * stack_bytes));
+  for (unsigned t = 0; t < nthreads; t++) { st.fibers[t].stack = stacks + (size_t)t * stack_bytes; st.fibers[t].stack_size = stack_bytes; }
   for (unsigned b : blocks) {
     const emu_idx bi = {b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y)};
     st.warps.assign((nthreads + 31) / 32, Warp());
@@ -182,11 +259,7 @@ inline const char* launch(dim3 grid, dim3 block, const std::function<void()>& bo
       f.done = false;
       f.tid = t;
       st.warps[t >> 5].alive |= 1u << (t & 31);
-      getcontext(&f.ctx);
-      f.ctx.uc_stack.ss_sp = f.stack.data();
-      f.ctx.uc_stack.ss_size = f.stack.size();
-      f.ctx.uc_link = &st.sched;
-      makecontext(&f.ctx, (void (*)())trampoline, 0);
+      prepare_fiber(f);
     }
     while (st.live > 0) {
       const uint64_t before = st.progress;
@@ -196,16 +269,17 @@ inline const char* launch(dim3 grid, dim3 block, const std::function<void()>& bo
         st.cur = &f;
         threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
         blockIdx = bi;
-        swapcontext(&st.sched, &f.ctx);
+        to_fiber(&f);
       }
       if (st.progress == before && st.live > 0) {   // a full round in which nobody moved: a barrier cannot complete
-        st.error = "deadlock: a barrier / warp collective is waiting for threads that never arrive";
         S = nullptr;
-        return st.error;
+        free(stacks);
+        return "deadlock: a barrier / warp collective is waiting for threads that never arrive";
       }
     }
   }
   S = nullptr;
+  free(stacks);
   return nullptr;
 }
 
@@ -322,3 +396,11 @@ inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
 }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 inline int __float2int_rn(float v) { return (int)lrintf(v); }   // round to nearest even (default rounding mode)
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+inline int atomicMax(int* p, int v) {
+  const int old = *p;
+  if (v > old) *p = v;
+  return old;
+}
