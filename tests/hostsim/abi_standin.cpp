@@ -22,18 +22,21 @@ int orc_match(const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8_
 int orc_ransac(const int32_t* kp1, const int32_t* kp2, const orc_dmatch* matches, int m, int iters, int nsamples,
                double thr, uint32_t seed, int div_mode, double* H, int* best_count, int32_t* samples, int32_t* counts,
                uint8_t* inlier_mask, uint64_t* draws, int* best_iter);
+int orc_match_knn(const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8_t* imq, int wq, int hq, size_t sq,
+                  const uint8_t* imt, int wt, int ht, size_t st, int patch, int descriptor, double ratio, orc_dmatch* out,
+                  float* second, int cap);
 void orc_mul33(const double* a, const double* b, double* d);
 void orc_perspective_transform(const float* pts, int n, const double* H, float* out);
 void orc_warp_perspective(const uint8_t* src, int sw, int sh, size_t sstride, const double* M, uint8_t* dst, int dw, int dh,
                           size_t dstride);
 }
 
-struct pano_ctx { uint32_t seed; std::string err; };
+struct pano_ctx { uint32_t seed; std::string err; int pending = 0, pending_status = 0; };
 
 extern "C" {
 void pano_default_harris_opts(pano_harris_opts* o) { *o = {0.04, 1e6, 3, 5, 1e8}; }
 void pano_default_ransac_opts(pano_ransac_opts* o) { *o = {1000, 4, 3.0}; }
-int pano_create(int, uint32_t seed, pano_ctx** out) { *out = new pano_ctx{seed, ""}; return PANO_OK; }
+int pano_create(int, uint32_t seed, pano_ctx** out) { *out = new pano_ctx{seed, "", 0, 0}; return PANO_OK; }
 void pano_destroy(pano_ctx* c) { delete c; }
 const char* pano_last_error(const pano_ctx* c) { return c ? c->err.c_str() : ""; }
 
@@ -118,4 +121,49 @@ int pano_warp_accumulate(pano_ctx*, const uint8_t* src, int w, int h, size_t str
     }
   return PANO_OK;
 }
+// ---- opt-in calls and the asynchronous forms (the Python binding on the CPU tier: tests/test_python_binding.py) -------
+int pano_set_matcher(pano_ctx*, int) { return PANO_OK; }
+void pano_default_knn_opts(pano_knn_opts* o) { *o = {5, PANO_KNN_PATCH_SSD, 0.75}; }
+
+int pano_match_knn(pano_ctx*, const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8_t* imq, int wq, int hq, size_t sq,
+                   const uint8_t* imt, int wt, int ht, size_t st, int, const pano_knn_opts* o, pano_dmatch* out, float* second,
+                   int cap, int* count) {
+  if (!(o->ratio > 0.0) || o->ratio > 1.0) return PANO_ERR_INVALID;
+  if (o->descriptor != PANO_KNN_PATCH_SSD && o->descriptor != PANO_KNN_BINARY) return PANO_ERR_UNSUPPORTED;
+  if ((o->patch_size != 1 && o->patch_size != 3 && o->patch_size != 5) || (o->descriptor == PANO_KNN_BINARY && o->patch_size != 5))
+    return PANO_ERR_UNSUPPORTED;
+  *count = orc_match_knn(kq, nq, kt, nt, imq, wq, hq, sq, imt, wt, ht, st, o->patch_size, o->descriptor, o->ratio,
+                         (orc_dmatch*)out, second, cap);
+  return *count > cap ? PANO_ERR_CAPACITY : PANO_OK;
+}
+
+// the worker of the real library is replaced by an immediate call; completion is reported by query / wait as there
+static int finish_async(pano_ctx* c, int status) {
+  if (c->pending) return PANO_ERR_BUSY;
+  c->pending = 1;
+  c->pending_status = status;
+  return PANO_OK;
+}
+int pano_detect_async(pano_ctx* c, const uint8_t* bgr, int w, int h, size_t stride, int mem, const pano_harris_opts* o, int32_t* xy,
+                      int cap, int* count, void*) {
+  if (c->pending) return PANO_ERR_BUSY;
+  return finish_async(c, pano_detect(c, bgr, w, h, stride, mem, o, xy, cap, count));
+}
+int pano_match_async(pano_ctx* c, const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8_t* imq, int wq, int hq,
+                     size_t sq, const uint8_t* imt, int wt, int ht, size_t st, int mem, const pano_harris_opts* o, int offset,
+                     pano_dmatch* out, int cap, int* count, void*) {
+  if (c->pending) return PANO_ERR_BUSY;
+  return finish_async(c, pano_match(c, kq, nq, kt, nt, imq, wq, hq, sq, imt, wt, ht, st, mem, o, offset, out, cap, count));
+}
+int pano_ransac_async(pano_ctx* c, const int32_t* kp1, int n1, const int32_t* kp2, int n2, const pano_dmatch* m, int n, int mem,
+                      const pano_ransac_opts* o, double H[9], int* best, int* best_it, int32_t* s, int32_t* cn, uint8_t* mask, void*) {
+  if (c->pending) return PANO_ERR_BUSY;
+  return finish_async(c, pano_ransac(c, kp1, n1, kp2, n2, m, n, mem, o, H, best, best_it, s, cn, mask));
+}
+int pano_pair_query(pano_ctx* c) {
+  if (!c->pending) return PANO_ERR_INVALID;
+  c->pending = 0;
+  return c->pending_status;
+}
+int pano_pair_wait(pano_ctx* c) { return pano_pair_query(c); }
 }
