@@ -124,6 +124,22 @@ def ransac_emu():
 
 
 @pytest.fixture(scope="session")
+def match_tc_emu():
+    """the tensor-core matcher's kernel body (csrc/match_tc_kernels.cuh) compiled by g++ on the CPU emulation of the CUDA
+    execution model plus a host model of mbarriers / TMA / tcgen05 / tensor memory (tests/hostsim/tcgen05_emu.hpp)"""
+    d = os.path.join(ROOT, "tests", "hostsim")
+    so = os.path.join(d, "libmatch_tc_emu.so")
+    srcs = [os.path.join(d, "match_tc_emu.cpp"), os.path.join(d, "cuda_emu.hpp"), os.path.join(d, "tcgen05_emu.hpp")]
+    srcs += [os.path.join(ROOT, PKG, "csrc", f) for f in ("match_tc_kernels.cuh", "knn_core.cuh", "pano_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                               "-Wno-unused-function", "-o", so, srcs[0]])
+    lib = ctypes.CDLL(so)
+    lib.tcemu_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+@pytest.fixture(scope="session")
 def pins():
     return np.load(os.path.join(GOLDEN, "opencv_pins.npz"))
 

@@ -140,7 +140,7 @@ inline State* S = nullptr;
 // the dynamic shared memory of the running block (128-byte aligned like the kernels ask for)
 inline uint8_t* dyn_smem() {
   uintptr_t a = reinterpret_cast<uintptr_t>(S->dyn.data());
-  return reinterpret_cast<uint8_t*>((a + 127) & ~uintptr_t(127));
+  return reinterpret_cast<uint8_t*>((a + 1023) & ~uintptr_t(1023));
 }
 
 #ifdef PANO_EMU_FAST_SWITCH
@@ -224,6 +224,20 @@ inline T exchange(unsigned mask, T v, unsigned src_lane) {
   return out;
 }
 
+// bar.sync id, count: a barrier among `count` threads of the block, identified by `id`
+struct NamedBarrier { unsigned arrived = 0, gen = 0; };
+inline NamedBarrier named[16];
+inline void named_barrier(int id, unsigned count) {
+  NamedBarrier& b = named[id & 15];
+  const unsigned gen = b.gen;
+  b.arrived++;
+  S->progress++;
+  while (b.gen == gen) {
+    if (b.arrived >= count) { b.arrived = 0; b.gen++; S->progress++; break; }
+    yield();
+  }
+}
+
 enum Order { FORWARD = 0, REVERSE = 1, SHUFFLED = 2 };
 
 // runs `body` (a call of a __global__ function) for every thread of every block of the grid
@@ -233,7 +247,7 @@ inline const char* launch(dim3 grid, dim3 block, const std::function<void()>& bo
   State st;
   S = &st;
   st.body = body;
-  st.dyn.assign(dyn_smem_bytes + 256, 0xCD);   // (not zero: shared memory is uninitialised on the device)
+  st.dyn.assign(dyn_smem_bytes + 1024, 0xCD);   // (not zero: shared memory is uninitialised on the device)
   gridDim = grid;
   blockDim = block;
   std::vector<unsigned> blocks(grid.x * grid.y * grid.z);
@@ -254,6 +268,7 @@ inline const char* launch(dim3 grid, dim3 block, const std::function<void()>& bo
     st.warps.assign((nthreads + 31) / 32, Warp());
     st.block_arrived = 0;
     st.live = nthreads;
+    for (auto& nb : named) nb = NamedBarrier();
     for (unsigned t = 0; t < nthreads; t++) {
       Fiber& f = st.fibers[t];
       f.done = false;
@@ -374,6 +389,7 @@ inline uint32_t atomicAdd(uint32_t* p, uint32_t v) {
 struct CUtensorMap {
   const uint8_t* base;
   uint64_t row_bytes, rows, pitch;
+  uint32_t box_rows = 0;   // (swizzled tile maps of the matcher model, tcgen05_emu.hpp)
 };
 namespace emu {
 inline void tma_tile_load_2d(uint8_t* dst, const CUtensorMap& m, int c0, int r0, int box_bytes, int box_rows) {
