@@ -9,7 +9,9 @@ the in-border region, some duplicated), a random ratio / patch size / descriptor
     against the brute-force "earliest train keypoint" rule instead);
   * the engine's kernels (csrc/knn_kernels.cuh compiled unchanged on the CPU emulation of the CUDA execution model,
     tests/hostsim) against the checker, bit for bit, for a random split of the train range and block order;
-  * the tensor-core epilogue's arithmetic (tests/hostsim emu_tc_top2) against the brute force on the same descriptors.
+  * the tensor-core epilogue's arithmetic (tests/hostsim emu_tc_top2) and the tensor-core kernel itself
+    (match_tc_top2_kernel on the host model of mbarriers / TMA / tcgen05, tests/hostsim/tcgen05_emu.hpp) against the
+    brute force on the same descriptors.
 One JSON line; exit code 1 on the first difference."""
 import argparse
 import ctypes as C
@@ -29,6 +31,19 @@ MATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("distance", "
 
 def p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+def load_tc_emu():
+    d = os.path.join(ROOT, "tests", "hostsim")
+    so = os.path.join(d, "libmatch_tc_emu.so")
+    srcs = [os.path.join(d, "match_tc_emu.cpp"), os.path.join(d, "cuda_emu.hpp"), os.path.join(d, "tcgen05_emu.hpp")]
+    srcs += [os.path.join(ROOT, PKG, "csrc", f) for f in ("match_tc_kernels.cuh", "knn_core.cuh", "pano_core.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                               "-Wno-unused-function", "-o", so, srcs[0]])
+    lib = C.CDLL(so)
+    lib.tcemu_last_error.restype = C.c_char_p
+    return lib
 
 
 def load_emu():
@@ -71,6 +86,7 @@ def main():
     from oracle.oracle import Oracle
     O = Oracle()
     emu = load_emu()
+    tc = load_tc_emu()
     rng = np.random.default_rng(a.seed)
     t0 = time.time()
     n = {"cases": 0, "queries": 0, "matches": 0, "pairs": 0, "tc_rows": 0}
@@ -154,6 +170,13 @@ def main():
                 if int(b1[r]) != (int(D[r, j1]) << 32 | j1) or int(b2[r]) != (int(D[r, j2]) << 32 | j2):
                     fail("tensor-core epilogue arithmetic", case=case, row=r)
             n["tc_rows"] += len(qi)
+            # ... and the tensor-core kernel itself (match_tc_top2_kernel on the host model of tcgen05 / TMA / mbarriers)
+            c1 = np.zeros(len(qi), np.uint64)
+            c2 = np.zeros(len(qi), np.uint64)
+            st = tc.tcemu_match(p(qd, C.c_uint8), len(qi), p(td, C.c_uint8), len(ti), int(rng.choice([1, 2, 5, 148])), 1,
+                                int(rng.integers(0, 3)), p(c1, C.c_uint64), p(c2, C.c_uint64))
+            if st != 0 or not np.array_equal(c1, b1) or not np.array_equal(c2, b2):
+                fail("tensor-core top-2 kernel on the host model", case=case, st=st, err=tc.tcemu_last_error())
     print(json.dumps({"ok": True, "fuzz_seed": a.seed, **n, "seconds": round(time.time() - t0, 1), "cv2": cv2.__version__}))
 
 
