@@ -78,7 +78,7 @@ extern "C" void pano_emu_switch(void** save_sp, void* load_sp);
 asm(R"(
 .text
 .p2align 4
-.globl pano_emu_switch
+.weak pano_emu_switch
 .type pano_emu_switch,@function
 pano_emu_switch:
   pushq %rbp

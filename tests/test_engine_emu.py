@@ -1,0 +1,211 @@
+"""CPU tier: the WHOLE engine without a GPU.  tests/hostsim/build_emu_lib.py compiles the engine's own sources - the C
+ABI, the host orchestration (stage sequencing, scratch buffers, read-backs, the async worker, replay planning and
+re-runs) and every kernel, the tensor-core matcher included - with g++ against a fake, synchronous CUDA runtime
+(tests/hostsim/fake_cuda) on the CPU emulation of the CUDA execution model (cuda_emu.hpp, tcgen05_emu.hpp); the only
+source change is the mechanical rewrite of `kernel<<<...>>>(...)` launches.  The package's Python binding then drives
+that library exactly as it drives libpano_b200.so on a B200, and the results must be the oracle's, bit for bit.
+TEST INFRASTRUCTURE ONLY: the emulated library is never shipped and never loaded by the package (which refuses to work
+without a GPU, tests/test_abi.py).  Sizes are small: a thread of the emulation is a fiber on one host core.
+Also runs the GPU-tier test code of the pieces that were written after the round's GPU budget was spent (the opt-in
+2-NN matcher, the asynchronous stage calls) against the emulated engine."""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_pkg, load_synth
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+@pytest.fixture(scope="module")
+def engine():
+    os.environ["PANO_BATCH_LANES"] = "1"        # (the emulation runs one launch at a time)
+    spec = importlib.util.spec_from_file_location("build_emu_lib", os.path.join(ROOT, "tests", "hostsim", "build_emu_lib.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pkg = load_pkg()
+    lib = C.CDLL(mod.build())
+    lib.pano_last_error.restype = C.c_char_p
+    lib.pano_version.restype = C.c_char_p
+    lib.pano_kernel_launches.restype = C.c_uint64
+    e = pkg.Engine.__new__(pkg.Engine)           # the binding's methods on the emulated library
+    e.lib, e.ctx, e.device = lib, C.c_void_p(), 0
+    assert lib.pano_create(0, C.c_uint32(12345), C.byref(e.ctx)) == 0
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def pair():
+    left, right, _ = load_synth().make_pair(320, 200, seed=9)
+    return left, right
+
+
+def test_emulated_engine_stitches_a_pair_like_the_reference(engine, oracle, pair):
+    """pano_stitch_pair end to end with the reference's options (1000 RANSAC iterations): detection of both images, tensor-
+    core matcher, shuffle replay on the side stream, DLT, scoring, canvas geometry, quad warp kernel, canvas fetch"""
+    left, right = pair
+    n0 = engine.kernel_launches()
+    canvas, r = engine.stitchTwoImages(left, right)
+    o = oracle.stitch_pair(left, right, seed=12345)
+    assert r["status"] == 0 and o["status"] == 1
+    assert (r["kl"], r["kr"], r["m"], r["best"]) == (o["stats"]["kl"], o["stats"]["kr"], o["stats"]["m"], o["stats"]["best"])
+    assert np.array_equal(bits(r["H"]), bits(o["H"])) and np.array_equal(canvas, o["canvas"])
+    assert engine.kernel_launches() - n0 > 20
+
+
+def test_emulated_engine_stage_calls(engine, oracle, pair):
+    pkg = load_pkg()
+    left, right = pair
+    kl, kr = engine.gpuHarrisCornerDetectorDetect(left), engine.gpuHarrisCornerDetectorDetect(right)
+    assert np.array_equal(kl, oracle.detect(left)) and np.array_equal(kr, oracle.detect(right))
+    assert np.array_equal(engine.gpuHarrisCornerDetectorDetect(left, nmsNeighborhood=5), oracle.detect(left, nbhd=5))
+    assert np.array_equal(bits(engine.harrisResponse(right)), bits(oracle.harris_response(right)))
+    mo = np.ascontiguousarray(oracle.match(kr, kl, right, left))
+    for matcher in (0, 1):                                   # tensor-core matcher (on its host model), SIMT matcher
+        engine.set_matcher(matcher)
+        try:
+            assert engine.gpuHarrisMatchKeyPoints(kr, kl, right, left).tobytes() == mo.tobytes()
+            m3 = engine.gpuHarrisMatchKeyPoints(kr, kl, right, left, patchSize=3, maxSSDThresh=900.0, offset=2)
+            assert m3.tobytes() == np.ascontiguousarray(oracle.match(kr, kl, right, left, patch=3, max_ssd=900.0, offset=2)).tobytes()
+        finally:
+            engine.set_matcher(0)
+    ro = pkg.RansacOptions(numIterations_=80)
+    d = engine.computeHomography(kr, kl, mo, options=ro, details=True)
+    o = oracle.ransac(kr, kl, mo, iters=80, seed=12345)
+    assert np.array_equal(d["samples"], o["samples"]) and np.array_equal(d["counts"], o["counts"])
+    assert np.array_equal(bits(d["H"]), bits(o["H"])) and np.array_equal(d["inlier_mask"].astype(bool), o["inlier_mask"])
+    bad = mo.copy()
+    bad["trainIdx"][3] = len(kl) + 9                          # checked on the device, reported through the error word
+    with pytest.raises(pkg.PanoError) as e:
+        engine.computeHomography(kr, kl, bad, options=ro)
+    assert e.value.status == pkg.PANO_ERR_INVALID
+    assert np.array_equal(engine.warpOverlay(left, right, o["H"]), oracle.compose(left, right, o["H"]))
+    M = np.array([[0.9, 0.05, 12.0], [-0.04, 1.1, -7.0], [1e-4, -2e-4, 1.0]])
+    assert np.array_equal(engine.warpPerspective(right, M, (260, 180)), oracle.warp_perspective(right, M, (260, 180)))
+
+
+def test_emulated_engine_fold_of_three_images(engine, oracle):
+    pkg = load_pkg()
+    views = load_synth().make_strip(n=3, w=240, h=160, seed=21)
+    ro = pkg.RansacOptions(numIterations_=1000)
+    pano, log = engine.stitchAllImages(views, ransacOpts=ro)
+    want, olog = oracle.stitch_fold(views, seed=12345)
+    assert [r["status"] == 0 for r in log] == [r["status"] == 1 for r in olog]
+    assert np.array_equal(np.asarray(pano), np.asarray(want))
+
+
+# ---- the GPU-tier test code of the late additions, against the emulated engine ------------------------------------------
+def _load_gpu_test_module(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tests", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="module")
+def knn_tests():
+    return _load_gpu_test_module("test_zz4_knn_gpu")
+
+
+@pytest.fixture(scope="module")
+def scenes(oracle):
+    """the GPU tier's 'small' scene (640 x 360) - the 1080p one is left to the B200"""
+    left, right, _ = load_synth().make_pair(640, 360, seed=11)
+    kl, kr = oracle.detect(left), oracle.detect(right)
+    kl = np.concatenate([kl, [[0, 0], [1, 359], [639, 5]], kl[:9]]).astype(np.int32)
+    kr = np.concatenate([[[2, 1]], kr, kr[3:6]]).astype(np.int32)
+    return {"small": (left, right, kl, kr)}
+
+
+def test_emulated_engine_knn_argument_checks(engine, scenes, knn_tests):
+    knn_tests.test_knn_argument_checks(engine, scenes)
+
+
+@pytest.mark.parametrize("matcher", ["simt", "tensor-core"])
+def test_emulated_engine_knn_patch_ssd(engine, oracle, scenes, knn_tests, matcher):
+    knn_tests.ssd_equals_checker(engine, oracle, scenes, knn_tests.SIMT if matcher == "simt" else knn_tests.TC, "small")
+
+
+def test_emulated_engine_knn_binary(engine, oracle, scenes, knn_tests):
+    left, right, kl, kr = scenes["small"]
+    for ratio in (0.8, 1.0):
+        knn_tests.check(engine, oracle, kr, kl, right, left, 1, ratio, min_matches=5)
+
+
+@pytest.mark.parametrize("descriptor,matcher", [(1, "simt"), (0, "simt"), (0, "tensor-core")])
+def test_emulated_engine_knn_edge_cases(engine, oracle, scenes, knn_tests, descriptor, matcher):
+    knn_tests.edge_cases_equal_checker(engine, oracle, scenes, descriptor, knn_tests.SIMT if matcher == "simt" else knn_tests.TC)
+
+
+def test_emulated_engine_knn_other_patch_sizes(engine, oracle, scenes, knn_tests):
+    for patch in (1, 3):
+        for matcher in (knn_tests.SIMT, knn_tests.TC):
+            knn_tests.other_patch_size(engine, oracle, scenes, patch, matcher)
+
+
+def test_emulated_engine_knn_at_ratio_one_is_the_reference_matcher(engine, scenes, knn_tests):
+    small = {"mid": scenes["small"]}                          # (the GPU test's 1080p scene, replaced by the small one)
+    knn_tests.test_knn_tensor_core_and_simt_agree_with_the_reference_matcher_at_ratio_one(engine, small)
+
+
+def test_emulated_engine_async_stage_calls(engine, oracle, pair):
+    """tests/test_zz3_async_stages_gpu.py's checks on a smaller pair with fewer iterations: the worker thread of the
+    asynchronous forms drives the same emulated device"""
+    pkg = load_pkg()
+    left, right = pair
+    kl = engine.gpuHarrisCornerDetectorDetect(left)
+    h = engine.gpuHarrisCornerDetectorDetectAsync(right)
+    opts, n, L = pkg.HarrisCornerOptions(), C.c_int(0), pkg._Img(left)
+    busy = engine.lib.pano_detect_async(engine.ctx, L.ptr, L.w, L.h, C.c_size_t(L.stride), 0, C.byref(opts), None, 0, C.byref(n), None)
+    assert busy == pkg.PANO_ERR_BUSY
+    kr = h.result()
+    assert h.done() and np.array_equal(kr, oracle.detect(right))
+    m = engine.gpuHarrisMatchKeyPointsAsync(kr, kl, right, left).result()
+    assert m.tobytes() == np.ascontiguousarray(oracle.match(kr, kl, right, left)).tobytes()
+    ro = pkg.RansacOptions(numIterations_=60)
+    H, best, it = engine.computeHomographyAsync(kr, kl, m, options=ro).result()
+    o = oracle.ransac(kr, kl, m, iters=60, seed=12345)
+    assert np.array_equal(bits(H), bits(o["H"])) and (best, it) == (o["best_count"], o["best_iter"])
+    H2, _, _ = engine.computeHomographyAsync(kr, kl, m[:3]).result()
+    assert H2 is None
+    pair_async = engine.stitchTwoImagesAsync(left, right, ransacOpts=ro)
+    r = pair_async.result()
+    assert r["status"] == 0 and np.array_equal(bits(r["H"]), bits(o["H"]))
+    assert np.array_equal(engine.getCanvas(), oracle.compose(left, right, o["H"]))
+
+
+def test_emulated_gpu_stitching_executable_chain_mode_and_fold(engine, oracle, tmp_path):
+    """host/gpu_stitching.cpp itself (with reader and image codecs) linked against the emulated library and the fake CUDA
+    runtime: PANO_MODE=chain over two "devices" (worker threads, per-device contexts, bands into the host canvas; the
+    check of tests/test_zz2_chain_cli_gpu.py) gives the oracle's chain panorama, and the default stays the reference's fold"""
+    import subprocess
+    cv2 = pytest.importorskip("cv2")
+    exe = os.path.join(ROOT, "tests", "hostsim", "gpu_stitching_emu")
+    assert os.path.exists(exe)                                   # built together with the emulated library (fixture `engine`)
+    views = load_synth().make_strip(n=3, w=240, h=160, seed=21)
+    paths = []
+    for i, v in enumerate(views):
+        p = str(tmp_path / ("v%d.ppm" % i))
+        assert cv2.imwrite(p, v)
+        paths.append(p)
+    pano, pair_H = oracle.stitch_chain(views, seed=12345)
+    assert all(H is not None for H in pair_H)
+    out = str(tmp_path / "chain.png")
+    r = subprocess.run([exe] + paths + ["--out", out], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, PANO_MODE="chain", PANO_GPUS="2", PANO_EMU_DEVICES="4"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Chain mode: 3 images, adjacent pairs sharded over 2 GPU(s)" in r.stdout and "(GPU 1)" in r.stdout
+    for needle in ("Harris Corner Detection (GPU): ", "RANSAC Homography Estimation (GPU): ", "Image Stitching: ",
+                   "Total Stitching Process: ", "Stitched result saved to " + out, "Total Execution Time: "):
+        assert needle in r.stdout, needle
+    assert np.array_equal(cv2.imread(out), pano)
+    out2 = str(tmp_path / "fold.png")
+    r = subprocess.run([exe] + paths[:2] + ["--out", out2], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "Chain mode" not in r.stdout and "Stitching image 2 of 2..." in r.stdout
+    assert np.array_equal(cv2.imread(out2), oracle.stitch_pair(views[0], views[1], seed=12345)["canvas"])

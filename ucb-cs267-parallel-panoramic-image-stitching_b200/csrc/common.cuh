@@ -60,8 +60,13 @@ inline cudaError_t stream_wait(cudaStream_t st) {
 
 // Programmatic dependent launch: the next kernel of a stream is set up while the previous one drains; every kernel
 // launched this way starts with pdl_wait() (= all earlier grids complete and visible) before it touches memory.
+#ifdef PANO_CUDA_EMU   // (CPU emulation tier, tests/hostsim: kernels run one after another)
+inline void pdl_wait() {}
+inline void pdl_trigger() {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 inline bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("PANO_PDL"); return !(e && atoi(e) == 0); }();
   return on;

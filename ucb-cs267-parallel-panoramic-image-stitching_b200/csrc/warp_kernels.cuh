@@ -451,7 +451,7 @@ bool fast_path_ok(const WarpParams& P, const uint8_t* src, size_t sstride, bool 
   return 32.0 * nmax / wmin < 4000000.0;   // < 2^22 with margin
 }
 
-#ifndef PANO_CUDA_EMU   // (kernel launches: device build only; the emulation tier mirrors this selection)
+#if !defined(PANO_CUDA_EMU) || defined(PANO_CUDA_EMU_LIB)   // (kernel launches: device build, and the whole-library emulation build)
 template <int MODE>
 void launch_fast(cudaStream_t st, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
                  const WarpParams& P, uint8_t* canvas, size_t cstride) {
