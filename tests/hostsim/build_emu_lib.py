@@ -20,6 +20,9 @@ CSRC = os.path.join(ROOT, PKG, "csrc")
 OUT = os.path.join(HERE, "libpano_b200_emu.so")
 EXE = os.path.join(HERE, "gpu_stitching_emu")
 BUILD = os.path.join(HERE, "_emu_build")
+# PANO_EMU_CXXFLAGS="-fsanitize=address -fno-omit-frame-pointer -g": the same build under a sanitizer (run the tests with
+# LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:verify_asan_link_order=0)
+EXTRA = os.environ.get("PANO_EMU_CXXFLAGS", "").split()
 UNITS = ["pano_api", "harris", "match", "match_tc", "knn", "ransac", "warp"]
 
 
@@ -111,7 +114,7 @@ def build(force=False):
     procs = []
     for u in UNITS:
         obj = os.path.join(BUILD, u + ".o")
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-unused-function",
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-unused-function"] + EXTRA + [
                "-DPANO_CUDA_EMU_LIB=1", "-I" + os.path.join(HERE, "fake_cuda"), "-c", os.path.join(csrc_out, u + ".cpp"), "-o", obj]
         procs.append((u, subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True)))
         objs.append(obj)
@@ -120,13 +123,13 @@ def build(force=False):
         if pr.returncode != 0:
             sys.stderr.write(err[-6000:])
             raise RuntimeError("emulated build of %s failed" % u)
-    subprocess.check_call(["g++", "-shared", "-o", OUT] + objs + ["-lpthread"])
+    subprocess.check_call(["g++", "-shared", "-o", OUT] + EXTRA + objs + ["-lpthread"])
     # the gpu_stitching executable itself (host/gpu_stitching.cpp, reader, image codecs without nvJPEG) on the emulated
     # library: the command-line paths (the reference's fold, PANO_MODE=chain over PANO_EMU_DEVICES "devices")
     host = os.path.join(ROOT, PKG, "host")
     zlib = ["-DPANO_WITH_ZLIB", "-lz"] if os.path.exists("/usr/include/zlib.h") else []
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-unused-function",
-                           "-DPANO_HAVE_CUDA", "-include", "cuda_runtime.h", "-I" + os.path.join(HERE, "fake_cuda"), "-I" + host, "-o", EXE,
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-unused-function"] + EXTRA +
+                          ["-DPANO_HAVE_CUDA", "-include", "cuda_runtime.h", "-I" + os.path.join(HERE, "fake_cuda"), "-I" + host, "-o", EXE,
                            os.path.join(host, "gpu_stitching.cpp"), os.path.join(host, "reader.cpp"), os.path.join(host, "image_io.cpp"),
                            OUT, "-Wl,-rpath,$ORIGIN", "-lpthread"] + zlib)
     return OUT
