@@ -20,6 +20,8 @@ overlay) over that batch through ONE pano_stitch_batch call.
                inside the C ABI (pano_set_profile), plus every other main kernel timed the same way.
 `cpu_baseline` the reference's own code (oracle/_ref: /root/reference/src/openmp/main.cpp and src/serial/main.cpp
                compiled unmodified against oracle/cvshim) on this box's host cores, rank 0 at N = 1 only.
+`other_configs` BASELINE configs 1 (images/mountain pair: engine next to the reference's serial and OpenMP code) and 2
+               (images/oilseed fold + evaluator score), each measured in a child process at N = 1 (--no-extras skips).
 Every number in the line is measured in this run, except those explicitly attributed to a committed capture
 under profiles/ (ncu-only metrics such as the tensor-pipe percentage).
 """
@@ -444,6 +446,13 @@ def run_engine(a):
                 cpu = cpu_baseline(a, Ld[0].cpu().numpy(), Rd[0].cpu().numpy(), res[0])
             except Exception as e:      # the line is still worth printing
                 cpu = {"value": None, "unit": UNIT, "error": "%s: %s" % (type(e).__name__, e)}
+        other = None
+        if world == 1 and not a.no_extras:
+            log("timing BASELINE configs 1 and 2 in child processes (--no-extras skips them)")
+            try:
+                other = other_configs(a)
+            except Exception as e:
+                other = {"error": "%s: %s" % (type(e).__name__, e)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_dev / a.steps, "ms_per_pair": ms_dev / (a.steps * P), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
@@ -464,13 +473,34 @@ def run_engine(a):
                 "canvas_MP_per_s": canvas_px / 1e6 * a.steps / (ms_dev / 1000.0),
                 "latency": latency, "wall_ms_per_step": wall_ms / a.steps,
                 "collective": ("all_gather of %d x 96 B homography records per step (NCCL)" % n_total) if world > 1 else "none (single GPU)",
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu, "other_configs": other}
     barrier()
     if rank == 0:
         print(json.dumps(line, default=float), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(a, runner=subprocess.run):
+    """BASELINE configs 1 (mountain pair, beside the reference's CPU code) and 2 (oilseed fold, scored with the evaluator)
+    measured in the same run: each in a CHILD process (`bench.py --workload c1|c2`, tools/bench_configs.py), so that
+    nothing they do - a missing image, an error, a crash - can touch the headline line; their JSON lines are embedded."""
+    out = {}
+    for name, extra in (("c1", []), ("c2", ["--no-cpu"])):
+        try:
+            t0 = time.perf_counter()
+            p = runner([sys.executable, os.path.abspath(__file__), "--workload", name] + extra, capture_output=True, text=True,
+                       timeout=a.extras_timeout)
+            lines = [l for l in (p.stdout or "").splitlines() if l.startswith("{")]
+            if p.returncode == 0 and lines:
+                out[name] = json.loads(lines[-1])
+                out[name]["child_seconds"] = round(time.perf_counter() - t0, 1)
+            else:
+                out[name] = {"error": "child exit code %s: %s" % (p.returncode, (p.stderr or "")[-300:])}
+        except Exception as e:      # timeout, unparsable output: the headline does not depend on it
+            out[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return out
 
 
 def cpu_baseline(a, l, r, eng_res):
@@ -537,6 +567,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="batch lanes (host threads) per GPU; 0 = from the core count")
     ap.add_argument("--size", default="3840x2160")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE config 1 / 2 child runs (other_configs)")
+    ap.add_argument("--extras-timeout", type=float, default=240.0, help="seconds per child run of other_configs")
     a = ap.parse_args()
     a.w, a.h = [int(v) for v in a.size.split("x")]
     if a.workload != "c5":

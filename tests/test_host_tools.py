@@ -63,3 +63,30 @@ def test_stall_summary_tool_reads_the_committed_source_pages():
     h = mod.summarise(os.path.join(d, "r02_harris_fused_kernel.source_sass.csv"))
     assert h["opcode_executed"]["DMUL"] > 2e7 and h["opcode_executed"]["DADD"] > 2e7           # separately rounded: no DFMA
     assert h["opcode_executed"].get("DFMA", 0) == 0
+
+
+def test_bench_other_configs_embeds_child_lines_and_survives_failures():
+    """bench.py's other_configs leg: the BASELINE config 1 / 2 child runs are embedded when they succeed and reduced to
+    an error note when they fail, time out or print garbage - the headline line never depends on them"""
+    import importlib.util
+    import subprocess
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = types.SimpleNamespace(extras_timeout=5.0)
+    calls = []
+
+    def runner(cmd, **kw):
+        calls.append(cmd)
+        name = cmd[cmd.index("--workload") + 1]
+        if name == "c1":
+            return types.SimpleNamespace(returncode=0, stdout='noise\n{"metric": "ms_per_pair", "engine": {"ms": 1.5}}\n', stderr="")
+        raise subprocess.TimeoutExpired(cmd, 5.0)
+    out = bench.other_configs(a, runner=runner)
+    assert out["c1"]["metric"] == "ms_per_pair" and out["c1"]["engine"]["ms"] == 1.5 and "child_seconds" in out["c1"]
+    assert "TimeoutExpired" in out["c2"]["error"]
+    assert [c[c.index("--workload") + 1] for c in calls] == ["c1", "c2"] and "--no-cpu" in calls[1]
+    bad = bench.other_configs(a, runner=lambda cmd, **kw: types.SimpleNamespace(returncode=3, stdout="", stderr="boom"))
+    assert "exit code 3" in bad["c1"]["error"] and "boom" in bad["c2"]["error"]
+
