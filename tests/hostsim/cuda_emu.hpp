@@ -113,8 +113,8 @@ struct Fiber {
 };
 
 struct Warp {
-  unsigned arrived = 0;   // lanes waiting at the current warp rendezvous
-  unsigned gen = 0;
+  unsigned arrived = 0;   // lanes waiting at a warp rendezvous
+  unsigned released = 0;  // lanes whose rendezvous has completed and that have not resumed yet
   unsigned alive = 0;
   uint64_t slot[32];
 };
@@ -193,15 +193,23 @@ inline void sync_block() {
   }
 }
 
+// rendezvous of the live lanes of `mask` (several disjoint groups of one warp may meet independently: a lane is
+// released by the completion of ITS group only)
 inline void sync_warp(unsigned mask) {
   State& s = *S;
   Warp& w = s.warps[s.cur->tid >> 5];
-  const unsigned lane = s.cur->tid & 31;
-  const unsigned gen = w.gen;
-  w.arrived |= 1u << lane;
+  const unsigned lane = s.cur->tid & 31, bit = 1u << lane;
+  w.arrived |= bit;
   s.progress++;
-  while (w.gen == gen) {
-    if ((w.arrived & mask) == (mask & w.alive)) { w.arrived &= ~mask; w.gen++; s.progress++; break; }
+  for (;;) {
+    if (w.released & bit) { w.released &= ~bit; break; }
+    const unsigned group = mask & w.alive;
+    if ((w.arrived & group) == group) {       // the last one in: release the others, go on
+      w.arrived &= ~group;
+      w.released |= group & ~bit;
+      s.progress++;
+      break;
+    }
     yield();
   }
 }

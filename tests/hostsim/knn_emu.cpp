@@ -87,9 +87,27 @@ __global__ void selftest_deadlock_kernel(int* flag) {
     flag[0] = x;
   }
 }
+// the two halves of a warp meet independently (different masks, different numbers of collectives), then together
+__global__ void selftest_half_warps_kernel(int* out) {
+  const int lane = threadIdx.x & 31;
+  int v = lane;
+  if (lane < 16) {
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0x0000ffffu, v, o);      // sum of lanes 0..15 = 120
+  } else {
+    v = __shfl_sync(0xffff0000u, v, 31);                                          // lane 31's value
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, v == 120);
+  out[threadIdx.x] = v + (int)(b & 0xffffu);
+}
 }  // namespace
 
 extern "C" {
+
+int emu_selftest_half_warps(int* out64) {
+  g_error = nullptr;
+  run(dim3(1), dim3(64), [&] { selftest_half_warps_kernel(out64); }, 0);
+  return g_error ? 1 : 0;
+}
 
 int emu_selftest_reduce(const int* in, int n, int blocks, int threads) {
   g_error = nullptr;

@@ -210,6 +210,9 @@ def test_emulation_selftests(knn_emu):
     v = rng.integers(-1000, 1000, 5000).astype(np.int32)
     for blocks, threads in ((1, 32), (3, 256), (7, 96), (2, 1024)):
         assert knn_emu.emu_selftest_reduce(p(v, C.c_int32), len(v), blocks, threads) == int(v.sum())
+    out = np.zeros(64, np.int32)
+    assert knn_emu.emu_selftest_half_warps(p(out, C.c_int32)) == 0          # disjoint groups of one warp meet independently
+    assert list(out[:16]) == [120 + 0xffff] * 16 and list(out[16:32]) == [31 + 0xffff] * 16 and list(out[32:]) == list(out[:32])
     assert knn_emu.emu_selftest_deadlock() == 1
     assert b"deadlock" in knn_emu.emu_last_error()
 
