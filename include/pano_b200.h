@@ -162,6 +162,15 @@ int pano_match_knn(pano_ctx* ctx, const int32_t* kp_query, int n_query, const in
                    const uint8_t* img_train, int wt, int ht, size_t stride_t, int mem,
                    const pano_knn_opts* opts, pano_dmatch* out, float* second_out, int cap, int* count);
 
+/* Matcher of the fused calls (pano_stitch_pair / _fold / _batch, pano_pair_homography and their asynchronous forms).
+ * mode 0 (default): the reference's matcher (pano_match) - results are the reference's, bit for bit.
+ * mode 1 (opt-in, behaviour changing): pano_match_knn with `ratio` and `descriptor`, patch size taken from the call's
+ *         pano_harris_opts - RANSAC then draws from the ratio-tested matches only.  Results differ from the reference's
+ *         by design (on its own oilseed sample the reference's outcome depends on the RANSAC seed because 77 % of its
+ *         matches are outliers; the ratio test leaves 9 %).  The shuffle replay cannot be started before the match count
+ *         is known in this mode, so a pair takes slightly longer. */
+int pano_set_match_mode(pano_ctx* ctx, int mode, double ratio, int descriptor);
+
 /* ref: GpuRansacHomographyCalculator::computeHomography(kp1, kp2, matches)
  *      (src/gpu/ransac.cuh:8-36) with the semantics of
  *      SeqRansacHomographyCalculator::computeHomography (src/serial/main.cpp:247-307).

@@ -260,10 +260,16 @@ void match_knn(const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8
     describe(imt, st, x, y, &tp[tp.size() - dlen]);
   }
   const double factor = descriptor == 1 ? ratio : ratio * ratio;
-  std::vector<uint8_t> qp((size_t)dlen);
+  std::vector<KnnMatch> res((size_t)nq);
+  std::vector<uint8_t> has((size_t)nq, 0);
+  if (descriptor == 1) { uint32_t warm[8]; knn_binary_descriptor(imt, st, 2, 2, warm); }   // (builds the pair table before threads start)
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
   for (int i = 0; i < nq; i++) {
     const int x = kq[2 * i], y = kq[2 * i + 1];
     if (x < border || y < border || x + border >= wq || y + border >= hq) continue;
+    std::vector<uint8_t> qp((size_t)dlen);
     describe(imq, sq, x, y, qp.data());
     int j1 = -1, j2 = -1;
     uint32_t d1 = 0, d2 = 0;
@@ -273,8 +279,10 @@ void match_knn(const int32_t* kq, int nq, const int32_t* kt, int nt, const uint8
       else if (j2 < 0 || d < d2) { j2 = (int)jj; d2 = d; }
     }
     if (j2 < 0) continue;   // fewer than two candidates: no runner-up, no match
-    if ((double)d1 < factor * (double)d2) out.push_back(KnnMatch{i, tj[(size_t)j1], (float)d1, (float)d2});
+    if ((double)d1 < factor * (double)d2) { res[(size_t)i] = KnnMatch{i, tj[(size_t)j1], (float)d1, (float)d2}; has[(size_t)i] = 1; }
   }
+  for (int i = 0; i < nq; i++)
+    if (has[(size_t)i]) out.push_back(res[(size_t)i]);
 }
 
 // Inlier predicate of ref: src/serial/main.cpp:285-293.

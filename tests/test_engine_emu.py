@@ -190,6 +190,79 @@ def test_emulated_engine_async_stage_calls(engine, oracle, pair):
     assert np.array_equal(engine.getCanvas(), oracle.compose(left, right, o["H"]))
 
 
+def oracle_pair_knn(oracle, left, right, ratio, descriptor, iters, seed=12345):
+    """what the fused calls do in match mode 1, assembled from the checker's stage functions"""
+    kl, kr = oracle.detect(left), oracle.detect(right)
+    m, _ = oracle.match_knn(kr, kl, right, left, descriptor=descriptor, ratio=ratio)
+    if len(m) < 4:
+        return None, len(kl), len(kr), len(m), None
+    o = oracle.ransac(kr, kl, m, iters=iters, seed=seed)
+    return o, len(kl), len(kr), len(m), (oracle.compose(left, right, o["H"]) if o["ok"] else None)
+
+
+@pytest.mark.parametrize("descriptor,ratio", [(0, 0.75), (1, 0.9)])
+def test_emulated_engine_pair_with_the_ratio_test_matcher(engine, oracle, pair, descriptor, ratio):
+    """pano_set_match_mode(ctx, 1, ...): the fused pair runs detection, the 2-NN matcher (tensor-core top-2 epilogue on its
+    model, or the binary path), RANSAC on the ratio-tested matches, and the warp - and goes back to the reference's
+    matcher afterwards"""
+    pkg = load_pkg()
+    left, right = pair
+    iters = 120
+    ro = pkg.RansacOptions(numIterations_=iters)
+    engine.set_match_mode(1, ratio=ratio, descriptor=descriptor)
+    try:
+        canvas, r = engine.stitchTwoImages(left, right, ransacOpts=ro)
+    finally:
+        engine.set_match_mode(0)
+    o, nkl, nkr, nm, want = oracle_pair_knn(oracle, left, right, ratio, descriptor, iters)
+    assert o is not None and o["ok"] and r["status"] == 0
+    assert (r["kl"], r["kr"], r["m"], r["best"]) == (nkl, nkr, nm, o["best_count"])
+    assert np.array_equal(bits(r["H"]), bits(o["H"])) and np.array_equal(canvas, want)
+    ref_m = len(oracle.match(oracle.detect(right), oracle.detect(left), right, left))
+    assert r["m"] < ref_m                                             # the ratio test removed matches
+    _, r0 = engine.stitchTwoImages(left, right, ransacOpts=ro, fetch=False)
+    assert r0["m"] == ref_m                                           # mode 0 again: the reference's matcher
+    with pytest.raises(pkg.PanoError):
+        engine.set_match_mode(1, ratio=1.5)
+    engine.set_match_mode(1, descriptor=pkg.KNN_BINARY)
+    try:
+        with pytest.raises(pkg.PanoError) as e:                        # the binary descriptor is defined on 5 x 5 patches
+            engine.stitchTwoImages(left, right, harrisOpts=pkg.HarrisCornerOptions(patchSize_=3))
+        assert e.value.status == pkg.PANO_ERR_UNSUPPORTED
+    finally:
+        engine.set_match_mode(0)
+
+
+def test_emulated_engine_batch_of_pairs_in_both_match_modes(engine, oracle):
+    """pano_stitch_batch (two lane threads taking turns on the emulated device; slots, the A / B pipeline, the shared
+    mt19937 stream, canvases written to host buffers) = the pairs one by one, with the reference's matcher and with the
+    opt-in ratio-test matcher handed down to the slots"""
+    pkg = load_pkg()
+    os.environ["PANO_BATCH_LANES"] = "2"
+    views = load_synth().make_strip(n=3, w=240, h=160, seed=21)
+    iters = 100
+    ro = pkg.RansacOptions(numIterations_=iters)
+    lefts, rights = [views[0], views[1]], [views[1], views[2]]
+    cap = 3 * 700 * 300
+    outs = [np.zeros(cap, np.uint8) for _ in lefts]
+    res, _ = engine.stitchBatch(lefts, rights, ransacOpts=ro, canvases_out=outs)
+    for i, (l, r) in enumerate(zip(lefts, rights)):
+        kl, kr = oracle.detect(l), oracle.detect(r)
+        o = oracle.ransac(kr, kl, oracle.match(kr, kl, r, l), iters=iters, seed=12345)
+        want = oracle.compose(l, r, o["H"])
+        assert res[i]["status"] == 0 and np.array_equal(bits(res[i]["H"]), bits(o["H"]))
+        assert np.array_equal(outs[i][:want.size].reshape(want.shape), want)
+    engine.set_match_mode(1, ratio=0.8)
+    try:
+        res, _ = engine.stitchBatch(lefts, rights, ransacOpts=ro)
+    finally:
+        engine.set_match_mode(0)
+        os.environ["PANO_BATCH_LANES"] = "1"
+    for i, (l, r) in enumerate(zip(lefts, rights)):
+        o, _, _, nm, _ = oracle_pair_knn(oracle, l, r, 0.8, 0, iters)
+        assert res[i]["status"] == 0 and res[i]["m"] == nm and np.array_equal(bits(res[i]["H"]), bits(o["H"]))
+
+
 def test_emulated_gpu_stitching_executable_chain_mode(engine, oracle, tmp_path):
     """host/gpu_stitching.cpp itself (with reader and image codecs) linked against the emulated library and the fake CUDA
     runtime: PANO_MODE=chain over two "devices" (worker threads, per-device contexts, bands into the host canvas; the

@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "pano_set_fold_mode", "pano_stitch_pair_async", "pano_pair_query", "pano_pair_wait", "pano_set_profile", "pano_get_profile",
     "pano_default_knn_opts", "pano_match_knn",
     "pano_detect_async", "pano_match_async", "pano_ransac_async", "pano_warp_overlay_async", "pano_stitch_fold_async",
-    "pano_stitch_batch_async",
+    "pano_stitch_batch_async", "pano_set_match_mode",
 ]
 
 
@@ -201,6 +201,11 @@ class Engine:
     def set_matcher(self, which):
         """0 = tensor-core matcher (product), 1 = SIMT cross-check kernel"""
         self._check(self.lib.pano_set_matcher(self.ctx, int(which)))
+
+    def set_match_mode(self, mode, ratio=0.75, descriptor=KNN_PATCH_SSD):
+        """matcher of the fused calls: 0 = the reference's (default), 1 = 2-NN + Lowe's ratio test (opt-in; results differ
+        from the reference's by design)"""
+        self._check(self.lib.pano_set_match_mode(self.ctx, int(mode), C.c_double(ratio), int(descriptor)))
 
     def set_fold_mode(self, mode):
         """0 = the reference's fold (re-detect on the panorama), 1 = incremental (carry the keypoints; opt-in)"""

@@ -28,6 +28,8 @@ struct pano_ctx {
   int device = 0;
   uint32_t seed = 0;
   int matcher = 0;  // 0 tensor-core, 1 SIMT
+  int match_mode = 0;        // fused calls: 0 the reference's matcher, 1 pano_match_knn (opt-in; pano_set_match_mode)
+  pano_knn_opts knn_mode = {5, PANO_KNN_PATCH_SSD, 0.75};
   double replay_target = 0;  // candidate walks per replay chunk (0 = default)
   bool overlap_replay = true;  // stitch: start the shuffle replay as soon as the match count is known (own stream)
   int replay_mode = 0;       // 0: chunked speculative replay (lowest latency), 1: resident one-CTA replay (least work)
@@ -158,6 +160,12 @@ int check_harris(const pano_harris_opts& o) {
   return PANO_OK;
 }
 
+// fused calls with the opt-in 2-NN matcher: the binary descriptor is defined on 5 x 5 patches only
+int check_match_mode(const pano_ctx* c, const pano_harris_opts& o) {
+  if (c->match_mode == 1 && c->knn_mode.descriptor == PANO_KNN_BINARY && o.patch_size != 5) return PANO_ERR_UNSUPPORTED;
+  return PANO_OK;
+}
+
 void run_matcher(pano_ctx* c, const DevDescriptors& q, const DevDescriptors& t) {
   c->best.reserve(sizeof(unsigned long long) * (size_t)std::max(q.count, 1));
   if (c->matcher == 0 && match_tc_available())
@@ -274,8 +282,9 @@ int pair_stage_a(pano_ctx* c, const DevImage& L, const DevImage& R, const pano_h
   res->n_kp_right = harris_detect_device(st, R, ho, c->hs, c->kpR, c->pin);
   bool prelaunched = false;
   int nqi = 0;
-  // (with per-kernel profiling on, the replay is not overlapped: every kernel is then timed alone on the GPU)
-  const bool try_overlap = c->overlap_replay && !c->prof.on && ro.num_samples == 4;
+  // (with per-kernel profiling on, the replay is not overlapped: every kernel is then timed alone on the GPU; with the
+  // opt-in 2-NN matcher the match count is only known after the ratio test)
+  const bool try_overlap = c->overlap_replay && !c->prof.on && ro.num_samples == 4 && c->match_mode == 0;
   if (try_overlap) {
     nqi = build_descriptors_device(st, R, c->kpR.xy.as<int32_t>(), c->kpR.count, ho.patch_size, c->ms, c->dQ, c->pin);
     if (nqi >= ro.num_samples && ro.num_iterations > 0) {
@@ -293,8 +302,24 @@ int pair_stage_a(pano_ctx* c, const DevImage& L, const DevImage& R, const pano_h
   c->job.n_left = kl->count;
   c->job.left_xy = kl->xy.as<int32_t>();
   PANO_CUDA(cudaEventRecord(c->ev[1], st));
-  int m = match_on_device(c, c->kpR.xy.as<int32_t>(), c->kpR.count, kl->xy.as<int32_t>(), kl->count, R, L,
-                          ho, 0, try_overlap, nqi);
+  int m;
+  if (c->match_mode == 0) {
+    m = match_on_device(c, c->kpR.xy.as<int32_t>(), c->kpR.count, kl->xy.as<int32_t>(), kl->count, R, L, ho, 0, try_overlap,
+                        nqi);
+  } else {
+    // opt-in: 2 nearest neighbours + Lowe's ratio test (knn.cu); the ratio-tested matches become RANSAC's input
+    pano_knn_opts ko = c->knn_mode;
+    ko.patch_size = ho.patch_size;
+    const int nq = build_descriptors_device(st, R, c->kpR.xy.as<int32_t>(), c->kpR.count, ko.patch_size, c->ms, c->dQ, c->pin);
+    const int nt = build_descriptors_device(st, L, kl->xy.as<int32_t>(), kl->count, ko.patch_size, c->ms, c->dT, c->pin);
+    m = 0;
+    if (nq > 0 && nt > 0)
+      m = match_knn_device(st, R, L, c->kpR.xy.as<int32_t>(), kl->xy.as<int32_t>(), c->dQ, c->dT, ko,
+                           c->matcher == 0 && match_tc_available(), c->ms, c->best, c->ks, c->pin, c->errw.as<int>());
+    c->matches.reserve(sizeof(pano_dmatch) * (size_t)std::max(m, 1));
+    if (m > 0)
+      PANO_CUDA(cudaMemcpyAsync(c->matches.p, c->ks.out.p, sizeof(pano_dmatch) * (size_t)m, cudaMemcpyDeviceToDevice, st));
+  }
   res->n_matches = m;
   PANO_CUDA(cudaEventRecord(c->ev[2], st));
   if (prelaunched && m != nqi) {   // not the count the replay was started for: let it drain, then ignore it
@@ -511,6 +536,19 @@ int pano_set_seed(pano_ctx* c, uint32_t seed) {
 int pano_set_matcher(pano_ctx* c, int which) {
   if (!c || (which != 0 && which != 1)) return PANO_ERR_INVALID;
   c->matcher = which;
+  return PANO_OK;
+}
+
+int pano_set_match_mode(pano_ctx* c, int mode, double ratio, int descriptor) {
+  if (!c || (mode != 0 && mode != 1)) return PANO_ERR_INVALID;
+  if (mode == 1) {
+    if (!(ratio > 0.0) || ratio > 1.0) return fail(c, PANO_ERR_INVALID, "pano_set_match_mode: ratio outside (0, 1]");
+    if (descriptor != PANO_KNN_PATCH_SSD && descriptor != PANO_KNN_BINARY)
+      return fail(c, PANO_ERR_UNSUPPORTED, "pano_set_match_mode: unknown descriptor");
+    c->knn_mode.ratio = ratio;
+    c->knn_mode.descriptor = descriptor;
+  }
+  c->match_mode = mode;
   return PANO_OK;
 }
 
@@ -737,6 +775,7 @@ int pano_stitch_pair(pano_ctx* c, const uint8_t* left, int wl, int hl, size_t st
   if (!valid_image(left, wl, hl, stride_l) || !valid_image(right, wr, hr, stride_r) || !hopts || !ropts || !res)
     return fail(c, PANO_ERR_INVALID, "pano_stitch_pair: bad argument");
   if (int e = check_harris(*hopts)) return fail(c, e, "pano_stitch_pair: unsupported option");
+  if (int e = check_match_mode(c, *hopts)) return fail(c, e, "pano_stitch_pair: the binary descriptor needs patch size 5");
   if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
   DevImage L = to_device(c, left, wl, hl, stride_l, mem, 0);
   DevImage R = to_device(c, right, wr, hr, stride_r, mem, 1);
@@ -752,6 +791,7 @@ int pano_stitch_pair_async(pano_ctx* c, const uint8_t* left, int wl, int hl, siz
   if (!valid_image(left, wl, hl, stride_l) || !valid_image(right, wr, hr, stride_r) || !hopts || !ropts || !res)
     return fail(c, PANO_ERR_INVALID, "pano_stitch_pair_async: bad argument");
   if (int e = check_harris(*hopts)) return fail(c, e, "pano_stitch_pair_async: unsupported option");
+  if (int e = check_match_mode(c, *hopts)) return fail(c, e, "pano_stitch_pair_async: the binary descriptor needs patch size 5");
   if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
   if (!c->ev_async) PANO_CUDA(cudaEventCreateWithFlags(&c->ev_async, cudaEventDisableTiming));
   c->async_stream = stream;
@@ -900,6 +940,7 @@ int pano_stitch_fold(pano_ctx* c, const uint8_t* const* images, const int* ws, c
   for (int i = 0; i < n; i++)
     if (!valid_image(images[i], ws[i], hs[i], strides[i])) return fail(c, PANO_ERR_INVALID, "pano_stitch_fold: bad image");
   if (int e = check_harris(*hopts)) return fail(c, e, "pano_stitch_fold: unsupported option");
+  if (int e = check_match_mode(c, *hopts)) return fail(c, e, "pano_stitch_fold: the binary descriptor needs patch size 5");
   if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
   // panorama = images[0] (ref :400): place it in the current canvas slot
   {
@@ -998,6 +1039,7 @@ int pano_pair_homography(pano_ctx* c, const uint8_t* left, int wl, int hl, size_
   if (!valid_image(left, wl, hl, stride_l) || !valid_image(right, wr, hr, stride_r) || !hopts || !ropts || !res)
     return fail(c, PANO_ERR_INVALID, "pano_pair_homography: bad argument");
   if (int e = check_harris(*hopts)) return fail(c, e, "pano_pair_homography: unsupported option");
+  if (int e = check_match_mode(c, *hopts)) return fail(c, e, "pano_pair_homography: the binary descriptor needs patch size 5");
   if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
   DevImage L = to_device(c, left, wl, hl, stride_l, mem, 0);
   DevImage R = to_device(c, right, wr, hr, stride_r, mem, 1);
@@ -1068,6 +1110,7 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
     if (!valid_image(lefts[i], wl, hl, stride_l) || !valid_image(rights[i], wr, hr, stride_r))
       return fail(c, PANO_ERR_INVALID, "pano_stitch_batch: bad image");
   if (int e = check_harris(*hopts)) return fail(c, e, "pano_stitch_batch: unsupported option");
+  if (int e = check_match_mode(c, *hopts)) return fail(c, e, "pano_stitch_batch: the binary descriptor needs patch size 5");
   if (ropts->num_samples != 4) return fail(c, PANO_ERR_UNSUPPORTED, "only num_samples == 4 is supported");
   // Pairs are independent: run them on several lanes (child contexts, each with its own stream,
   // scratch and host thread) so that one pair's host synchronisations, copies and low-occupancy
@@ -1133,6 +1176,8 @@ int pano_stitch_batch(pano_ctx* c, int n, const uint8_t* const* lefts, const uin
         pano_ctx* sl = lane_slots[q];
         sl->seed = c->seed;
         sl->matcher = c->matcher;
+        sl->match_mode = c->match_mode;
+        sl->knn_mode = c->knn_mode;
         sl->rs.shared_mt = &c->mt;
         sl->pack_tight = host_io && canvases_out != nullptr;
         // replay: chunked with small chunks (least speculative work) unless PANO_BATCH_REPLAY=1 asks for the resident

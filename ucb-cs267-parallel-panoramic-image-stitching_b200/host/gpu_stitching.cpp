@@ -9,6 +9,7 @@
 // Opt-in, behaviour changing: PANO_MODE=chain stitches in chain mode (adjacent pairs estimated independently, SURVEY
 // 8e2) over PANO_GPUS devices of this box (default: all visible) inside this one process - pairs sharded over the
 // devices, canvas bands rendered per device (host/chain_multi_gpu.hpp).  The default is the reference's fold.
+// PANO_MATCH=knn[:ratio] makes the fold use the 2-NN / Lowe-ratio matcher (pano_set_match_mode).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -126,12 +127,27 @@ int main(int argc, char** argv) {
   uint32_t seed = sd ? (uint32_t)std::strtoul(sd, nullptr, 10) : 12345u;
   if (const char* mode = std::getenv("PANO_MODE"))
     if (std::string(mode) == "chain") return run_chain(rr, seed, harrisOpts, ransacOpts, totalTimer);
+  // (PANO_MATCH below applies to the fold; chain mode keeps the reference's matcher)
   pano_ctx* ctx = nullptr;
   int st = pano_create(device, seed, &ctx);
   if (st != PANO_OK) {
     std::cerr << "gpu_stitching: cannot create the B200 engine (status " << st
               << "): an sm_100 GPU is required, there is no CPU path" << std::endl;
     return -1;
+  }
+
+  // opt-in, behaviour changing: PANO_MATCH=knn[:ratio] - 2 nearest neighbours + Lowe's ratio test (default ratio 0.75)
+  // instead of the reference's nearest-patch matcher (pano_set_match_mode)
+  if (const char* mm = std::getenv("PANO_MATCH")) {
+    const std::string v(mm);
+    if (v.rfind("knn", 0) == 0) {
+      const double ratio = v.size() > 4 && v[3] == ':' ? std::atof(v.c_str() + 4) : 0.75;
+      if (pano_set_match_mode(ctx, 1, ratio, PANO_KNN_PATCH_SSD) != PANO_OK) {
+        std::cerr << "gpu_stitching: bad PANO_MATCH value '" << v << "': " << pano_last_error(ctx) << std::endl;
+        return -1;
+      }
+      std::cout << "Matcher: 2-NN + ratio test " << ratio << " (opt-in; not the reference's matcher)" << std::endl;
+    }
   }
 
   // stitchAllImages: left fold, the panorama stays in device memory
