@@ -284,9 +284,23 @@ inline const char* launch(dim3 grid, dim3 block, const std::function<void()>& bo
       st.warps[t >> 5].alive |= 1u << (t & 31);
       prepare_fiber(f);
     }
+    // PANO_EMU_THREAD_ORDER: the order in which the runnable threads of a block get their turn between two rendezvous
+    // points - 0 ascending (default), 1 descending, 2 a new pseudo-random permutation every round.  A kernel whose result
+    // depends on it has a race (a missing __syncthreads / __syncwarp, an assumption of warp lockstep): the emulation
+    // tests are run under all three (tools/emu_sanitize.sh).
+    static const int thread_order = [] { const char* e = getenv("PANO_EMU_THREAD_ORDER"); return e ? atoi(e) : 0; }();
+    std::vector<unsigned> turn(nthreads);
+    for (unsigned t = 0; t < nthreads; t++) turn[t] = thread_order == 1 ? nthreads - 1 - t : t;
+    uint32_t rs = 88172645u + b;
     while (st.live > 0) {
       const uint64_t before = st.progress;
-      for (unsigned t = 0; t < nthreads; t++) {
+      if (thread_order == 2)
+        for (unsigned i = nthreads; i > 1; i--) {
+          rs ^= rs << 13; rs ^= rs >> 17; rs ^= rs << 5;
+          std::swap(turn[i - 1], turn[rs % i]);
+        }
+      for (unsigned ti = 0; ti < nthreads; ti++) {
+        const unsigned t = turn[ti];
         Fiber& f = st.fibers[t];
         if (f.done) continue;
         st.cur = &f;

@@ -7,7 +7,10 @@ descriptors into tensor memory, tcgen05.commit, tcgen05.ld, named barriers).  Wh
 logic: super-tile scheduling and runs that cross super-rows, pipeline stages and barrier phases (a wrong wait or release
 shows up as a reported deadlock), descriptor arithmetic, the epilogue's packed keys and reductions, padding columns and
 rows, the cross-CTA merge (atomicMin / the two-slot publication).  That the hardware agrees with the model is what the
-GPU tier establishes (tests/test_gpu_parity.py: tensor-core matcher = SIMT matcher = oracle)."""
+GPU tier establishes (tests/test_gpu_parity.py: tensor-core matcher = SIMT matcher = oracle).
+(Run with the emulation's default thread order.  Under PANO_EMU_THREAD_ORDER=1|2 - adversarial scheduling - a consumer
+warp can be held back until its stage's barrier has advanced two phases, which the emulation reports as a deadlock:
+DESIGN section 9.)"""
 import ctypes as C
 
 import numpy as np

@@ -25,3 +25,13 @@ for SAN in ${1:-address undefined}; do
     UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 python -m pytest $TESTS -x -q 2>&1 | tail -3
 done
 rm -f tests/hostsim/lib*_emu.so tests/hostsim/gpu_stitching_emu
+# Scheduling-order independence: the same kernels with the runnable threads of a block taking their turns in descending
+# and in pseudo-random order (PANO_EMU_THREAD_ORDER).  A result that depends on the order is a race (missing barrier,
+# warp-lockstep assumption).  The tensor-core matcher is left out: under adversarial scheduling a consumer warp can be
+# held back until its operand stage's barrier has advanced two phases - reported as a deadlock by the
+# emulation, bounded by the spin limit and the error word on the device.
+for ORDER in 1 2; do
+  echo "== thread order $ORDER"
+  PANO_EMU_THREAD_ORDER=$ORDER python -m pytest tests/test_knn.py tests/test_harris_emu.py tests/test_warp_emu.py tests/test_match_emu.py \
+    tests/test_ransac_emu.py -q 2>&1 | tail -2
+done
