@@ -288,3 +288,39 @@ def test_emulated_gpu_stitching_executable_chain_mode(engine, oracle, tmp_path):
                    "Total Stitching Process: ", "Stitched result saved to " + out, "Total Execution Time: "):
         assert needle in r.stdout, needle
     assert np.array_equal(cv2.imread(out), pano)
+
+
+def test_reference_gpu_main_on_the_emulated_engine(engine, tmp_path):
+    """SURVEY 8 b2 without a GPU: the reference's own GPU executable - src/gpu/main.cpp compiled UNMODIFIED from
+    /root/reference - with its four .cu stage files replaced by the maintainer-side binding
+    (examples/reference_shim/pano_b200_shim.cpp -> C ABI), linked against the EMULATED engine library: detection, matching
+    (tensor-core matcher on its model) and RANSAC are the engine's own code, geometry / warp / overlay the reference's.
+    Its panorama must be the one the reference's serial code produces for the same seed.  (tests/test_reference_shim.py
+    does this on a stand-in of the ABI, tests/test_zz1_reference_gpu_main.py on a B200.)"""
+    import subprocess
+    cv2 = pytest.importorskip("cv2")
+    ref_root = "/root/reference"
+    if not os.path.exists(os.path.join(ref_root, "src", "gpu", "main.cpp")):
+        pytest.skip("/root/reference not present: nothing to compile")
+    from oracle import ref as refmod
+    if not refmod.available():
+        pytest.skip("oracle/_ref not built")
+    o = os.path.join(ROOT, "oracle")
+    hs = os.path.join(ROOT, "tests", "hostsim")
+    exe = str(tmp_path / "gpu_stitching_refmain_emu")
+    subprocess.check_call(
+        ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-w", "-I" + os.path.join(o, "cvshim"), "-I" + ref_root + "/src",
+         "-I" + ref_root + "/src/reader", "-I" + ref_root + "/src/gpu", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+         ref_root + "/src/gpu/main.cpp", ref_root + "/src/reader/reader.cpp",
+         os.path.join(ROOT, "examples", "reference_shim", "pano_b200_shim.cpp"), os.path.join(o, "cvshim", "cvshim.cpp"),
+         os.path.join(hs, "libpano_b200_emu.so"), "-Wl,-rpath," + hs, "-lpthread"])
+    left, right, _ = load_synth().make_pair(320, 200, seed=9)
+    a, b, out = str(tmp_path / "a.ppm"), str(tmp_path / "b.ppm"), str(tmp_path / "pano.ppm")
+    assert cv2.imwrite(a, left) and cv2.imwrite(b, right)
+    r = subprocess.run([exe, a, b, "--out", out], capture_output=True, text=True, timeout=900, env=dict(os.environ, PANO_SEED="7"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Harris Corner Matching (GPU):" in r.stdout and "RANSAC Homography Estimation (GPU):" in r.stdout
+    assert "falling back" not in r.stderr
+    ref = refmod.Reference().stitch_pair(left, right, seed=7)
+    assert ref["status"] == 1 and np.array_equal(cv2.imread(out), ref["canvas"])
+
