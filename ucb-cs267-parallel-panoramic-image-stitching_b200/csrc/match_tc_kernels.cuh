@@ -258,6 +258,17 @@ __device__ __forceinline__ void match_tc_body(const CUtensorMap& tmap_q, const C
         // every thread acquires the stage (descriptor tile + column constants written by the async proxy)
         ok = mbar_wait(&S.b_full[s], sph, abort_flag);
         if (!ok) break;
+#ifdef PANO_TC_BARRIER_AFTER_STAGE_WAIT
+        // (variant, off by default - DESIGN section 9: the group meets AFTER every thread has observed this unit's stage
+        // instead of right after draining the previous one.  Same number of barriers; the leader's MMAs - whose commit
+        // lets the producer refill the stage - then cannot be issued before all 128 threads have passed their wait, so no
+        // thread can find the stage barrier two phases on.  The drain of the previous unit still precedes the barrier.)
+#ifdef PANO_CUDA_EMU
+        emu::named_barrier(1 + g, 128);
+#else
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory");
+#endif
+#endif
         if (leader) {
           // accumulator g is free: the whole group passed the named barrier below after draining the previous unit
           tc_fence_after();
@@ -294,10 +305,12 @@ __device__ __forceinline__ void match_tc_body(const CUtensorMap& tmap_q, const C
         }
         tc_fence_before();
         // the group's 128 threads have read the accumulator: its leader may overwrite it (named barrier 1 + g)
+#ifndef PANO_TC_BARRIER_AFTER_STAGE_WAIT
 #ifdef PANO_CUDA_EMU
         emu::named_barrier(1 + g, 128);
 #else
         asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(128) : "memory");
+#endif
 #endif
         if constexpr (TOP2) {
           // the tile's two smallest keys out of the four chains' (valid keys of a tile are distinct: the column sits
