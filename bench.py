@@ -568,7 +568,7 @@ def main():
     ap.add_argument("--size", default="3840x2160")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE config 1 / 2 child runs (other_configs)")
-    ap.add_argument("--extras-timeout", type=float, default=240.0, help="seconds per child run of other_configs")
+    ap.add_argument("--extras-timeout", type=float, default=120.0, help="seconds per child run of other_configs")
     a = ap.parse_args()
     a.w, a.h = [int(v) for v in a.size.split("x")]
     if a.workload != "c5":
