@@ -52,10 +52,22 @@ inline void mbar_arrive(unsigned long long* bar) {
   b->pending--;
   mbar_check(b);
 }
+// Fault injection (tests only): PANO_EMU_TC_DROP_LOAD=N makes the TMA model drop the N-th tile load of the next matcher
+// kernel - no data, no complete_tx, so that stage's barrier never completes, like a lost transaction would on the
+// device.  From then on the waits are bounded the way the device's are (a wait that keeps failing raises the abort flag
+// and gives up), so that the host's recovery path - error word, failed call, tensor-core matcher disabled, SIMT matcher
+// taking over - can be exercised.
+inline long emu_tc_drop_countdown = -1;
+inline bool emu_tc_fault = false;
 inline bool mbar_wait(unsigned long long* bar, uint32_t parity, volatile int* abort_flag) {
   const MBarModel* b = reinterpret_cast<const MBarModel*>(bar);
+  unsigned spins = 0;
   while (b->phase == parity) {          // the phase of parity `parity` has not completed yet
     if (*abort_flag) return false;
+    if (emu_tc_fault) {                 // (bounded like the device's SPIN_LIMIT; polling counts as activity here)
+      emu::S->progress++;
+      if (++spins > 4096) { *abort_flag = 1; return false; }
+    }
     emu::yield();
   }
   emu::S->progress++;
@@ -80,6 +92,7 @@ inline uint32_t swizzle128_offset(uint32_t start, int row, int k) {
          (uint32_t)(kk & 15);
 }
 inline void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int row0, unsigned long long* bar) {
+  if (emu_tc_drop_countdown >= 0 && emu_tc_drop_countdown-- == 0) { emu_tc_fault = true; return; }   // (fault injection)
   uint8_t* smem = emu::dyn_smem();
   const uint32_t start = smem_u32(smem_dst);
   for (int r = 0; r < (int)map->box_rows; r++)
@@ -122,6 +135,13 @@ inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   for (int i = 0; i < 32; i++) r[i] = tmem_model[lane][col + i];
 }
 inline void tmem_ld_wait() {}
-inline void tmem_alloc_emu(uint32_t* slot, uint32_t) { *slot = 0; }
+inline void tmem_alloc_emu(uint32_t* slot, uint32_t) {
+  *slot = 0;
+  if (emu::S->cur->tid % 32 == 0 && blockIdx.x == 0) {      // once per launch: arm the fault injection, if asked for
+    const char* e = getenv("PANO_EMU_TC_DROP_LOAD");
+    emu_tc_drop_countdown = e ? atol(e) : -1;
+    emu_tc_fault = false;
+  }
+}
 
 }  // namespace pano

@@ -324,3 +324,48 @@ def test_reference_gpu_main_on_the_emulated_engine(engine, tmp_path):
     ref = refmod.Reference().stitch_pair(left, right, seed=7)
     assert ref["status"] == 1 and np.array_equal(cv2.imread(out), ref["canvas"])
 
+
+def test_emulated_engine_survives_a_matcher_pipeline_timeout(engine, tmp_path):
+    """The tensor-core matcher bounds every pipeline wait; a wait that gives up raises the context's error word.  The host
+    must then fail THAT call loudly (never emit matches from an aborted kernel), clear the word, stop using the
+    tensor-core matcher in this process and answer the next call with the SIMT matcher.  The device has never taken this
+    path in a test; here the TMA model drops one tile load, its stage barrier never completes and the (bounded) waits
+    give up (tests/hostsim/tcgen05_emu.hpp fault injection).  Runs in a child process because the switch to the SIMT
+    matcher is process-wide."""
+    import subprocess
+    import sys
+    script = tmp_path / "abort_child.py"
+    script.write_text("""
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import load_pkg, load_synth
+from oracle.oracle import Oracle
+pkg, o = load_pkg(), Oracle()
+lib = C.CDLL(%r)
+lib.pano_last_error.restype = C.c_char_p
+e = pkg.Engine.__new__(pkg.Engine)
+e.lib, e.ctx, e.device = lib, C.c_void_p(), 0
+assert lib.pano_create(0, C.c_uint32(12345), C.byref(e.ctx)) == 0
+left, right, _ = load_synth().make_pair(320, 200, seed=9)
+kl, kr = o.detect(left), o.detect(right)
+want = np.ascontiguousarray(o.match(kr, kl, right, left)).tobytes()
+assert e.gpuHarrisMatchKeyPoints(kr, kl, right, left).tobytes() == want          # tensor-core matcher (on its model)
+os.environ["PANO_EMU_TC_DROP_LOAD"] = "1"
+try:
+    e.gpuHarrisMatchKeyPoints(kr, kl, right, left)
+    raise SystemExit("the aborted call returned matches")
+except pkg.PanoError as err:
+    assert err.status == pkg.PANO_ERR_CUDA and "tensor-core matcher pipeline timed out" in str(err), str(err)
+del os.environ["PANO_EMU_TC_DROP_LOAD"]
+n0 = e.kernel_launches()
+assert e.gpuHarrisMatchKeyPoints(kr, kl, right, left).tobytes() == want          # the SIMT matcher has taken over
+canvas, r = e.stitchTwoImages(left, right, ransacOpts=pkg.RansacOptions(numIterations_=40))
+assert r["status"] == 0 and r["m"] == len(o.match(kr, kl, right, left))
+os.environ["PANO_EMU_TC_DROP_LOAD"] = "0"                                        # no tensor-core kernel runs any more
+assert e.gpuHarrisMatchKeyPoints(kr, kl, right, left).tobytes() == want
+print("OK")
+""" % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "hostsim", "libpano_b200_emu.so")))
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-500:], r.stderr[-1500:])
+
