@@ -46,7 +46,13 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 148; return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 
+// Fault injection (tests only): pano_emu_fail_malloc(n) makes the n-th cudaMalloc / cudaMallocHost from now on fail
+// (n = 0: the next one; negative: never), to exercise the engine's error paths under memory exhaustion.
+inline long emu_fail_malloc_countdown = -1;
+extern "C" __attribute__((weak)) void pano_emu_fail_malloc(long n) { emu_fail_malloc_countdown = n; }
+inline bool emu_malloc_should_fail() { return emu_fail_malloc_countdown >= 0 && emu_fail_malloc_countdown-- == 0; }
 inline cudaError_t cudaMalloc(void** p, size_t n) {
+  if (emu_malloc_should_fail()) { *p = nullptr; return cudaErrorMemoryAllocation; }
   const size_t bytes = (n + 255) / 256 * 256 + 256;
   *p = aligned_alloc(256, bytes);
   if (!*p) return cudaErrorMemoryAllocation;
@@ -55,7 +61,11 @@ inline cudaError_t cudaMalloc(void** p, size_t n) {
 }
 template <typename T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n); }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaMallocHost(void** p, size_t n) {
+  if (emu_malloc_should_fail()) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  *p = malloc(n ? n : 1);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }

@@ -369,3 +369,47 @@ print("OK")
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-500:], r.stderr[-1500:])
 
+
+def test_emulated_engine_survives_every_failed_allocation(engine, oracle):
+    """memory exhaustion at every allocation of a pair in turn (fault injection in the fake runtime: the n-th cudaMalloc /
+    cudaMallocHost fails): the call must return PANO_ERR_CUDA - never crash, never return a wrong result - and the same
+    context must stitch the pair correctly right afterwards (grow-only buffers left in a consistent state)"""
+    pkg = load_pkg()
+    lib = engine.lib
+    left, right, _ = load_synth().make_pair(200, 140, seed=9)
+    iters = 12
+    ro = pkg.RansacOptions(numIterations_=iters)
+    kl, kr = oracle.detect(left), oracle.detect(right)
+    o = oracle.ransac(kr, kl, oracle.match(kr, kl, right, left), iters=iters, seed=12345)
+    want = oracle.compose(left, right, o["H"])
+    n = handled = 0
+    try:
+        while True:
+            e = pkg.Engine.__new__(pkg.Engine)
+            e.lib, e.ctx, e.device = lib, C.c_void_p(), 0
+            lib.pano_emu_fail_malloc(C.c_long(n))
+            if lib.pano_create(0, C.c_uint32(12345), C.byref(e.ctx)) != 0:       # the failure hit the context's own buffers
+                e.ctx = None
+                lib.pano_emu_fail_malloc(C.c_long(-1))
+                handled += 1
+                n += 1
+                continue
+            failed = False
+            try:
+                e.stitchTwoImages(left, right, ransacOpts=ro)
+            except pkg.PanoError as err:
+                failed = True
+                assert err.status == pkg.PANO_ERR_CUDA
+            lib.pano_emu_fail_malloc(C.c_long(-1))
+            canvas, r = e.stitchTwoImages(left, right, ransacOpts=ro)
+            assert r["status"] == 0 and np.array_equal(bits(r["H"]), bits(o["H"])) and np.array_equal(canvas, want), n
+            e.close()
+            if not failed:
+                break
+            handled += 1
+            n += 1
+            assert n < 200
+    finally:
+        lib.pano_emu_fail_malloc(C.c_long(-1))
+    assert handled >= 20          # a pair allocates a few dozen buffers on a fresh context: every one of them was failed once
+
