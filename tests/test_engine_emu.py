@@ -413,3 +413,47 @@ def test_emulated_engine_survives_every_failed_allocation(engine, oracle):
         lib.pano_emu_fail_malloc(C.c_long(-1))
     assert handled >= 20          # a pair allocates a few dozen buffers on a fresh context: every one of them was failed once
 
+
+def test_emulated_engine_batch_survives_failed_allocations_in_lane_threads(engine, oracle):
+    """the same for pano_stitch_batch with two lane threads: an allocation that fails inside a lane (slot contexts, upload
+    and scratch buffers, replay plans) must come back as PANO_ERR_CUDA of the batch call - an exception leaving a lane's
+    std::thread would terminate the host process - and the next batch on the same context must be right.  Every seventh
+    allocation index up to the first success (the full sweep - 116 indices for three pairs - was run once: all handled)."""
+    pkg = load_pkg()
+    lib = engine.lib
+    views = load_synth().make_strip(n=3, w=200, h=140, seed=21)
+    lefts, rights = list(views[:2]), list(views[1:])
+    iters = 10
+    ro = pkg.RansacOptions(numIterations_=iters)
+    want = []
+    for l, r in zip(lefts, rights):
+        kl, kr = oracle.detect(l), oracle.detect(r)
+        want.append(oracle.ransac(kr, kl, oracle.match(kr, kl, r, l), iters=iters, seed=12345)["H"])
+    os.environ["PANO_BATCH_LANES"] = "2"
+    n = handled = 0
+    try:
+        while n < 400:
+            e = pkg.Engine.__new__(pkg.Engine)
+            e.lib, e.ctx, e.device = lib, C.c_void_p(), 0
+            assert lib.pano_create(0, C.c_uint32(12345), C.byref(e.ctx)) == 0
+            lib.pano_emu_fail_malloc(C.c_long(n))
+            failed = False
+            try:
+                e.stitchBatch(lefts, rights, ransacOpts=ro)
+            except pkg.PanoError as err:
+                failed = True
+                assert err.status == pkg.PANO_ERR_CUDA
+            lib.pano_emu_fail_malloc(C.c_long(-1))
+            res, _ = e.stitchBatch(lefts, rights, ransacOpts=ro)
+            for i in range(2):
+                assert res[i]["status"] == 0 and np.array_equal(bits(res[i]["H"]), bits(want[i])), (n, i)
+            e.close()
+            if not failed:
+                break
+            handled += 1
+            n += 7
+    finally:
+        lib.pano_emu_fail_malloc(C.c_long(-1))
+        os.environ["PANO_BATCH_LANES"] = "1"
+    assert handled >= 8
+
