@@ -457,3 +457,73 @@ def test_emulated_engine_batch_survives_failed_allocations_in_lane_threads(engin
         os.environ["PANO_BATCH_LANES"] = "1"
     assert handled >= 8
 
+
+def test_emulated_engine_rejects_bad_arguments_without_touching_memory(engine):
+    """every entry point of the C ABI with arguments that must be refused: a status, never a crash (under
+    tools/emu_sanitize.sh also: never an out-of-bounds access), and the context works afterwards"""
+    pkg = load_pkg()
+    lib, ctx = engine.lib, engine.ctx
+    INVALID, UNSUPPORTED, TOO_FEW = pkg.PANO_ERR_INVALID, pkg.PANO_ERR_UNSUPPORTED, pkg.PANO_ERR_TOO_FEW_MATCHES
+    img = np.ascontiguousarray(load_synth().make_pair(96, 64, seed=3)[0])
+    ip, w, h, st = img.ctypes.data_as(C.c_void_p), 96, 64, C.c_size_t(img.strides[0])
+    ho, ro, ko = pkg.HarrisCornerOptions(), pkg.RansacOptions(), pkg.KnnOptions()
+    n = C.c_int(0)
+    xy = np.zeros((64, 2), np.int32)
+    xp = xy.ctypes.data_as(C.c_void_p)
+    m = np.zeros(8, pkg.MATCH_DTYPE)
+    mp = m.ctypes.data_as(C.c_void_p)
+    H = np.eye(3)
+    Hp = H.ctypes.data_as(C.c_void_p)
+    res = pkg.PairResult()
+    info = pkg.CanvasInfo()
+    canvas = np.zeros(1 << 16, np.uint8)
+    cp = canvas.ctypes.data_as(C.c_void_p)
+
+    def opts(**kw):
+        o = pkg.HarrisCornerOptions()
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+    cases = [
+        (lib.pano_detect(ctx, None, w, h, st, 0, C.byref(ho), xp, 64, C.byref(n)), INVALID),
+        (lib.pano_detect(ctx, ip, 0, h, st, 0, C.byref(ho), xp, 64, C.byref(n)), INVALID),
+        (lib.pano_detect(ctx, ip, w, h, C.c_size_t(3 * w - 1), 0, C.byref(ho), xp, 64, C.byref(n)), INVALID),
+        (lib.pano_detect(ctx, ip, w, h, st, 0, None, xp, 64, C.byref(n)), INVALID),
+        (lib.pano_detect(ctx, ip, w, h, st, 0, C.byref(ho), xp, 64, None), INVALID),
+        (lib.pano_detect(ctx, ip, w, h, st, 0, C.byref(opts(nmsNeighborhood_=4)), xp, 64, C.byref(n)), UNSUPPORTED),
+        (lib.pano_detect(ctx, ip, w, h, st, 0, C.byref(opts(patchSize_=7)), xp, 64, C.byref(n)), UNSUPPORTED),
+        (lib.pano_detect(None, ip, w, h, st, 0, C.byref(ho), xp, 64, C.byref(n)), INVALID),
+        (lib.pano_harris_response(ctx, ip, w, h, st, 0, C.c_double(0.04), None), INVALID),
+        (lib.pano_convolve_f64(ctx, cp, 8, 8, cp, 4, 0, cp), INVALID),
+        (lib.pano_match(ctx, xp, -1, xp, 4, ip, w, h, st, ip, w, h, st, 0, C.byref(ho), 0, mp, 8, C.byref(n)), INVALID),
+        (lib.pano_match(ctx, None, 4, xp, 4, ip, w, h, st, ip, w, h, st, 0, C.byref(ho), 0, mp, 8, C.byref(n)), INVALID),
+        (lib.pano_match(ctx, xp, 4, xp, 4, ip, w, h, st, None, w, h, st, 0, C.byref(ho), 0, mp, 8, C.byref(n)), INVALID),
+        (lib.pano_match_knn(ctx, xp, 4, xp, 4, ip, w, h, st, ip, w, h, st, 0, None, mp, None, 8, C.byref(n)), INVALID),
+        (lib.pano_match_knn(ctx, xp, 4, xp, 4, ip, w, h, st, ip, w, h, st, 0, C.byref(ko), mp, None, -1, C.byref(n)), INVALID),
+        (lib.pano_ransac(ctx, xp, 8, xp, 8, mp, 8, 0, None, Hp, None, None, None, None, None), INVALID),
+        (lib.pano_ransac(ctx, xp, 8, xp, 8, mp, 8, 0, C.byref(pkg.RansacOptions(numSamples_=3)), Hp, None, None, None, None, None), UNSUPPORTED),
+        (lib.pano_ransac(ctx, xp, 8, xp, 8, mp, 3, 0, C.byref(ro), Hp, None, None, None, None, None), TOO_FEW),
+        (lib.pano_ransac(ctx, xp, 8, xp, 8, mp, 8, 0, C.byref(pkg.RansacOptions(numIterations_=0)), Hp, None, None, None, None, None), TOO_FEW),
+        (lib.pano_canvas_geometry(0, h, w, h, Hp, C.byref(info)), INVALID),
+        (lib.pano_canvas_geometry(w, h, w, h, None, C.byref(info)), INVALID),
+        (lib.pano_warp_overlay(ctx, ip, w, h, st, ip, w, h, st, 0, None, cp, C.c_size_t(3 * w), C.c_size_t(canvas.nbytes), C.byref(info)), INVALID),
+        (lib.pano_stitch_pair(ctx, ip, w, h, st, None, w, h, st, 0, C.byref(ho), C.byref(ro), C.byref(res)), INVALID),
+        (lib.pano_stitch_pair(ctx, ip, w, h, st, ip, w, h, st, 0, C.byref(ho), C.byref(ro), None), INVALID),
+        (lib.pano_stitch_pair(ctx, ip, w, h, st, ip, w, h, st, 0, C.byref(ho), C.byref(pkg.RansacOptions(numSamples_=5)), C.byref(res)), UNSUPPORTED),
+        (lib.pano_set_match_mode(ctx, 2, C.c_double(0.75), 0), INVALID),
+        (lib.pano_set_match_mode(ctx, 1, C.c_double(-1.0), 0), INVALID),
+        (lib.pano_set_match_mode(ctx, 1, C.c_double(0.75), 9), UNSUPPORTED),
+        (lib.pano_pair_query(ctx), INVALID),                       # nothing pending
+        (lib.pano_pair_wait(ctx), INVALID),
+        (lib.pano_get_profile(ctx, None, None, 0) >= 0, True),
+    ]
+    for i, (got, want) in enumerate(cases):
+        assert got == want, (i, got, want)
+    # a flat image pair: the reference's failure cases as statuses, not errors
+    flat = np.full((64, 96, 3), 50, np.uint8)
+    canvas_, r = engine.stitchTwoImages(flat, flat)
+    assert canvas_ is None and r["status"] == pkg.PANO_ERR_NO_MATCHES
+    # and the context is intact
+    k = engine.gpuHarrisCornerDetectorDetect(img)
+    assert len(k) > 0
+

@@ -21,8 +21,12 @@ for SAN in ${1:-address undefined}; do
   PRE=""
   [ "$SAN" = address ] && PRE=$(gcc -print-file-name=libasan.so)
   echo "== $SAN"
+  # (the two allocation-failure tests make the engine throw C++ exceptions internally; a preloaded libasan inside the
+  # Python process cannot intercept __cxa_throw of a library loaded later, so they run in the plain and UBSan builds only)
+  SKIP=""
+  [ "$SAN" = address ] && SKIP="not failed_allocation"
   LD_PRELOAD="$PRE" ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:verify_asan_link_order=0 \
-    UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 python -m pytest $TESTS -x -q 2>&1 | tail -3
+    UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 python -m pytest $TESTS -x -q -k "$SKIP" 2>&1 | tail -3
 done
 rm -f tests/hostsim/lib*_emu.so tests/hostsim/gpu_stitching_emu
 # Scheduling-order independence: the same kernels with the runnable threads of a block taking their turns in descending
