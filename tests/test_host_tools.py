@@ -87,6 +87,12 @@ def test_bench_other_configs_embeds_child_lines_and_survives_failures():
     assert out["c1"]["metric"] == "ms_per_pair" and out["c1"]["engine"]["ms"] == 1.5 and "child_seconds" in out["c1"]
     assert "TimeoutExpired" in out["c2"]["error"]
     assert [c[c.index("--workload") + 1] for c in calls] == ["c1", "c2"] and "--no-cpu" in calls[1]
+    # a child whose CPU leg ran into the limit has already printed its engine-side line: that line is kept
+    def slow(cmd, **kw):
+        assert kw["env"]["PANO_BENCH_CHILD"] == "1"
+        raise subprocess.TimeoutExpired(cmd, 5.0, output=b'log\n{"metric": "ms_per_pair", "engine": {"ms": 2.5}}\n{"metric": "trunc')
+    part = bench.other_configs(a, runner=slow)
+    assert part["c1"]["engine"]["ms"] == 2.5 and "not finished" in part["c1"]["cpu_legs"]
     bad = bench.other_configs(a, runner=lambda cmd, **kw: types.SimpleNamespace(returncode=3, stdout="", stderr="boom"))
     assert "exit code 3" in bad["c1"]["error"] and "boom" in bad["c2"]["error"]
 

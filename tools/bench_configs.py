@@ -109,6 +109,8 @@ def run_pair_config(a, name):
                                  "source": "tests/golden/ref_runs.json (the reference's own code, oracle/_ref)"},
             "cpu_model": _cpu_model(), "host_threads": len(os.sched_getaffinity(0))}
     if not a.no_cpu:
+        if os.environ.get("PANO_BENCH_CHILD"):     # (bench.py's other_configs leg: the engine side first, see there)
+            print(json.dumps(line, default=float), flush=True)
         line["cpu"] = _ref_pair(left, right, SEED, serial=True)
         for k, v in line["cpu"].items():
             v["MP_per_s"] = mp / v["seconds"]
