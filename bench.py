@@ -20,8 +20,9 @@ overlay) over that batch through ONE pano_stitch_batch call.
                inside the C ABI (pano_set_profile), plus every other main kernel timed the same way.
 `cpu_baseline` the reference's own code (oracle/_ref: /root/reference/src/openmp/main.cpp and src/serial/main.cpp
                compiled unmodified against oracle/cvshim) on this box's host cores, rank 0 at N = 1 only.
-`other_configs` BASELINE configs 1 (images/mountain pair: engine next to the reference's serial and OpenMP code) and 2
-               (images/oilseed fold + evaluator score), each measured in a child process at N = 1 (--no-extras skips).
+`other_configs` BASELINE configs 1 (images/mountain pair: engine next to the reference's serial and OpenMP code), 2
+               (images/oilseed fold + evaluator score) and 4 (8-image strip, chain mode, on this one GPU), each measured
+               in a child process at N = 1 (--no-extras skips).
 Every number in the line is measured in this run, except those explicitly attributed to a committed capture
 under profiles/ (ncu-only metrics such as the tensor-pipe percentage).
 """
@@ -487,13 +488,15 @@ def other_configs(a, runner=subprocess.run):
     measured in the same run: each in a CHILD process (`bench.py --workload c1|c2`, tools/bench_configs.py), so that
     nothing they do - a missing image, an error, a crash - can touch the headline line; their JSON lines are embedded."""
     out = {}
-    for name, extra in (("c1", []), ("c2", ["--no-cpu"])):
+    # (chain = BASELINE config 4 on this one GPU; its 2 / 4 / 8-GPU lines are profiles/r02_chain_*gpu.json, measured with
+    # the same command under torchrun and with the per-rank uploads PANO_CHAIN_NVLINK=0 selects)
+    for name, extra in (("c1", []), ("c2", ["--no-cpu"]), ("chain", ["--steps", "5", "--warmup", "2"])):
         try:
             t0 = time.perf_counter()
             # PANO_BENCH_CHILD: the child prints its line once the engine side is measured and again with the CPU legs, so
             # that a CPU leg running into the time limit on a slow host costs that leg only
             p = runner([sys.executable, os.path.abspath(__file__), "--workload", name] + extra, capture_output=True, text=True,
-                       timeout=a.extras_timeout, env=dict(os.environ, PANO_BENCH_CHILD="1"))
+                       timeout=a.extras_timeout, env=dict(os.environ, PANO_BENCH_CHILD="1", PANO_CHAIN_NVLINK="0"))
             lines = [l for l in (p.stdout or "").splitlines() if l.startswith("{")]
             if p.returncode == 0 and lines:
                 out[name] = json.loads(lines[-1])

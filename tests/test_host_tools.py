@@ -86,7 +86,7 @@ def test_bench_other_configs_embeds_child_lines_and_survives_failures():
     out = bench.other_configs(a, runner=runner)
     assert out["c1"]["metric"] == "ms_per_pair" and out["c1"]["engine"]["ms"] == 1.5 and "child_seconds" in out["c1"]
     assert "TimeoutExpired" in out["c2"]["error"]
-    assert [c[c.index("--workload") + 1] for c in calls] == ["c1", "c2"] and "--no-cpu" in calls[1]
+    assert [c[c.index("--workload") + 1] for c in calls] == ["c1", "c2", "chain"] and "--no-cpu" in calls[1]
     # a child whose CPU leg ran into the limit has already printed its engine-side line: that line is kept
     def slow(cmd, **kw):
         assert kw["env"]["PANO_BENCH_CHILD"] == "1"
