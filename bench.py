@@ -22,7 +22,8 @@ overlay) over that batch through ONE pano_stitch_batch call.
                compiled unmodified against oracle/cvshim) on this box's host cores, rank 0 at N = 1 only.
 `other_configs` BASELINE configs 1 (images/mountain pair: engine next to the reference's serial and OpenMP code), 2
                (images/oilseed fold + evaluator score) and 4 (8-image strip, chain mode, on this one GPU), each measured
-               in a child process at N = 1 (--no-extras skips).
+               in a child process at N = 1 (--no-extras skips).  At N > 1 (the scaling runs) config 4 is measured on
+               the same N GPUs by a child job of rank 0 after the headline's measurements (chain_config_at_n).
 Every number in the line is measured in this run, except those explicitly attributed to a committed capture
 under profiles/ (ncu-only metrics such as the tensor-pipe percentage).
 """
@@ -234,6 +235,7 @@ def run_engine(a):
             print("[bench %6.1f s] %s" % (time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
     pkg = importlib.import_module(PKG)
     synth = importlib.import_module(PKG + ".synth")
+    cpus_before_binding = sorted(os.sched_getaffinity(0))
     numa = importlib.import_module(PKG + ".numa").bind_to_gpu(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     dist = None
     if world > 1:
@@ -475,12 +477,127 @@ def run_engine(a):
                 "latency": latency, "wall_ms_per_step": wall_ms / a.steps,
                 "collective": ("all_gather of %d x 96 B homography records per step (NCCL)" % n_total) if world > 1 else "none (single GPU)",
                 "roofline": roofline, "cpu_baseline": cpu, "other_configs": other}
+    if world > 1 and not a.no_extras:
+        # BASELINE config 4 at this GPU count: every measurement of the headline is complete by now
+        chain = chain_config_at_n(a, dist, rank, world, cpus_before_binding, log)
+        if rank == 0:
+            line["other_configs"] = {"chain": chain}
     barrier()
     if rank == 0:
         print(json.dumps(line, default=float), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+TORCHRUN_ENV = ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK",
+                "ROLE_WORLD_SIZE", "ROLE_NAME", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS", "PANO_BATCH_LANES")
+
+
+def chain_child_command(world, cpus, port):
+    """`bench.py --workload chain` under its own torchrun with `world` ranks; the bootstrap restores the CPU set this
+    rank had before it bound itself next to its GPU (a child inherits the affinity of its parent)"""
+    boot = ("import os, sys; os.sched_setaffinity(0, {%s}); os.execv(sys.executable, [sys.executable] + sys.argv[1:])"
+            % ", ".join(str(c) for c in cpus))
+    return [sys.executable, "-c", boot, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__), "--workload", "chain",
+            "--steps", "5", "--warmup", "2"]
+
+
+def free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def descendants(pid):
+    """every live descendant of `pid` (children of children included), from /proc"""
+    kids = {}
+    for d in os.listdir("/proc"):
+        if d.isdigit():
+            try:
+                with open("/proc/%s/stat" % d) as f:
+                    st = f.read()
+                kids.setdefault(int(st[st.rindex(")") + 2:].split()[1]), []).append(int(d))
+            except (OSError, ValueError, IndexError):
+                pass
+    out, todo = [], [pid]
+    while todo:
+        for k in kids.get(todo.pop(), []):
+            out.append(k)
+            todo.append(k)
+    return out
+
+
+def run_child_group(cmd, env, timeout):
+    """runs `cmd` and returns (exit code or None on timeout, stdout, stderr).  On timeout the child AND every descendant
+    is killed (torchrun starts its workers in sessions of their own: a process-group kill would miss them), so that no
+    rank of a stuck child job is left on a GPU."""
+    import signal
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
+    try:
+        so, se = p.communicate(timeout=timeout)
+        return p.returncode, so, se
+    except subprocess.TimeoutExpired:
+        victims = descendants(p.pid) + [p.pid]
+        for sig, grace in ((signal.SIGTERM, 3.0), (signal.SIGKILL, 0.0)):
+            victims = sorted(set(victims + descendants(p.pid)))
+            for v in victims:
+                try:
+                    os.kill(v, sig)
+                except OSError:
+                    pass
+            t_end = time.perf_counter() + grace
+            while time.perf_counter() < t_end and p.poll() is None:
+                time.sleep(0.1)
+        try:
+            so, se = p.communicate(timeout=20)
+        except subprocess.TimeoutExpired:      # (a survivor still holds the pipes: give the output up, not the run)
+            so, se = "", "output of the killed child job abandoned"
+        return None, so, se
+
+
+def chain_config_at_n(a, dist, rank, world, cpus, log=lambda m: None, make_cmd=chain_child_command, store=None):
+    """N > 1 (the driver's scaling runs): BASELINE config 4 - the 8-image 24 MP strip in chain mode, pairs and canvas
+    bands sharded over the same N GPUs - measured by rank 0 as a CHILD job (`bench.py --workload chain` under its own
+    torchrun, the command profiles/r02_chain_*gpu.json was measured with; per-rank uploads) once the headline's
+    measurements are complete.  The other ranks wait on the rendezvous store (a host-side wait: no barrier kernel
+    spins on their GPUs meanwhile).  A child that fails or runs into the limit leaves an error note."""
+    import datetime
+    key = "pano_bench_chain_leg_done"
+    try:
+        store = store or dist.distributed_c10d._get_default_store()
+    except Exception as e:
+        return {"error": "no rendezvous store: %s" % e} if rank == 0 else None
+    if rank != 0:
+        try:
+            store.wait([key], datetime.timedelta(seconds=a.extras_timeout + 480))
+        except Exception:
+            pass
+        return None
+    out = None
+    try:
+        log("timing BASELINE config 4 (chain mode) on %d GPUs in a child job" % world)
+        env = {k: v for k, v in os.environ.items() if k not in TORCHRUN_ENV and not k.startswith("TORCHELASTIC")}
+        env.update(PANO_CHAIN_NVLINK="0", PANO_BENCH_CHILD="1", NCCL_DEBUG="WARN")
+        t0 = time.perf_counter()
+        rc, so, se = run_child_group(make_cmd(world, cpus, free_port()), env, a.extras_timeout)
+        lines = [l for l in (so or "").splitlines() if l.startswith("{") and l.rstrip().endswith("}")]
+        if rc == 0 and lines:
+            out = json.loads(lines[-1])
+            out["child_seconds"] = round(time.perf_counter() - t0, 1)
+        else:
+            out = {"error": ("child job exit code %s" % rc if rc is not None else "child job killed after %.0f s" % a.extras_timeout)
+                   + ": " + (se or "")[-300:]}
+    except Exception as e:
+        out = {"error": "%s: %s" % (type(e).__name__, e)}
+    finally:
+        try:
+            store.set(key, "1")
+        except Exception:
+            pass
+    return out
 
 
 def other_configs(a, runner=subprocess.run):

@@ -134,3 +134,79 @@ def test_distributed_chain_two_ranks(tmp_path):
     synth = importlib.import_module(PKG + ".synth")
     ref, _ = Oracle().stitch_chain(synth.make_strip(n=4, w=320, h=200, seed=21), seed=12345)
     assert a.shape == ref.shape and np.array_equal(a, ref)
+
+
+# ---- bench.py's chain leg at N > 1: rank 0 runs a child torchrun job, the other ranks wait on the rendezvous store ----
+def _bench_mod():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    return bench
+
+
+_STUB = r'''
+import json, os, sys, time
+import torch.distributed as dist
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+mode = sys.argv[1]
+if mode == "hang":
+    time.sleep(600)
+dist.barrier()
+if rank == 0:
+    print("noise")
+    print(json.dumps({"metric": "stub", "n_gpus": world, "cpus": len(os.sched_getaffinity(0)),
+                      "nvlink": os.environ.get("PANO_CHAIN_NVLINK"), "lanes": os.environ.get("PANO_BATCH_LANES"),
+                      "pid": os.getpid()}), flush=True)
+dist.destroy_process_group()
+'''
+
+
+def _chain_leg_worker(rank, world, port, out_dir, mode):
+    sys.path.insert(0, ROOT)
+    import json
+    import time
+    import types
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    # what a torchrun worker of bench.py has in its environment, and a rank that bound itself to one CPU
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), PANO_BATCH_LANES="7", TORCHELASTIC_RUN_ID="x")
+    cpus = sorted(os.sched_getaffinity(0))
+    os.sched_setaffinity(0, {cpus[rank % len(cpus)]})
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    bench = _bench_mod()
+    stub = os.path.join(out_dir, "stub.py")
+    if rank == 0:
+        open(stub, "w").write(_STUB)
+    dist.barrier()
+
+    def make_cmd(w, c, p):
+        cmd = bench.chain_child_command(w, c, p)
+        i = cmd.index(os.path.join(ROOT, "bench.py"))
+        return cmd[:i] + [stub, mode]
+    a = types.SimpleNamespace(extras_timeout=60.0 if mode == "ok" else 8.0)
+    t0 = time.time()
+    out = bench.chain_config_at_n(a, dist, rank, world, cpus, make_cmd=make_cmd)
+    json.dump({"out": out, "seconds": time.time() - t0, "cpus": len(cpus)}, open(os.path.join(out_dir, "r%d_%s.json" % (rank, mode)), "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["ok", "hang"])
+def test_bench_chain_leg_child_job_and_store_wait(tmp_path, mode):
+    import json
+    port = 31000 + os.getpid() % 2000 + (7 if mode == "ok" else 11)
+    mp.spawn(_chain_leg_worker, args=(2, port, str(tmp_path), mode), nprocs=2, join=True)
+    r0, r1 = [json.load(open(tmp_path / ("r%d_%s.json" % (r, mode)))) for r in (0, 1)]
+    assert r1["out"] is None                                   # only rank 0 reports
+    if mode == "ok":
+        o = r0["out"]
+        assert o["metric"] == "stub" and o["n_gpus"] == 2 and "child_seconds" in o
+        assert o["cpus"] == r0["cpus"]                         # the affinity before binding is back in the child job
+        assert o["nvlink"] == "0" and o["lanes"] is None       # validated upload variant; the parent's lane count is not inherited
+        assert r1["seconds"] >= r0["seconds"] - 2.0            # rank 1 waited for rank 0's child job
+    else:
+        assert "killed after 8 s" in r0["out"]["error"]
+        assert r0["seconds"] < 40 and r1["seconds"] < 40       # the stuck job is killed as a group; nobody keeps waiting
