@@ -178,8 +178,10 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1000 * tot / len(times), "ms_per_pair": 1000 * tot / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+u8", "data": "synthetic",
-            "config": {"workload": workload_name(w, h, a.pairs) + "; each reference step = 1 pair of it (seeds 1000, 1001 alternating)",
-                       "pairs_per_step": 1, "seed": SEED, "cpu_model": cpu_model(), "host_threads": ncpu},
+            # (the engine arm's workload, named identically; what a reference step covers of it is said separately)
+            "config": {"workload": workload_name(w, h, a.pairs), "pairs_per_step_per_gpu": a.pairs, "distinct_pairs_per_gpu": a.pairs,
+                       "seed": SEED, "reference_step": "a bounded sample of that workload: 1 pair per step (seeds 1000, 1001 alternating)",
+                       "pairs_per_reference_step": 1, "cpu_model": cpu_model(), "host_threads": ncpu},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": "%d step(s) of 1 pair; %s" % (len(times), what),
                              "stage_ms_last_step": stages},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
