@@ -434,9 +434,11 @@ def run_engine(a):
                                         "hbm_frac": 3 * npx / (k_ms["harris_fused"] / 1e3) / 1e9 / hbm},
                 "match_tc_kernel": {"ms": k_ms["match_tc"], "bound": "tensor (int8 tcgen05) / epilogue",
                                     "pairs": r0["kr"] * r0["kl"], "achieved_TOPs": match_ops / (k_ms["match_tc"] / 1e3) / 1e12,
+                                    **tensor_fraction(r0["kr"], r0["kl"], k_ms["match_tc"], mb, clocks),
                                     "tensor_pipe_active_pct_ncu": (ncu.get("match_tc_kernel") or {}).get("tensor_pipe_active_pct"),
                                     "ncu_source": "profiles/r02_ncu_metrics.json (ncu --set full capture of this kernel)"},
-                "replay (all kernels of the shuffle replay)": {"ms_per_pair": k_per_pair["replay"], "bound": "integer ALU + dependent phases"},
+                "replay (all kernels of the shuffle replay)": replay_floor(eng, r0["m"], k_per_pair["replay"], mb, P,
+                                                                           ms_dev / (a.steps * P)),
                 "dlt_kernel": {"ms": k_ms["dlt"], "bound": "latency (136 dependent Jacobi rotations per hypothesis)"},
                 "score_kernel": {"ms": k_ms["score"], "bound": "fp64 pipe"},
                 "descriptor_gather": {"ms_per_image": k_ms["descriptor_gather"]},
@@ -599,6 +601,41 @@ def chain_config_at_n(a, dist, rank, world, cpus, log=lambda m: None, make_cmd=c
             store.set(key, "1")
         except Exception:
             pass
+    return out
+
+
+def tensor_fraction(nq, nt, kernel_ms, mb, clocks):
+    """The matcher's MMA work as issued (128 x 128 tiles, K = 75 padded to 128, int8) per second of its event time,
+    against the tcgen05 int8 rate tools/microbench.cu measured per SM and clock (profiles/r02_microbench.json) x 148 SMs
+    x the SM clock sampled during this run."""
+    try:
+        per_clk = max(e["mac_per_clk_per_sm"] for e in mb["tcgen05_mma"] if e["kind"] == "i8")
+        mhz = float((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz"))
+        macs = (-(-nq // 128) * 128) * (-(-nt // 128) * 128) * 128.0
+        peak = per_clk * 148 * mhz * 1e6
+        ach = macs / (kernel_ms / 1e3)
+        return {"mma_macs_issued": macs, "achieved_mac_per_s": ach, "peak_mac_per_s": peak, "frac_of_tensor_peak": ach / peak,
+                "peak_source": "tools/microbench.cu (%d int8 MAC/clk/SM) x 148 SMs x %.0f MHz sampled in this run" % (per_clk, mhz)}
+    except Exception as e:
+        return {"frac_of_tensor_peak": None, "tensor_peak_note": "not computed: %s" % e}
+
+
+def replay_floor(eng, m, replay_ms, mb, batch_pairs, batch_ms_per_pair):
+    """The shuffle replay against its operation-count floor: pass 1 evaluates `cells` tests of 3 integer-ALU instructions
+    (pano_replay_work_estimate: the plan for this match count), the cell kernel's measured rate on an otherwise idle GPU
+    is tools/microbench.cu's (profiles/r02_microbench.json).  Single-pair plan (chunks of 50 000 candidate walks) against
+    the replay's event time of the profiled pair; throughput-mode plan (4000 per chunk) against the whole step."""
+    out = {"ms_per_pair": replay_ms, "bound": "integer ALU + dependent phases"}
+    try:
+        rate = float(mb.get("replay_cells_per_s"))
+        w1, wb = eng.replayWork(m, 1000, 0.0), eng.replayWork(m, 1000, 4000.0)
+        f1, fb = w1["cells"] / rate * 1e3, wb["cells"] / rate * 1e3
+        out.update({"cells_per_pair": w1["cells"], "chunks": w1["chunks"], "floor_ms": f1, "floor_over_measured": f1 / replay_ms,
+                    "cell_rate_per_s": rate, "cell_rate_source": "tools/microbench.cu (profiles/r02_microbench.json)",
+                    "throughput_mode": {"cells_per_pair": wb["cells"], "chunks": wb["chunks"], "floor_ms_per_pair": fb,
+                                        "share_of_ms_per_pair": fb / batch_ms_per_pair}})
+    except Exception as e:
+        out["floor"] = "not computed: %s" % e
     return out
 
 

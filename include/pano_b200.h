@@ -273,6 +273,26 @@ int pano_stitch_fold(pano_ctx* ctx, const uint8_t* const* images, const int* ws,
  * current panorama.  Results differ from the reference's by design; a failed step keeps panorama and list. */
 int pano_set_fold_mode(pano_ctx* ctx, int mode);
 
+/* ---- measurement aid (host only, no GPU work) ----
+ * The work the chunked shuffle replay plans for one RANSAC run over n_matches matches: pass 1
+ * evaluates `cells` (candidate diagonal, shuffle step) tests of 3 integer-ALU instructions each -
+ * the operation count bench.py turns into the replay's floor (cells / measured cell rate).
+ * target_candidates: candidate walks per chunk (0 = the single-pair default of 50 000;
+ * pano_stitch_batch uses 4000 for resident inputs and 16 000 for host buffers).
+ * ref: what is being replayed is the per-iteration std::shuffle of src/serial/main.cpp:264-275. */
+typedef struct pano_replay_work {
+  int32_t chunk_iterations;      /* G: iterations replayed per chunk */
+  int32_t chunks;                /* ceil(iterations / G): sequential phases */
+  uint32_t steps;                /* engine draws of one rejection-free shuffle */
+  uint32_t candidates_per_chunk; /* speculative start offsets (walks) per chunk */
+  uint32_t diagonals_per_chunk;  /* diagonals pass 1 evaluates per chunk */
+  uint32_t reserved;
+  double rejections_mean;        /* mu: expected rejected draws per shuffle */
+  double rejections_sigma;
+  double cells;                  /* chunks x diagonals_per_chunk x steps rounded up to 32 */
+} pano_replay_work;
+int pano_replay_work_estimate(int n_matches, int iterations, double target_candidates, pano_replay_work* out);
+
 /* ---- chain mode (multi-image panoramas whose adjacent pairs are independent work items) ----
  * The reference folds images sequentially and re-detects on the growing panorama, which cannot
  * be sharded.  Chain mode instead estimates H(i <- i+1) for every adjacent pair

@@ -66,3 +66,28 @@ def test_canvas_geometry_is_host_side_and_matches_oracle(oracle):
     assert st == 0 and (info.canvas_w, info.canvas_h, info.left_x, info.left_y) == (6400, 3117, 0, 0)
     ok, g, TH = oracle.canvas_geometry(4156, 3117, 4156, 3117, H)
     assert ok and g == (6400, 3117, 0, 0)
+
+
+def test_replay_work_estimate_is_host_side_and_consistent_with_the_plan():
+    """pano_replay_work_estimate (measurement aid for bench.py's replay floor): planning only, callable without a GPU;
+    the numbers follow the plan's definition (ref: the shuffle being replayed is src/serial/main.cpp:264-275)"""
+    pkg = load_pkg()
+    lib = pkg.load_library()
+    e = pkg.Engine.__new__(pkg.Engine)
+    e.lib = lib
+    for m, target in ((10833, 0.0), (10833, 4000.0), (37, 0.0), (4, 0.0), (70000, 16000.0)):
+        w = e.replayWork(m, 1000, target)
+        assert w["chunks"] == -(-1000 // w["chunk_iterations"]) and w["chunk_iterations"] >= 1
+        assert w["diagonals_per_chunk"] >= w["candidates_per_chunk"] >= w["chunk_iterations"]
+        assert w["diagonals_per_chunk"] % 32 == 0
+        assert w["cells"] == w["chunks"] * w["diagonals_per_chunk"] * (-(-w["steps"] // 32) * 32)
+        assert w["candidates_per_chunk"] <= (target or 50000.0) + 1 or w["chunk_iterations"] == 8
+    # libstdc++ draws two swap positions per engine output while the range product fits 32 bits
+    assert e.replayWork(10833, 1000)["steps"] == 10833 // 2 and e.replayWork(70000, 1000)["steps"] == 69999
+    # smaller chunks: more sequential phases, less speculative work
+    a, b = e.replayWork(10833, 1000, 0.0), e.replayWork(10833, 1000, 4000.0)
+    assert b["chunks"] > a["chunks"] and b["cells"] < a["cells"]
+    for bad in ((3, 1000, 0.0), (100, 0, 0.0), (100, 1000, 10.0), (100, 1000, 1e6)):
+        with pytest.raises(pkg.PanoError) as ex:
+            e.replayWork(*bad)
+        assert ex.value.status == pkg.PANO_ERR_INVALID

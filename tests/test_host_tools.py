@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-from conftest import PKG, ROOT, load_synth
+from conftest import PKG, ROOT, load_pkg, load_synth
 
 
 def test_numa_helpers_parse_and_degrade_gracefully():
@@ -96,3 +96,25 @@ def test_bench_other_configs_embeds_child_lines_and_survives_failures():
     bad = bench.other_configs(a, runner=lambda cmd, **kw: types.SimpleNamespace(returncode=3, stdout="", stderr="boom"))
     assert "exit code 3" in bad["c1"]["error"] and "boom" in bad["c2"]["error"]
 
+
+
+def test_bench_floor_helpers_compute_from_the_plan_and_the_microbenchmarks():
+    """bench.py's live fractions: the replay against its operation-count floor (pano_replay_work_estimate x the measured
+    cell rate) and the matcher's issued MMA work against the measured tcgen05 int8 rate; missing inputs leave a note"""
+    import ctypes as C
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    pkg = load_pkg()
+    e = pkg.Engine.__new__(pkg.Engine)
+    e.lib = pkg.load_library()
+    mb = json.load(open(os.path.join(ROOT, "profiles", "r02_microbench.json")))
+    r = bench.replay_floor(e, 10833, 0.84, mb, 256, 0.753)
+    assert r["chunks"] == 8 and 1e9 < r["cells_per_pair"] < 4e9 and 0.1 < r["floor_over_measured"] < 0.5
+    assert r["throughput_mode"]["cells_per_pair"] < r["cells_per_pair"] and 0 < r["throughput_mode"]["share_of_ms_per_pair"] < 0.5
+    assert "not computed" in bench.replay_floor(e, 10833, 0.84, {}, 256, 0.753)["floor"]
+    t = bench.tensor_fraction(10833, 10797, 0.02834, mb, {"sm_mhz": 1965.0})
+    assert t["mma_macs_issued"] == 10880 * 10880 * 128 and 0.15 < t["frac_of_tensor_peak"] < 0.3
+    assert bench.tensor_fraction(10833, 10797, 0.02834, {}, None)["frac_of_tensor_peak"] is None

@@ -48,11 +48,21 @@ EXPORTED_SYMBOLS = [
     "pano_set_fold_mode", "pano_stitch_pair_async", "pano_pair_query", "pano_pair_wait", "pano_set_profile", "pano_get_profile",
     "pano_default_knn_opts", "pano_match_knn",
     "pano_detect_async", "pano_match_async", "pano_ransac_async", "pano_warp_overlay_async", "pano_stitch_fold_async",
-    "pano_stitch_batch_async", "pano_set_match_mode",
+    "pano_stitch_batch_async", "pano_set_match_mode", "pano_replay_work_estimate",
 ]
 
 
 KNN_PATCH_SSD, KNN_BINARY = 0, 1
+
+
+class ReplayWork(C.Structure):
+    """pano_replay_work (measurement aid: what the chunked shuffle replay plans for one RANSAC run; include/pano_b200.h)"""
+    _fields_ = [("chunk_iterations", C.c_int32), ("chunks", C.c_int32), ("steps", C.c_uint32),
+                ("candidates_per_chunk", C.c_uint32), ("diagonals_per_chunk", C.c_uint32), ("reserved", C.c_uint32),
+                ("rejections_mean", C.c_double), ("rejections_sigma", C.c_double), ("cells", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
 class KnnOptions(C.Structure):
@@ -574,6 +584,14 @@ class Engine:
                 break
             Hs.append(self.mul33(Hs[-1], H))
         return Hs
+
+    def replayWork(self, n_matches, iterations=1000, target_candidates=0.0):
+        """operation count of the chunked shuffle replay for this match count (host-side planning only)"""
+        w = ReplayWork()
+        st = self.lib.pano_replay_work_estimate(int(n_matches), int(iterations), C.c_double(target_candidates), C.byref(w))
+        if st != PANO_OK:
+            raise PanoError(st, "pano_replay_work_estimate")
+        return w.as_dict()
 
     def chainGeometry(self, sizes, Hs):
         """sizes: [(w, h)], Hs: H(0 <- i).  Returns ok, (cw, ch, x0, y0), T"""

@@ -4,6 +4,7 @@
 // interfaces of ref src/gpu/*.cuh.  No CPU fallback anywhere: without an sm_100 device
 // pano_create fails and nothing else can be called.
 #include "common.cuh"
+#include "replay_plan.hpp"
 #include <array>
 
 #include <algorithm>
@@ -1048,6 +1049,30 @@ int pano_pair_homography(pano_ctx* c, const uint8_t* left, int wl, int hl, size_
 }
 
 void pano_mul33(const double A[9], const double B[9], double out[9]) { mul33(A, B, out); }
+
+// measurement aid: the plan ransac.cu makes for this match count (default window scale and width), as numbers
+int pano_replay_work_estimate(int n_matches, int iterations, double target_candidates, pano_replay_work* out) {
+  if (n_matches < 4 || iterations < 1 || !out || target_candidates < 0 || (target_candidates > 0 && target_candidates < 64) ||
+      target_candidates > 51000.0)
+    return PANO_ERR_INVALID;
+  try {
+    const ReplayPlan P = plan_replay((uint32_t)n_matches, iterations, 1, target_candidates > 0 ? target_candidates : 50000.0);
+    const uint32_t steps = shuffle_steps((uint32_t)n_matches);
+    const uint32_t nkb = (steps + 31u) / 32u;
+    memset(out, 0, sizeof *out);
+    out->chunk_iterations = P.G;
+    out->chunks = (iterations + P.G - 1) / P.G;
+    out->steps = steps;
+    out->candidates_per_chunk = P.n_cand;
+    out->diagonals_per_chunk = P.n_diag;
+    out->rejections_mean = P.mu;
+    out->rejections_sigma = P.sigma;
+    out->cells = (double)out->chunks * (double)P.n_diag * (double)nkb * 32.0;
+    return PANO_OK;
+  } catch (const std::exception&) {
+    return PANO_ERR_CUDA;
+  }
+}
 
 int pano_chain_geometry(int n, const int* ws, const int* hs, const double* Hs, pano_canvas_info* out) {
   if (n < 1 || !ws || !hs || !Hs || !out) return PANO_ERR_INVALID;
