@@ -586,13 +586,14 @@ def chain_config_at_n(a, dist, rank, world, cpus, log=lambda m: None, make_cmd=c
         env = {k: v for k, v in os.environ.items() if k not in TORCHRUN_ENV and not k.startswith("TORCHELASTIC")}
         env.update(PANO_CHAIN_NVLINK="0", PANO_BENCH_CHILD="1", NCCL_DEBUG="WARN")
         t0 = time.perf_counter()
-        rc, so, se = run_child_group(make_cmd(world, cpus, free_port()), env, a.extras_timeout)
+        limit = max(a.extras_timeout, 180.0) if a.extras_timeout >= 60.0 else a.extras_timeout   # (N torch imports, NCCL start-up)
+        rc, so, se = run_child_group(make_cmd(world, cpus, free_port()), env, limit)
         lines = [l for l in (so or "").splitlines() if l.startswith("{") and l.rstrip().endswith("}")]
         if rc == 0 and lines:
             out = json.loads(lines[-1])
             out["child_seconds"] = round(time.perf_counter() - t0, 1)
         else:
-            out = {"error": ("child job exit code %s" % rc if rc is not None else "child job killed after %.0f s" % a.extras_timeout)
+            out = {"error": ("child job exit code %s" % rc if rc is not None else "child job killed after %.0f s" % limit)
                    + ": " + (se or "")[-300:]}
     except Exception as e:
         out = {"error": "%s: %s" % (type(e).__name__, e)}
