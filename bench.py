@@ -737,7 +737,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="batch lanes (host threads) per GPU; 0 = from the core count")
     ap.add_argument("--size", default="3840x2160")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE config 1 / 2 child runs (other_configs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the child runs of BASELINE configs 1 / 2 / 4 (other_configs)")
     ap.add_argument("--extras-timeout", type=float, default=120.0, help="seconds per child run of other_configs")
     a = ap.parse_args()
     a.w, a.h = [int(v) for v in a.size.split("x")]
