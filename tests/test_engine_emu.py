@@ -527,3 +527,17 @@ def test_emulated_engine_rejects_bad_arguments_without_touching_memory(engine):
     k = engine.gpuHarrisCornerDetectorDetect(img)
     assert len(k) > 0
 
+
+
+def test_whole_engine_fuzz_tool_short_run():
+    """tools/fuzz_emu_engine.py (random scenes, options, seeds, engine settings and calls through the emulated library,
+    against the composition of the oracle's stage functions): a short run inside the suite; the long runs are logged in
+    profiles/r02_fuzz_emulated_engine_vs_oracle_build_container.jsonl"""
+    import json
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_emu_engine.py"), "--cases", "24", "--seed", "77"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-1500:])
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["ok"] and line["cases"] == 24 and line["pair"] + line["homography_only"] + line["fold"] + line["batch"] > 12
