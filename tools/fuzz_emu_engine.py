@@ -9,7 +9,7 @@ of the CUDA execution model, through the package's Python binding, exactly as a 
 random scene (the kernel fuzz's generator: textured pairs, noise, quantised images with exact SSD ties, flat images,
 sparse blobs, odd and tiny sizes), random detector / matcher / RANSAC options, random seed, random engine settings
 (tensor-core or SIMT matcher, chunked or resident replay, the reference's matcher or the opt-in ratio-test matcher,
-blocking or asynchronous call) and one of: fused pair, homography only, three-image fold (the reference's or the opt-in
+blocking or asynchronous call) and one of: the stage entry points one by one, fused pair, homography only, three-image fold (the reference's or the opt-in
 incremental one is left to its own test), batch of pairs.  Everything the call returns - status, counts, best inlier
 count, H bits, canvas bytes - must equal the composition of the oracle's stage functions (detect, match / match_knn,
 ransac, compose; ref: src/serial/main.cpp:311-414).  One JSON line; exit code 1 on the first difference.
@@ -91,7 +91,7 @@ def main():
         return names.get(code, str(code)).replace("PANO_ERR_", "").replace("PANO_OK", "OK")
 
     rng = np.random.default_rng(a.seed)
-    tot = dict(cases=0, pair=0, homography_only=0, fold=0, batch=0, asynchronous=0, ratio_test_matcher=0, resident_replay=0,
+    tot = dict(cases=0, stage_calls=0, pair=0, homography_only=0, fold=0, batch=0, asynchronous=0, ratio_test_matcher=0, resident_replay=0,
                simt_matcher=0, status_ok=0, no_matches=0, too_few=0, no_homography=0, roi=0, canvas_px=0, ransac_iterations=0)
     t0 = time.time()
 
@@ -133,7 +133,48 @@ def main():
         tot["ransac_iterations"] += ro.numIterations_
         op = rng.random()
         try:
-            if op < 0.7:
+            if op < 0.15:
+                # the stage entry points (ref: src/gpu/*.cuh), blocking or asynchronous form, one by one
+                eng.set_match_mode(0)
+                use_async = bool(rng.random() < 0.5)
+                tot["stage_calls"] += 1
+                tot["asynchronous"] += use_async
+                hk = dict(k=ho.k_, nmsThresh=ho.nmsThresh_, nmsNeighborhood=ho.nmsNeighborhood_)
+                if use_async:
+                    kl = eng.gpuHarrisCornerDetectorDetectAsync(left, **hk).result()
+                    kr = eng.gpuHarrisCornerDetectorDetectAsync(right, **hk).result()
+                else:
+                    kl, kr = eng.gpuHarrisCornerDetectorDetect(left, **hk), eng.gpuHarrisCornerDetectorDetect(right, **hk)
+                okl = oracle.detect(left, k=ho.k_, thresh=ho.nmsThresh_, nbhd=ho.nmsNeighborhood_)
+                okr = oracle.detect(right, k=ho.k_, thresh=ho.nmsThresh_, nbhd=ho.nmsNeighborhood_)
+                if not (np.array_equal(kl, okl) and np.array_equal(kr, okr)):
+                    fail(case, "detect", got=(len(kl), len(kr)), want=(len(okl), len(okr)))
+                off = int(rng.choice([0, 0, 3]))
+                mk = dict(patchSize=ho.patchSize_, maxSSDThresh=ho.maxSSDThresh_, offset=off)
+                m = (eng.gpuHarrisMatchKeyPointsAsync(kr, kl, right, left, **mk).result() if use_async
+                     else eng.gpuHarrisMatchKeyPoints(kr, kl, right, left, **mk))
+                om = np.ascontiguousarray(oracle.match(okr, okl, right, left, patch=ho.patchSize_, max_ssd=ho.maxSSDThresh_, offset=off))
+                if np.ascontiguousarray(m).tobytes() != om.tobytes():
+                    fail(case, "match", got=len(m), want=len(om))
+                if off == 0 and len(om) > 0:
+                    o = oracle.ransac(okr, okl, om, iters=ro.numIterations_, thr=ro.distanceThreshold_, seed=seed)
+                    if use_async:
+                        H, best, _ = eng.computeHomographyAsync(kr, kl, m, options=ro).result()
+                        same = (H is None) == (not o["ok"]) and (H is None or (best == o["best_count"] and np.array_equal(bits(H), bits(o["H"]))))
+                    else:
+                        d = eng.computeHomography(kr, kl, m, options=ro, details=True)
+                        same = d["ok"] == o["ok"] and (len(om) < 4 or (np.array_equal(d["samples"], o["samples"]) and np.array_equal(d["counts"], o["counts"])))
+                        same = same and (not o["ok"] or (np.array_equal(bits(d["H"]), bits(o["H"])) and d["best_count"] == o["best_count"]
+                                                          and np.array_equal(d["inlier_mask"], o["inlier_mask"])))
+                    if not same:
+                        fail(case, "ransac", matches=len(om), oracle_ok=o["ok"])
+                    if o["ok"]:
+                        ok, geom, _ = oracle.canvas_geometry(left.shape[1], left.shape[0], right.shape[1], right.shape[0], o["H"])
+                        if ok and geom[0] * geom[1] <= MAX_CANVAS_PX:
+                            if not np.array_equal(eng.warpOverlay(left, right, o["H"]), oracle.compose(left, right, o["H"])):
+                                fail(case, "warp_overlay")
+                            tot["canvas_px"] += geom[0] * geom[1]
+            elif op < 0.7:
                 st, e = expected(oracle, left, right, ho, ro, seed, knn)
                 big = st == "OK" and e["geom"][0] * e["geom"][1] > MAX_CANVAS_PX
                 if big or rng.random() < 0.15:
