@@ -589,9 +589,11 @@ def chain_config_at_n(a, dist, rank, world, cpus, log=lambda m: None, make_cmd=c
         limit = max(a.extras_timeout, 180.0) if a.extras_timeout >= 60.0 else a.extras_timeout   # (N torch imports, NCCL start-up)
         rc, so, se = run_child_group(make_cmd(world, cpus, free_port()), env, limit)
         lines = [l for l in (so or "").splitlines() if l.startswith("{") and l.rstrip().endswith("}")]
-        if rc == 0 and lines:
+        if lines and (rc == 0 or rc is None):
             out = json.loads(lines[-1])
             out["child_seconds"] = round(time.perf_counter() - t0, 1)
+            if rc is None:      # measured and printed, then stuck on its way out
+                out["note"] = "the child job had printed its line but had not exited after %.0f s and was killed" % limit
         else:
             out = {"error": ("child job exit code %s" % rc if rc is not None else "child job killed after %.0f s" % limit)
                    + ": " + (se or "")[-300:]}

@@ -159,6 +159,8 @@ if rank == 0:
     print(json.dumps({"metric": "stub", "n_gpus": world, "cpus": len(os.sched_getaffinity(0)),
                       "nvlink": os.environ.get("PANO_CHAIN_NVLINK"), "lanes": os.environ.get("PANO_BATCH_LANES"),
                       "pid": os.getpid()}), flush=True)
+if mode == "late":
+    time.sleep(600)
 dist.destroy_process_group()
 '''
 
@@ -186,7 +188,7 @@ def _chain_leg_worker(rank, world, port, out_dir, mode):
         cmd = bench.chain_child_command(w, c, p)
         i = cmd.index(os.path.join(ROOT, "bench.py"))
         return cmd[:i] + [stub, mode]
-    a = types.SimpleNamespace(extras_timeout=60.0 if mode == "ok" else 8.0)
+    a = types.SimpleNamespace(extras_timeout={"ok": 60.0, "hang": 8.0, "late": 30.0}[mode])
     t0 = time.time()
     out = bench.chain_config_at_n(a, dist, rank, world, cpus, make_cmd=make_cmd)
     json.dump({"out": out, "seconds": time.time() - t0, "cpus": len(cpus)}, open(os.path.join(out_dir, "r%d_%s.json" % (rank, mode)), "w"))
@@ -194,10 +196,10 @@ def _chain_leg_worker(rank, world, port, out_dir, mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["ok", "hang"])
+@pytest.mark.parametrize("mode", ["ok", "hang", "late"])
 def test_bench_chain_leg_child_job_and_store_wait(tmp_path, mode):
     import json
-    port = 31000 + os.getpid() % 2000 + (7 if mode == "ok" else 11)
+    port = 31000 + os.getpid() % 2000 + {"ok": 7, "hang": 11, "late": 13}[mode]
     mp.spawn(_chain_leg_worker, args=(2, port, str(tmp_path), mode), nprocs=2, join=True)
     r0, r1 = [json.load(open(tmp_path / ("r%d_%s.json" % (r, mode)))) for r in (0, 1)]
     assert r1["out"] is None                                   # only rank 0 reports
@@ -207,6 +209,9 @@ def test_bench_chain_leg_child_job_and_store_wait(tmp_path, mode):
         assert o["cpus"] == r0["cpus"]                         # the affinity before binding is back in the child job
         assert o["nvlink"] == "0" and o["lanes"] is None       # validated upload variant; the parent's lane count is not inherited
         assert r1["seconds"] >= r0["seconds"] - 2.0            # rank 1 waited for rank 0's child job
+    elif mode == "late":                                       # measured and printed, stuck on its way out: the line is kept
+        assert r0["out"]["metric"] == "stub" and "had not exited after 30 s" in r0["out"]["note"]
+        assert r0["seconds"] < 75 and r1["seconds"] < 75
     else:
         assert "killed after 8 s" in r0["out"]["error"]
         assert r0["seconds"] < 40 and r1["seconds"] < 40       # the stuck job is killed as a group; nobody keeps waiting
