@@ -424,6 +424,8 @@ def run_engine(a):
             "peak_source": how, "kernel_ms": k_ms["warp"], "algorithmic_bytes": alg_warp,
             "how": "CUDA events on the engine's stream right around the launch, inside pano_stitch_pair, mean of %d "
                    "single-pair runs (the RANSAC kernels before it have flushed the sources from L2)" % reps,
+            # the kernel's second ceiling: it is bound by instruction issue, not by bytes
+            "issue": issue_fraction((ncu.get("warp_quad_kernel") or {}).get("warp_instructions"), k_ms["warp"], clocks),
             "other_kernels": {
                 "harris_fused_kernel": {"ms_per_image": k_ms["harris_fused"], "bound": "fp64 pipe",
                                         "fp64_instr": harris_fp64,
@@ -605,6 +607,21 @@ def chain_config_at_n(a, dist, rank, world, cpus, log=lambda m: None, make_cmd=c
         except Exception:
             pass
     return out
+
+
+def issue_fraction(warp_instructions, kernel_ms, clocks):
+    """warp instructions of one launch (from the committed ncu capture of the same kernel on the same input size) against
+    the issue ceiling of the GPU - 148 SMs x 4 schedulers x 1 instruction per clock at the SM clock sampled in this run -
+    over the kernel's event time measured in this run"""
+    try:
+        mhz = float((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz"))
+        floor_ms = float(warp_instructions) / (148 * 4 * mhz * 1e6) * 1e3
+        return {"warp_instructions_ncu": warp_instructions, "issue_floor_ms": floor_ms, "frac_of_issue_peak": floor_ms / kernel_ms,
+                "source": "instruction count: profiles/r02_ncu_metrics.json (ncu capture of this kernel on a 4K pair of the same generator: "
+                          "approximate for this pair's canvas); "
+                          "time and clock: this run"}
+    except Exception as e:
+        return {"frac_of_issue_peak": None, "note": "not computed: %s" % e}
 
 
 def tensor_fraction(nq, nt, kernel_ms, mb, clocks):

@@ -118,3 +118,6 @@ def test_bench_floor_helpers_compute_from_the_plan_and_the_microbenchmarks():
     t = bench.tensor_fraction(10833, 10797, 0.02834, mb, {"sm_mhz": 1965.0})
     assert t["mma_macs_issued"] == 10880 * 10880 * 128 and 0.15 < t["frac_of_tensor_peak"] < 0.3
     assert bench.tensor_fraction(10833, 10797, 0.02834, {}, None)["frac_of_tensor_peak"] is None
+    i = bench.issue_fraction(32311417.0, 0.0487, {"sm_mhz": 1965.0})
+    assert abs(i["issue_floor_ms"] - 0.02778) < 1e-4 and 0.5 < i["frac_of_issue_peak"] < 0.65
+    assert bench.issue_fraction(None, 0.0487, None)["frac_of_issue_peak"] is None
